@@ -1,0 +1,145 @@
+"""
+Lane-level numpy model of the CUDA wavefront DTW kernel
+(whisper-timestamped_b200/csrc/dtw.cu: dtw_fill_strip + the row-wise backtrack).
+
+It mirrors the kernel's data flow step by step — 31-row strips, lane 0 as the row above the
+strip, shfl_up for `up`, last step's `up` as `diag`, the skewed 64-slot shared-memory staging
+with its 16-step software pipeline, 2-bit direction fields packed by step index, boundary row
+hand-over between strips, and the clz-based one-step-per-token backtrack — so that the index
+arithmetic of the kernel can be checked on the CPU (no GPU in the build container) against the
+oracle.  It is a test helper, not product code.
+"""
+import numpy as np
+
+RS = 31
+PITCH = 65
+
+
+def niter_of(F):
+    return (F + RS - 1 + 31) // 32
+
+
+def model_dtw(cost):
+    """cost: [T, F] float32/float64.  Returns jumps (T+1 int32) exactly as the kernel computes."""
+    cost = np.asarray(cost)
+    T, F = cost.shape
+    lanes = np.arange(32)
+    niter = niter_of(F)
+    W = 2 * niter
+    nstrips = (T + RS - 1) // RS
+    dirs = np.zeros((nstrips, W, 32), dtype=np.uint32)
+    bnd = np.full(F + 4, np.nan)
+    tile = np.zeros((32, PITCH), dtype=cost.dtype)
+    INF = np.inf
+    flat = cost.reshape(-1)
+
+    for strip in range(nstrips):
+        row0 = strip * RS
+        Ts = min(RS, T - row0)
+        first = strip == 0
+        write_bnd = strip + 1 < nstrips
+        cur = np.full(32, INF)
+        upprev = np.full(32, INF)
+        if first:
+            upprev[1] = 0.0
+        else:
+            cur[0] = bnd[0]
+        acc = np.zeros(32, dtype=np.uint32)
+        a = np.zeros((16, 32), dtype=cost.dtype)
+        b = np.zeros((16, 32), dtype=cost.dtype)
+        base = row0 * F
+
+        # prologue
+        off = np.minimum(lanes, F - 1).astype(np.int64)
+        for k in range(16):
+            v = flat[base + off]
+            tile[k, (lanes + k - 1) & 63] = v
+            if 1 <= k < Ts:
+                off = off + F
+        for k in range(16, 32):
+            b[k - 16] = flat[base + off]
+            if k < Ts:
+                off = off + F
+        bndnext = np.full(32, INF)
+        if not first:
+            idx = 1 + lanes
+            bndnext = np.where(idx < F, bnd[np.minimum(idx, F - 1)], INF)
+
+        for t in range(niter):
+            if not first:
+                bndreg = bndnext
+                idx = 32 * (t + 1) + 1 + lanes
+                bndnext = np.where(idx < F, bnd[np.minimum(idx, F + 3)], INF)
+            off = np.minimum(32 * (t + 1) + lanes, F - 1).astype(np.int64)
+            cb = (t & 1) * 32
+            nb = 32 - cb
+            for k in range(32):
+                if k < 16:
+                    tile[16 + k, (cb + 63 + lanes + 16 + k) & 63] = b[k]
+                    a[k] = flat[base + off]
+                else:
+                    tile[k - 16, (nb + 63 + lanes + k - 16) & 63] = a[k - 16]
+                    b[k - 16] = flat[base + off]
+                if 1 <= k < Ts:
+                    off = off + F
+                s = 32 * t + k
+                l = tile[lanes, cb + k].astype(np.float64)
+                # staging check: every active cell must see its own cost value
+                for L in range(1, Ts + 1):
+                    j = s + 1 - L
+                    if 0 <= j < F:
+                        assert l[L] == np.float64(cost[row0 + L - 1, j]), (strip, t, k, L, j)
+                up = np.empty(32)
+                up[1:] = cur[:-1]
+                up[0] = cur[0]
+                diag = upprev.copy()
+                upprev = up.copy()
+                c1, c2, c3 = diag + l, cur + l, up + l
+                p2 = c2 < c1
+                m = np.where(p2, c2, c1)
+                p3 = c3 < m
+                best = np.where(p3, c3, m)
+                cur = best.copy()
+                if (k & 15) == 0:
+                    acc[:] = 0
+                acc |= (p2.astype(np.uint32) << np.uint32(2 * (k & 15)))
+                acc |= (p3.astype(np.uint32) << np.uint32(2 * (k & 15) + 1))
+                if (k & 15) == 15:
+                    dirs[strip, 2 * t + (k >> 4), :] = acc
+                if write_bnd:
+                    j = s - (Ts - 1)
+                    if 0 <= j < F:
+                        bnd[j] = best[Ts]
+                if not first:
+                    cur[0] = bndreg[k]
+
+    def clz(x):
+        return 32 - int(x).bit_length()
+
+    jumps = np.zeros(T + 1, dtype=np.int32)
+    jumps[T] = F - 1
+    i, j = T - 1, F - 1
+    while i > 0:
+        strip, ln = i // RS, i % RS + 1
+        s = j + ln - 1
+        w, pos = s >> 4, s & 15
+        while True:
+            x = int(dirs[strip, w, ln])
+            lo, hi = x & 0x55555555, (x >> 1) & 0x55555555
+            nl = 0x55555555 & ~(lo & ~hi)
+            m = nl & (0xFFFFFFFF >> (30 - 2 * pos))
+            if m:
+                kf = (31 - clz(m)) >> 1
+                break
+            if w == 0:
+                kf = 0
+                break
+            w -= 1
+            pos = 15
+        jj = max(w * 16 + kf - (ln - 1), 0)
+        is_up = (x >> (2 * kf + 1)) & 1
+        jumps[i] = jj
+        j = jj - 1 if (not is_up and jj > 0) else jj
+        i -= 1
+    jumps[0] = 0
+    return jumps

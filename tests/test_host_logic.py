@@ -1,0 +1,89 @@
+"""CPU-side checks of product pieces that do not need a GPU: the median-of-9 selection network and
+scipy-'reflect' index map shared with the CUDA prep kernel (csrc/median9.h, built here with gcc),
+the C-ABI export list, and the descriptor planner."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+from scipy.ndimage import median_filter
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "whisper-timestamped_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def medlib(tmp_path_factory):
+    d = tmp_path_factory.mktemp("med")
+    src = d / "med.c"
+    src.write_text(f'''
+#include "{CSRC}/median9.h"
+void median_rows(const float* x, int rows, int n, float* out) {{
+    for (int r = 0; r < rows; ++r) for (int c = 0; c < n; ++c) {{
+        float p[9];
+        for (int k = 0; k < 9; ++k) p[k] = x[r * n + wts_reflect_index(c - 4 + k, n)];
+        out[r * n + c] = wts_median9(p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8]);
+    }}
+}}
+int reflect_index(int p, int n) {{ return wts_reflect_index(p, n); }}
+''')
+    so = d / "med.so"
+    subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", str(so), str(src), "-lm"])
+    return ctypes.CDLL(str(so))
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 8, 9, 10, 17, 150, 1500])
+def test_median9_matches_scipy(medlib, n):
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal((7, n)).astype(np.float32)
+    x[0, : min(n, 5)] = 1.0                      # ties
+    out = np.empty_like(x)
+    medlib.median_rows(x.ctypes.data_as(ctypes.c_void_p), 7, n, out.ctypes.data_as(ctypes.c_void_p))
+    ref = median_filter(x, (1, 9))               # same call as transcribe.py:1546 (mode='reflect')
+    assert np.array_equal(out, ref)
+
+
+def test_reflect_index_is_numpy_symmetric(medlib):
+    for n in (1, 2, 3, 5, 9, 40):
+        padded = np.pad(np.arange(n), (4, 4), mode="symmetric")
+        got = [medlib.reflect_index(p, n) for p in range(-4, n + 4)]
+        assert got == padded.tolist()
+
+
+def test_abi_exports_every_declared_symbol():
+    """libwts.so loads on a CPU-only box and exports what include/wts.h declares."""
+    from whisper_timestamped import _native as nat
+    header = open(os.path.join(ROOT, "include", "wts.h")).read()
+    declared = set(re.findall(r"\b(wts_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    for name in declared:
+        assert hasattr(nat.lib, name), f"{name} declared in include/wts.h but not exported"
+    assert set(nat.EXPORTED_SYMBOLS) <= declared
+    assert nat.lib.wts_version() >= 100
+
+
+def test_plan_segments_layout():
+    from whisper_timestamped import _native as nat
+    from whisper_timestamped.alignment import plan_segments
+    plan = plan_segments([(0, 0, None, 24, 10, 300, 0), (1, 5, 40, 33, 0, 90, 50), (0, 30, None, 2, 0, 9, 0)])
+    s = plan.segs
+    assert s["last_row"].tolist() == [23, 40, 31]
+    assert s["cost_off"].tolist() == [0, 7200, 7200 + 2972]          # 33*90=2970 -> padded to 4
+    assert s["jumps_off"].tolist() == [0, 25, 59]
+    assert plan.jumps_elems == 62 and plan.max_T == 33 and plan.max_F == 300
+    assert s["dir_off"][1] == nat.lib.wts_dtw_dir_words(24, 300)
+    assert nat.lib.wts_dtw_bnd_doubles(24, 300) == 0 and nat.lib.wts_dtw_bnd_doubles(33, 90) == 92
+    assert plan.dtw_order.tolist() == [0, 1, 2]
+    with pytest.raises(ValueError):
+        plan_segments([(0, 0, None, 0, 0, 5, 0)])
+
+
+def test_no_cpu_fallback():
+    import torch
+    from whisper_timestamped import _native as nat
+    from whisper_timestamped.alignment import plan_segments, attn_prep
+    plan = plan_segments([(0, 0, None, 3, 0, 9, 0)])
+    with pytest.raises(nat.WtsError):
+        attn_prep(torch.zeros(1, 2, 4, 16), plan)

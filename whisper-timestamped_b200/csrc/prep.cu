@@ -1,0 +1,139 @@
+// Fused attention post-processing for word alignment (sm_100a).
+//
+// Replaces, for a whole batch of segments at once, the per-segment CPU sequence of
+// /root/reference/whisper_timestamped/transcribe.py:
+//   1540  weights[..., start_token:end_token]                (frame slice)
+//   1545  stack of the alignment heads                       (already only those N heads in d_qk)
+//   1546  scipy.ndimage.median_filter(weights, (1,1,9))      (mode='reflect')
+//   1547  softmax over frames
+//   1548  mean over heads
+//   1549  divide by the L2 norm over the token axis
+//   1550  negate (-> float64 in the reference; the values are float32-exact, kept as float32)
+//   1561-1565 padding mask, 1568 weights[0,0] = weights.min()
+//
+// Kernel A (rows): one warp per (segment, token) row; for each head: coalesced load of the F-frame
+// slice into shared memory, median-of-9 selection network, numerically stable softmax, accumulate
+// the head mean in shared memory; the N*T*F*4 input bytes are read exactly once.
+// Kernel B (cols): one CTA per segment; per frame column: L2 norm over tokens, divide, negate,
+// padding mask, running minimum; finally cost[0,0] = min.  Reads the [T,F] mean twice (L2-hot).
+#include "common.cuh"
+#include "median9.h"
+
+namespace wts {
+
+constexpr int PREP_WARPS = 4;
+
+__global__ void __launch_bounds__(PREP_WARPS * 32)
+prep_rows_kernel(const float* __restrict__ qk, const int N, const int Tmax, const int Fmax,
+                 const WtsSegDesc* __restrict__ segs, const int max_F, float* __restrict__ cost)
+{
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const WtsSegDesc sd = segs[blockIdx.x];
+    const int t = blockIdx.y * PREP_WARPS + warp;
+    if (t >= sd.T) return;
+    const int F = sd.F;
+    float* xbuf = smem + (size_t)warp * 3 * max_F;   // raw slice of one head
+    float* mbuf = xbuf + max_F;                      // median-filtered -> exp
+    float* acc = mbuf + max_F;                       // sum over heads of the softmax rows
+
+    const int row = (t == sd.T - 1) ? sd.last_row : sd.row0 + t;
+    const float* src0 = qk + (((int64_t)sd.window * N) * Tmax + row) * (int64_t)Fmax + sd.f0;
+    const int64_t head_stride = (int64_t)Tmax * Fmax;
+
+    for (int n = 0; n < N; ++n) {
+        const float* src = src0 + n * head_stride;
+        for (int c = lane; c < F; c += 32) xbuf[c] = __ldg(src + c);
+        __syncwarp();
+        float mx = -INFINITY;
+        for (int c = lane; c < F; c += 32) {
+            float m;
+            if (c >= 4 && c + 4 < F) {
+                m = wts_median9(xbuf[c - 4], xbuf[c - 3], xbuf[c - 2], xbuf[c - 1], xbuf[c],
+                                xbuf[c + 1], xbuf[c + 2], xbuf[c + 3], xbuf[c + 4]);
+            } else {
+                float p[9];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) p[k] = xbuf[wts_reflect_index(c - 4 + k, F)];
+                m = wts_median9(p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8]);
+            }
+            mbuf[c] = m;
+            mx = fmaxf(mx, m);
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int c = lane; c < F; c += 32) {
+            const float e = expf(mbuf[c] - mx);
+            mbuf[c] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        for (int c = lane; c < F; c += 32) {
+            const float p = mbuf[c] / sum;
+            acc[c] = (n == 0) ? p : acc[c] + p;
+        }
+        __syncwarp();
+    }
+    float* dst = cost + sd.cost_off + (int64_t)t * F;
+    const float fn = (float)N;
+    for (int c = lane; c < F; c += 32) dst[c] = acc[c] / fn;
+}
+
+__global__ void __launch_bounds__(256)
+prep_cols_kernel(const WtsSegDesc* __restrict__ segs, float* __restrict__ cost)
+{
+    __shared__ float red[8];
+    const WtsSegDesc sd = segs[blockIdx.x];
+    const int T = sd.T, F = sd.F;
+    float* M = cost + sd.cost_off;
+    const bool masked = sd.max_dur > 0 && sd.f0 < sd.max_dur;
+    float vmin = INFINITY;
+    for (int c = threadIdx.x; c < F; c += blockDim.x) {
+        float ss = 0.f;
+        for (int t = 0; t < T; ++t) {
+            const float v = M[(int64_t)t * F + c];
+            ss += v * v;
+        }
+        const float nrm = sqrtf(ss);
+        for (int t = 0; t < T; ++t) {
+            float v = -(M[(int64_t)t * F + c] / nrm);
+            if (masked && t < T - 1 && c >= sd.max_dur) v = 0.f;
+            M[(int64_t)t * F + c] = v;
+            vmin = fminf(vmin, v);
+        }
+    }
+    vmin = warp_min(vmin);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = vmin;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = red[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fminf(m, red[w]);
+        M[0] = m;
+    }
+}
+
+}  // namespace wts
+
+using namespace wts;
+
+extern "C" int wts_attn_prep_batch(const float* d_qk, int32_t N, int32_t Tmax, int32_t Fmax,
+                                   const WtsSegDesc* d_segs, int32_t nseg, int32_t max_T,
+                                   int32_t max_F, float* d_cost, void* stream)
+{
+    if (nseg <= 0) return 0;
+    if (!d_qk || !d_segs || !d_cost) { set_error("wts_attn_prep_batch: null pointer"); return -2; }
+    if (N <= 0 || max_T <= 0 || max_F <= 0 || max_F > Fmax) {
+        set_error("wts_attn_prep_batch: bad geometry N=%d max_T=%d max_F=%d Fmax=%d", N, max_T, max_F, Fmax);
+        return -2;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = (size_t)PREP_WARPS * 3 * max_F * sizeof(float);
+    if (smem > 48 * 1024)
+        WTS_CUDA_CHECK(cudaFuncSetAttribute(prep_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(nseg, (max_T + PREP_WARPS - 1) / PREP_WARPS);
+    prep_rows_kernel<<<grid, PREP_WARPS * 32, smem, st>>>(d_qk, N, Tmax, Fmax, d_segs, max_F, d_cost);
+    WTS_LAUNCH_CHECK();
+    prep_cols_kernel<<<nseg, 256, 0, st>>>(d_segs, d_cost);
+    WTS_LAUNCH_CHECK();
+    return 0;
+}

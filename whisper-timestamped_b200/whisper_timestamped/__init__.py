@@ -1,0 +1,10 @@
+"""B200-native drop-in for the hot path of whisper-timestamped.
+
+Same import name and API surface as the reference package
+(/root/reference/whisper_timestamped/__init__.py:1-10): `transcribe`, `transcribe_timestamped`,
+`load_model`, `__version__`.  All device work goes through libwts.so (hand-written sm_100a CUDA
+behind the C-ABI of include/wts.h); importing this package fails if that library is missing.
+"""
+from . import _native  # noqa: F401  (fails loudly when libwts.so is absent)
+
+__version__ = "1.15.9+b200.r1"
