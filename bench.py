@@ -91,6 +91,7 @@ class ClockSampler:
 def make_align_batch(nseg, T, F, N, seed, device, rows_per_window=216):
     """Synthetic alignment problems per SURVEY.md §8(d): qk ~ 3*N(0,1) + 6*exp(-((f - F*t/T)/8)^2)."""
     import torch
+    rows_per_window = max(rows_per_window, T)
     per_win = rows_per_window // T
     nwin = (nseg + per_win - 1) // per_win
     g = torch.Generator(device=device)
@@ -98,7 +99,7 @@ def make_align_batch(nseg, T, F, N, seed, device, rows_per_window=216):
     qk = torch.empty((nwin, N, rows_per_window, 1500), dtype=torch.float32, device=device)
     qk.normal_(0.0, 3.0, generator=g)
     items = []
-    f0 = 100
+    f0 = min(100, 1500 - F)
     tt = torch.arange(T, device=device, dtype=torch.float32)[:, None]
     ff = torch.arange(F, device=device, dtype=torch.float32)[None, :]
     ridge = 6.0 * torch.exp(-((ff - F * (tt + 0.5) / T) / 8.0) ** 2)

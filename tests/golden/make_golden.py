@@ -58,7 +58,7 @@ def main():
     rng = np.random.default_rng(4321)
     pout = {}
     specs = [(10, 12, 150, 40, 0), (8, 24, 300, 0, 0), (6, 5, 7, 3, 0), (10, 3, 3, 0, 0),
-             (8, 20, 120, 1400, 1450), (10, 40, 90, 100, 150), (10, 2, 9, 0, 0),
+             (8, 20, 120, 1300, 1350), (10, 40, 90, 100, 150), (10, 2, 9, 0, 0),
              (8, 20, 120, 10, 60), (6, 9, 200, 0, 1), (10, 12, 80, 70, 70)]
     for n, (N, T, F, f0, max_dur) in enumerate(specs):
         qk = (3.0 * rng.standard_normal((N, T, 1500))).astype(np.float32)
