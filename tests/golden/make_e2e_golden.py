@@ -1,0 +1,103 @@
+"""Generates tests/golden/e2e_*.json by running the UNMODIFIED reference
+(/root/reference/whisper_timestamped) on CPU over the oracle's stand-ins for its two missing
+third-party dependencies (oracle/upstream/{whisper,dtw}).  Runs only in the build container
+(the reference does not exist on the GPU box); the JSON fixtures are committed.
+
+    python tests/golden/make_e2e_golden.py [case ...]
+
+Inputs are fully synthetic and reproducible from the recipe stored in each fixture:
+model = synthetic_state_dict(DIMS[name], seed), audio = synthetic_speech(duration, audio_seed).
+"""
+import importlib.util
+import json
+import os
+import sys
+import time
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle", "upstream"))
+sys.path.insert(0, "/root/reference")
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import whisper  # noqa: E402  (oracle stand-in)
+import whisper_timestamped as ref  # noqa: E402  (the real reference)
+
+assert ref.__file__.startswith("/root/reference"), ref.__file__
+
+
+def _load(path, name):
+    spec = importlib.util.spec_from_file_location(name, path)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+PKG = os.path.join(ROOT, "whisper-timestamped_b200", "whisper_timestamped")
+zoo = _load(os.path.join(PKG, "model_zoo.py"), "wts_model_zoo")
+sa = _load(os.path.join(PKG, "synthetic_audio.py"), "wts_synthetic_audio")
+
+CASES = {
+    # name: (model, model kwargs, audio (duration, seed), transcribe kwargs)
+    "tiny_en_30s": ("tiny.en", {}, (30.0, 7), {}),
+    "tiny_75s_cond": ("tiny", {}, (75.0, 11), {"language": "en"}),
+    "tiny_60s_nocond": ("tiny", {}, (60.0, 12), {"language": "en", "condition_on_previous_text": False}),
+    "tiny_detect_lang": ("tiny", {}, (35.0, 13), {}),
+    "tiny_stuck": ("tiny", {"eot_logit": 4.0, "ts_offset": 0.5}, (45.0, 14), {"language": "en"}),
+    "tiny_opts": ("tiny", {}, (50.0, 15), {"language": "fr", "remove_punctuation_from_words": True,
+                                            "include_punctuation_in_confidence": True,
+                                            "refine_whisper_precision": 0.2, "min_word_duration": 0.1}),
+    "tiny_norefine": ("tiny", {}, (40.0, 16), {"language": "en", "refine_whisper_precision": 0.0}),
+    "tiny_short": ("tiny", {}, (3.3, 17), {"language": "en"}),
+    "tiny_ja_unspaced": ("tiny", {}, (40.0, 18), {"language": "ja"}),
+}
+
+
+def build_model(name, seed=1234, **kw):
+    dims = zoo.DIMS[name]
+    sd = zoo.synthetic_state_dict(dims, seed=seed, **kw)
+    model = whisper.Whisper(whisper.ModelDimensions(**dims.asdict()))
+    model.load_state_dict(sd)
+    mask = torch.zeros(dims.n_text_layer, dims.n_text_head, dtype=torch.bool)
+    for l, h in zoo.ALIGNMENT_HEADS[name]:
+        mask[l, h] = True
+    model.register_buffer("alignment_heads", mask.to_sparse(), persistent=False)
+    return model.eval()
+
+
+def to_py(o):
+    if isinstance(o, dict):
+        return {k: to_py(v) for k, v in o.items()}
+    if isinstance(o, (list, tuple)):
+        return [to_py(v) for v in o]
+    if isinstance(o, (np.floating,)):
+        return float(o)
+    if isinstance(o, (np.integer,)):
+        return int(o)
+    return o
+
+
+def main():
+    names = sys.argv[1:] or list(CASES)
+    for case in names:
+        mname, mkw, (dur, aseed), tkw = CASES[case]
+        model = build_model(mname, **mkw)
+        audio = sa.synthetic_speech(dur, seed=aseed)
+        t0 = time.time()
+        res = ref.transcribe(model, audio, **tkw)
+        dt = time.time() - t0
+        out = {"case": case, "model": mname, "model_seed": 1234, "model_kwargs": mkw, "audio": [dur, aseed],
+               "transcribe_kwargs": tkw, "reference_version": ref.__version__, "cpu_seconds": round(dt, 2),
+               "result": to_py(res)}
+        with open(os.path.join(HERE, f"e2e_{case}.json"), "w") as f:
+            json.dump(out, f, indent=1, ensure_ascii=False)
+        nseg = len(res["segments"])
+        nw = sum(len(s.get("words", [])) for s in res["segments"])
+        ntok = sum(len(s["tokens"]) for s in res["segments"])
+        print(f"{case}: {nseg} segments, {nw} words, {ntok} tokens, {dt:.1f}s")
+
+
+if __name__ == "__main__":
+    main()
