@@ -1,0 +1,64 @@
+"""Product HOST logic (windows.py / words.py / transcribe.py) vs the golden outputs of the
+UNMODIFIED reference (tests/golden/e2e_*.json, produced by tests/golden/make_e2e_golden.py).
+The device work is done by the test-only OracleEngine (CPU stand-ins), so this runs without a GPU
+and checks that the offline replay of the reference's hook state machine gives the same tokens,
+segments, words, timestamps and confidences."""
+import glob
+import json
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+from whisper_timestamped import model_zoo as zoo
+from whisper_timestamped.synthetic_audio import synthetic_speech
+from whisper_timestamped.transcribe import transcribe_timestamped
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CASES = sorted(glob.glob(os.path.join(HERE, "golden", "e2e_*.json")))
+
+
+def run_case(path, **extra):
+    from oracle_engine import OracleEngine, build_oracle_model
+    g = json.load(open(path))
+    dims = zoo.DIMS[g["model"]]
+    sd = zoo.synthetic_state_dict(dims, seed=g["model_seed"], **g["model_kwargs"])
+    heads = zoo.ALIGNMENT_HEADS[g["model"]]
+    om = build_oracle_model(dims, sd, heads)
+    eng = OracleEngine(om, heads)
+    shim = SimpleNamespace(dims=dims, is_multilingual=om.is_multilingual, num_languages=om.num_languages)
+    audio = synthetic_speech(*g["audio"])
+    res = transcribe_timestamped(shim, audio, engine=eng, **g["transcribe_kwargs"], **extra)
+    return g, res
+
+
+def compare(res, ref, conf_tol=0.0015, time_tol=0.0):
+    assert res["language"] == ref["language"]
+    assert res["text"] == ref["text"]
+    assert len(res["segments"]) == len(ref["segments"])
+    for a, b in zip(res["segments"], ref["segments"]):
+        assert a["tokens"] == b["tokens"], (a["id"], a["tokens"], b["tokens"])
+        assert a["text"] == b["text"] and a["seek"] == b["seek"] and a["id"] == b["id"]
+        for k in ("start", "end"):
+            assert abs(a[k] - b[k]) <= time_tol + 1e-9, (a["id"], k, a[k], b[k])
+        for k in ("avg_logprob", "no_speech_prob", "compression_ratio", "temperature"):
+            assert abs(a[k] - b[k]) <= 1e-4 * max(1.0, abs(b[k])), (a["id"], k, a[k], b[k])
+        assert ("confidence" in a) == ("confidence" in b)
+        if "confidence" in b:
+            assert abs(a["confidence"] - b["confidence"]) <= conf_tol
+        wa, wb = a.get("words", []), b.get("words", [])
+        assert [w["text"] for w in wa] == [w["text"] for w in wb], a["id"]
+        for x, y in zip(wa, wb):
+            assert abs(x["start"] - y["start"]) <= time_tol + 1e-9 and abs(x["end"] - y["end"]) <= time_tol + 1e-9, \
+                (a["id"], x, y)
+            assert abs(x["confidence"] - y["confidence"]) <= conf_tol, (a["id"], x, y)
+    if "language_probs" in ref:
+        for k, v in ref["language_probs"].items():
+            assert abs(res["language_probs"][k] - v) < 1e-5
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[4:-5] for p in CASES])
+def test_host_logic_matches_reference_golden(path):
+    g, res = run_case(path)
+    compare(res, g["result"])
