@@ -87,6 +87,119 @@ int wts_dtw_batch(const void* d_cost, int32_t cost_is_f64,
                   int32_t* d_jumps, int32_t* d_path, const int64_t* d_path_off,
                   int32_t* d_path_len, int32_t* d_status, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Model forward operators (replace the openai-whisper modules the reference drives through
+ * model.transcribe / model(mfcc, tokens), T.py:904, 1244, and hooks into at T.py:887-900).
+ *
+ * "split-bf16" (SB16) is the GEMM operand format of this library: a float32 value x is carried as
+ * two bfloat16 planes hi = bf16(x), lo = bf16(x - hi) (16 mantissa bits).  Tensor-core GEMMs form
+ * hi*hi + lo*hi + hi*lo in float32 (error-compensated, ~1e-5 relative) so that logits and
+ * cross-attention scores stay within the 1e-3 bar against the reference's float32 CPU path.
+ * ------------------------------------------------------------------------------------------------ */
+
+typedef struct WtsGemm {
+    /* C[z][m][n] = act(alpha * sum_k A[z][m][k] * B[z][n][k] + bias) + residual   (z = zo*batch_inner + zi) */
+    const void* a;  int64_t lda, a_plane, a_bo, a_bi;   /* SB16 [M,K]: row stride, hi->lo plane stride, batch strides (elements) */
+    const void* b;  int64_t ldb, b_plane, b_bo, b_bi;   /* SB16 [N,K] */
+    int32_t M, N, K, batch_outer, batch_inner;
+    float alpha;
+    const float* bias;        /* [N] (bias_on_m == 0) or [M] (bias_on_m == 1), may be NULL */
+    int32_t bias_on_m;
+    int32_t act;              /* 0 = none, 1 = exact (erf) GELU */
+    const float* residual; int64_t ldr, r_bo, r_bi;     /* float32, may be NULL, may alias out_f32 */
+    float* out_f32;   int64_t ldc, c_bo, c_bi;          /* float32 output (may be NULL) */
+    void*  out_sb16;  int64_t ldo, o_plane, o_bo, o_bi; /* SB16 output (may be NULL) */
+    int32_t head_dim; int64_t head_stride;   /* if head_dim > 0 output column n goes to
+                                                (n / head_dim) * head_stride + m * ld + (n % head_dim) */
+    int32_t backend;          /* 0 = tcgen05 tensor cores, 1 = SIMT float32 validator */
+    int32_t a_is_f32, b_is_f32;   /* SIMT backend only: operand is plain float32 (log-mel DFT / filterbank GEMMs) */
+} WtsGemm;
+
+/* Error-compensated GEMM.  Replaces every torch Linear / Conv1d / matmul of the encoder and decoder. */
+int wts_gemm(const WtsGemm* g, void* stream);
+
+/* float32 -> SB16 planes (used for weights at load time and for mel / embeddings). */
+int wts_to_sb16(const float* d_x, int64_t n, void* d_hi, void* d_lo, void* stream);
+
+/* LayerNorm over the last dim (eps 1e-5, float32 statistics): rows [M, D] float32 -> SB16 and/or f32. */
+int wts_layernorm(const float* d_x, int64_t ldx, const float* d_gamma, const float* d_beta, int32_t M,
+                  int32_t D, void* d_out_sb16, int64_t ldo, int64_t o_plane, float* d_out_f32, int64_t ldf,
+                  void* stream);
+
+/* Row softmax over float32 scores [rows, n] (ld) -> SB16 probabilities (encoder self-attention). */
+int wts_softmax_rows(const float* d_s, int64_t lds, int64_t rows, int32_t n, void* d_out_sb16, int64_t ldo,
+                     int64_t o_plane, void* stream);
+
+/* Log-mel front end — replaces whisper.log_mel_spectrogram (T.py:1213; upstream transcribe()).
+ * wts_frames:  audio [n] -> Hann-windowed, reflect-padded frames float32 [n_frames, 400] (hop 160).
+ * (DFT as a float32 GEMM against the [2*208, 400] cos|-sin basis, wts_gemm with a_is_f32/b_is_f32.)
+ * wts_power:   DFT GEMM output [n_frames, 2*208] (re | im) -> power float32 [n_frames, 208].
+ * (mel filterbank as a float32 GEMM.)
+ * wts_logmel_max / wts_logmel_finish: mel energies [n_frames, n_mels] -> log10(clamp 1e-10), floor at
+ *              (global max - 8), (x+4)/4; time-major float32 [n_frames, n_mels].  d_max holds an order-
+ *              preserving int key and must be initialised to INT32_MIN by the caller. */
+int wts_frames(const float* d_audio, int64_t n_samples, int64_t n_total, int64_t n_frames, void* d_out,
+               int64_t o_plane, void* stream);
+int wts_power(const float* d_y, int64_t ldy, int64_t n_frames, void* d_out, int64_t ldo, int64_t o_plane,
+              void* stream);
+int wts_logmel_max(const float* d_m, int64_t n, float* d_max, void* stream);
+int wts_logmel_finish(const float* d_m, int64_t n_frames, int32_t n_mels, const float* d_max, float* d_out_f32,
+                      void* stream);
+
+/* Gathers 30-s windows of the log-mel (zero padded past `segment_size`, like pad_or_trim) into the padded
+ * conv1 input [B, 3002, n_mels] SB16.  d_mel_ptr[b]: device address of window b's time-major float32 log-mel
+ * [frames, n_mels]; d_seek[b] / d_size[b]: first frame and number of content frames of the window. */
+int wts_window_gather(const int64_t* d_mel_ptr, int32_t n_mels, const int32_t* d_seek, const int32_t* d_size,
+                      int32_t B, void* d_out, int64_t o_plane, void* stream);
+
+/* Decoder token embedding + learned positions for a ragged token batch: row r <- emb[token[r]] + pos[position[r]]. */
+int wts_embed(const int32_t* d_tokens, const int32_t* d_positions, const float* d_emb, const float* d_pos,
+              int32_t rows, int32_t D, float* d_out, void* stream);
+
+/* out[r] = x[idx[r]] (float32 rows). */
+int wts_gather_rows(const float* d_x, int64_t ldx, const int32_t* d_idx, int32_t rows, int32_t D, float* d_out,
+                    void* stream);
+
+/* Decoder attention for a ragged token batch (one query row per (sequence, position)).
+ * kind 0: causal self-attention over the sequence's KV cache (keys 0..position);
+ * kind 1: cross-attention over the 1500 encoder positions; when d_qk_out != NULL the PRE-softmax
+ *         scores of head `h` are written to d_qk_out[(seq*N + slot)*qk_rows + qk_row[r]] for every head
+ *         whose d_head_slot[h] >= 0 (= the alignment heads; replaces hook_attention_weights T.py:783-793).
+ * q: float32 [rows, D] (ldq); K/V caches float32 head-major [seq][H][ctx][64]. */
+int wts_decoder_attention(int32_t kind, const float* d_q, int64_t ldq, const float* d_k, const float* d_v,
+                          int64_t seq_stride, int32_t ctx, const int32_t* d_row_seq, const int32_t* d_row_pos,
+                          int32_t rows, int32_t H, void* d_out_sb16, int64_t ldo, int64_t o_plane,
+                          float* d_qk_out, const int32_t* d_head_slot, int32_t n_slots, int32_t qk_rows,
+                          const int32_t* d_qk_row, void* stream);
+
+/* Scatter new self-attention K/V rows (float32 [rows, D]) into the head-major caches at (seq, position). */
+int wts_kv_append(const float* d_k, const float* d_v, int64_t ld, const int32_t* d_row_seq,
+                  const int32_t* d_row_pos, int32_t rows, int32_t H, int32_t ctx, float* d_kc, float* d_vc,
+                  int64_t seq_stride, void* stream);
+
+/* Logit filters + greedy choice for one decode step — replaces SuppressBlank / SuppressTokens /
+ * ApplyTimestampRules / GreedyDecoder.update (upstream whisper.decoding; rebuilt by the reference at
+ * T.py:1371-1393 and re-applied in hook_output_logits T.py:871-875).  One CTA per sequence. */
+typedef struct WtsDecodeCfg {
+    int32_t n_vocab, eot, timestamp_begin, no_timestamps, max_initial_ts;   /* max_initial_ts < 0: none */
+    int32_t sample_len, n_ctx, tokens_ld;
+} WtsDecodeCfg;
+int wts_decode_select(float* d_logits, int64_t ldl, const WtsDecodeCfg* cfg, const uint8_t* d_suppress,
+                      const uint8_t* d_blank, int32_t* d_tokens, int32_t* d_n_tokens, const int32_t* d_n_prompt,
+                      int32_t* d_done, float* d_logprobs, int32_t lp_ld, float* d_full_logprobs,
+                      int32_t B, void* stream);
+
+/* Per-step decoder inputs from the token buffers: tok[b] = last token, pos[b] = its position,
+ * qk_row[b] = number of tokens sampled so far (row that the step predicts), or -1 when the sequence is done. */
+int wts_step_inputs(const int32_t* d_tokens, int32_t tokens_ld, const int32_t* d_n_tokens, const int32_t* d_n_prompt,
+                    const int32_t* d_done, int32_t B, int32_t* d_tok, int32_t* d_pos, int32_t* d_qk_row,
+                    void* stream);
+
+/* probability of <|nospeech|> at the <|startoftranscript|> position (T.py:856-859). */
+int wts_softmax_pick(const float* d_logits, int64_t ldl, int32_t n, int32_t index, float* d_out, int32_t rows,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

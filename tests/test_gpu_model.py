@@ -1,0 +1,154 @@
+"""GPU parity of the model path (log-mel, encoder, batched greedy decoder, cross-attention capture)
+and of the whole transcribe() against (a) the oracle CPU stand-in run on the same inputs and
+(b) the committed golden outputs of the unmodified reference.  Tolerance for floating point values:
+1e-3 absolute (BASELINE.json north_star); token sequences must be identical."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+TOL = 1e-3
+BACKENDS = [int(x) for x in os.environ.get("WTS_TEST_BACKENDS", "1,0").split(",")]
+
+
+def _models(name="tiny", **kw):
+    import whisper_timestamped as wt
+    from whisper_timestamped import model_zoo as zoo
+    from oracle_engine import OracleEngine, build_oracle_model
+    dims = zoo.DIMS[name]
+    sd = zoo.synthetic_state_dict(dims, seed=1234, **kw)
+    heads = zoo.ALIGNMENT_HEADS[name]
+    om = build_oracle_model(dims, sd, heads)
+    gm = wt.load_model(f"synthetic:{name}", device="cuda:0", synthetic_kwargs=kw)
+    return gm, om, OracleEngine(om, heads, keep_logprobs=True)
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    return _models("tiny")
+
+
+def _engine(gm, backend, **kw):
+    from whisper_timestamped.engine import CudaEngine
+    return CudaEngine(gm, gemm_backend=backend, **kw)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_gemm_backends_vs_torch(backend):
+    """wts_gemm (SB16 operands) against a float64 torch matmul of the same SB16 values."""
+    import whisper_timestamped as wt
+    from whisper_timestamped.model import SB16
+    from whisper_timestamped.engine import CudaEngine
+    from types import SimpleNamespace
+    dev = torch.device("cuda:0")
+    eng = CudaEngine.__new__(CudaEngine)
+    eng.dev, eng.backend, eng.launches = dev, backend, 0
+    g = torch.Generator(device="cpu").manual_seed(5)
+    for (M, N, K) in [(200, 300, 136), (1500, 384, 384), (5, 51865, 384), (128, 64, 1500), (33, 17, 72)]:
+        a = torch.randn(M, K, generator=g).to(dev)
+        b = torch.randn(N, K, generator=g).to(dev)
+        bias = torch.randn(N, generator=g).to(dev)
+        res = torch.randn(M, N, generator=g).to(dev)
+        A, Bm = SB16.from_f32(a), SB16.from_f32(b)
+        out = torch.zeros(M, N, device=dev)
+        osb = SB16(M, N, dev)
+        eng.gemm(A, Bm, M, N, K, bias=bias, act=1, residual=res, ldr=N, out_f32=out, ldc=N, out_sb=osb)
+        torch.cuda.synchronize()
+        ref = torch.nn.functional.gelu(A.to_f32().double() @ Bm.to_f32().double().T + bias.double()) + res.double()
+        err = (out.double() - ref).abs().max().item()
+        scale = ref.abs().max().item()
+        assert err <= 2e-4 * max(1.0, scale), (M, N, K, err, scale)
+        assert (osb.to_f32().double() - ref).abs().max().item() <= 3e-4 * max(1.0, scale)
+
+
+@pytest.mark.parametrize("backend", BACKENDS[:1])
+def test_log_mel_matches_oracle(tiny, backend):
+    from whisper_timestamped.synthetic_audio import synthetic_speech
+    gm, om, oe = tiny
+    eng = _engine(gm, backend)
+    for dur, seed in ((30.0, 1), (7.3, 2), (0.5, 3)):
+        audio = synthetic_speech(dur, seed=seed)
+        mel = eng.log_mel(eng.load_audio(audio)).cpu().numpy()           # [frames, n_mels]
+        ref = oe.log_mel(torch.from_numpy(audio)).numpy().T
+        assert mel.shape == ref.shape
+        assert np.max(np.abs(mel - ref)) <= TOL, np.max(np.abs(mel - ref))
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_encoder_matches_oracle(tiny, backend):
+    from whisper_timestamped.synthetic_audio import synthetic_speech
+    gm, om, oe = tiny
+    eng = _engine(gm, backend)
+    audio = synthetic_speech(40.0, seed=21)
+    mel = eng.log_mel(eng.load_audio(audio))
+    jobs = [dict(mel=mel, seek=0, segment_size=3000), dict(mel=mel, seek=2500, segment_size=1500)]
+    xa = eng.encode(jobs).to_f32().cpu().numpy().reshape(2, 1500, -1)
+    omel = oe.log_mel(torch.from_numpy(audio))
+    import whisper
+    for k, job in enumerate(jobs):
+        seg = whisper.pad_or_trim(omel[:, job["seek"]: job["seek"] + job["segment_size"]], 3000)
+        with torch.no_grad():
+            ref = om.encoder(seg[None])[0].numpy()
+        err = np.max(np.abs(xa[k] - ref))
+        assert err <= TOL, (k, err)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_decode_windows_matches_oracle(tiny, backend):
+    """Same windows through the CUDA engine and the oracle engine: identical tokens, log-probs, no-speech
+    probability and alignment-head cross-attention rows within 1e-3."""
+    from whisper_timestamped.synthetic_audio import synthetic_speech
+    from whisper_timestamped.tokenizer import get_tokenizer
+    from whisper_timestamped.windows import make_decode_setup
+    gm, om, oe = tiny
+    eng = _engine(gm, backend, keep_full_logprobs=True)
+    tok = get_tokenizer(True, num_languages=gm.num_languages, language="en", task="transcribe")
+    setup = make_decode_setup(tok, gm.dims.n_text_ctx)
+    audio = synthetic_speech(65.0, seed=33)
+    gmel = eng.log_mel(eng.load_audio(audio))
+    omel = oe.log_mel(torch.from_numpy(audio))
+    prompt_long = setup.initial_tokens(list(range(1000, 1040)))
+    specs = [(0, 3000, setup.initial_tokens([])), (3000, 3000, prompt_long), (6000, 500, setup.initial_tokens([]))]
+    gj = [dict(mel=gmel, seek=s, segment_size=z, prompt=p) for (s, z, p) in specs]
+    oj = [dict(mel=omel, seek=s, segment_size=z, prompt=p) for (s, z, p) in specs]
+    grec = eng.decode_windows(gj, setup)
+    orec = oe.decode_windows(oj, setup)
+    for k, (a, b) in enumerate(zip(grec, orec)):
+        assert a.tokens == b.tokens, (k, a.tokens[:20], b.tokens[:20])
+        assert a.ended_by_eot == b.ended_by_eot
+        assert abs(a.no_speech_prob - b.no_speech_prob) <= TOL
+        assert np.max(np.abs(a.logprobs - b.logprobs)) <= TOL, (k, np.max(np.abs(a.logprobs - b.logprobs)))
+        buf, bi = eng.window_index[a.qk_window]
+        qk = eng.qk_buffers[buf][bi, :, : a.n_rows].cpu().numpy()
+        ref = oe.qk[b.qk_window].numpy()
+        assert qk.shape == ref.shape
+        assert np.max(np.abs(qk - ref)) <= TOL, (k, np.max(np.abs(qk - ref)))
+        full = eng.full_logprobs[buf][bi, : a.n_rows].cpu().numpy()
+        oref = oe.full_logprobs[b.qk_window].numpy()
+        finite = np.isfinite(oref)
+        assert np.array_equal(finite, np.isfinite(full))
+        assert np.max(np.abs(full[finite] - oref[finite])) <= TOL
+
+
+CASES = sorted(glob.glob(os.path.join(HERE, "golden", "e2e_*.json")))
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[4:-5] for p in CASES])
+def test_transcribe_matches_reference_golden(path, backend):
+    """whisper_timestamped.transcribe() on the GPU vs the unmodified reference's output (CPU fp32)."""
+    import whisper_timestamped as wt
+    from whisper_timestamped.synthetic_audio import synthetic_speech
+    from test_host_e2e import compare
+    g = json.load(open(path))
+    gm = wt.load_model(f"synthetic:{g['model']}", device="cuda:0", synthetic_seed=g["model_seed"],
+                       synthetic_kwargs=g["model_kwargs"])
+    eng = _engine(gm, backend)
+    audio = synthetic_speech(*g["audio"])
+    res = wt.transcribe(gm, audio, engine=eng, **g["transcribe_kwargs"])
+    compare(res, g["result"], conf_tol=2e-3, time_tol=0.0)

@@ -1,0 +1,610 @@
+// Model-forward operators other than the GEMM: format conversion, LayerNorm, row softmax, log-mel
+// pre/post kernels, window gather, token embedding, ragged decoder attention (with the alignment
+// heads' pre-softmax rows written straight into the alignment buffer), KV-cache append, and the
+// fused logit-filter / log-softmax / greedy-argmax step.  See include/wts.h for the reference
+// interfaces each entry replaces.
+#include <cuda_bf16.h>
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace wts {
+
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo)
+{
+    hi = __float2bfloat16_rn(x);
+    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+__device__ __forceinline__ float block_reduce_sum(float v, float* red)
+{
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    float r = (threadIdx.x < nw) ? red[threadIdx.x] : 0.f;
+    if (w == 0) { r = warp_sum(r); if (l == 0) red[0] = r; }
+    __syncthreads();
+    return red[0];
+}
+__device__ __forceinline__ float block_reduce_max(float v, float* red)
+{
+    v = warp_max(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    float r = (threadIdx.x < nw) ? red[threadIdx.x] : -CUDART_INF_F;
+    if (w == 0) { r = warp_max(r); if (l == 0) red[0] = r; }
+    __syncthreads();
+    return red[0];
+}
+
+// ------------------------------------------------------------------------------------------ to_sb16
+__global__ void to_sb16_kernel(const float* __restrict__ x, int64_t n, __nv_bfloat16* __restrict__ hi,
+                               __nv_bfloat16* __restrict__ lo)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        __nv_bfloat16 h, l;
+        split_bf16(x[i], h, l);
+        hi[i] = h;
+        lo[i] = l;
+    }
+}
+
+// ---------------------------------------------------------------------------------------- layernorm
+// one warp per row; float32 statistics (mean, biased variance), eps = 1e-5
+__global__ void __launch_bounds__(128)
+layernorm_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, int M, int D, __nv_bfloat16* __restrict__ o, int64_t ldo,
+                 int64_t o_plane, float* __restrict__ of, int64_t ldf)
+{
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float* xr = x + (int64_t)row * ldx;
+    float s = 0.f;
+    for (int c = lane; c < D; c += 32) s += xr[c];
+    const float mean = warp_sum(s) / (float)D;
+    float v = 0.f;
+    for (int c = lane; c < D; c += 32) { const float d = xr[c] - mean; v += d * d; }
+    const float rstd = 1.0f / sqrtf(warp_sum(v) / (float)D + 1e-5f);
+    for (int c = lane; c < D; c += 32) {
+        const float y = (xr[c] - mean) * rstd * gamma[c] + beta[c];
+        if (o) {
+            __nv_bfloat16 h, l;
+            split_bf16(y, h, l);
+            o[(int64_t)row * ldo + c] = h;
+            o[(int64_t)row * ldo + c + o_plane] = l;
+        }
+        if (of) of[(int64_t)row * ldf + c] = y;
+    }
+}
+
+// ------------------------------------------------------------------------------------- softmax rows
+// one warp per row, n <= 2048; scores float32 -> probabilities SB16
+__global__ void __launch_bounds__(128)
+softmax_rows_kernel(const float* __restrict__ s, int64_t lds, int64_t rows, int n,
+                    __nv_bfloat16* __restrict__ o, int64_t ldo, int64_t o_plane)
+{
+    const int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* sr = s + row * lds;
+    float v[64];
+    float mx = -CUDART_INF_F;
+#pragma unroll
+    for (int k = 0; k < 64; ++k) {
+        const int c = lane + 32 * k;
+        v[k] = c < n ? sr[c] : -CUDART_INF_F;
+        mx = fmaxf(mx, v[k]);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 64; ++k) {
+        v[k] = expf(v[k] - mx);
+        sum += v[k];
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int k = 0; k < 64; ++k) {
+        const int c = lane + 32 * k;
+        if (c < n) {
+            __nv_bfloat16 h, l;
+            split_bf16(v[k] * inv, h, l);
+            o[row * ldo + c] = h;
+            o[row * ldo + c + o_plane] = l;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ log-mel
+// frames: Hann(400, periodic) * reflect-padded audio, hop 160; float32 out [n_frames, 400]
+__global__ void frames_kernel(const float* __restrict__ audio, int64_t n_samples, int64_t n_total,
+                              int64_t n_frames, float* __restrict__ out)
+{
+    const int64_t t = blockIdx.x;
+    if (t >= n_frames) return;
+    for (int n = threadIdx.x; n < 400; n += blockDim.x) {
+        int64_t i = t * 160 - 200 + n;
+        if (i < 0) i = -i;
+        if (i >= n_total) i = 2 * (n_total - 1) - i;
+        const float x = (i >= 0 && i < n_samples) ? audio[i] : 0.f;
+        const float w = 0.5f - 0.5f * cospif((float)n / 200.0f);
+        out[t * 400 + n] = x * w;
+    }
+}
+
+// power: y [n_frames, 2*208] (re | im) -> p [n_frames, 208]
+__global__ void power_kernel(const float* __restrict__ y, int64_t ldy, int64_t n_frames, float* __restrict__ p,
+                             int64_t ldp)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_frames * 208) return;
+    const int64_t t = i / 208;
+    const int k = (int)(i - t * 208);
+    const float re = y[t * ldy + k], im = y[t * ldy + 208 + k];
+    p[t * ldp + k] = re * re + im * im;
+}
+
+__device__ __forceinline__ float mel_log10(float m) { return log10f(fmaxf(m, 1e-10f)); }
+
+__global__ void logmel_max_kernel(const float* __restrict__ m, int64_t n, float* __restrict__ out)
+{
+    __shared__ float red[32];
+    float mx = -CUDART_INF_F;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        mx = fmaxf(mx, mel_log10(m[i]));
+    mx = block_reduce_max(mx, red);
+    if (threadIdx.x == 0) {
+        // float max via int ordering (values may be negative): atomicMax on the monotone key
+        int key = __float_as_int(mx);
+        key = key >= 0 ? key : key ^ 0x7fffffff;
+        atomicMax(reinterpret_cast<int*>(out), key);
+    }
+}
+
+__global__ void logmel_finish_kernel(const float* __restrict__ m, int64_t n, const float* __restrict__ mxkey,
+                                     float* __restrict__ out)
+{
+    int key = *reinterpret_cast<const int*>(mxkey);
+    key = key >= 0 ? key : key ^ 0x7fffffff;
+    const float gmax = __int_as_float(key);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float x = mel_log10(m[i]);
+        x = fmaxf(x, gmax - 8.0f);
+        out[i] = (x + 4.0f) / 4.0f;
+    }
+}
+
+// window gather: conv1 input [B, 3002, n_mels] SB16, rows 0 and 3001 zero, frames >= size zero
+__global__ void window_gather_kernel(const int64_t* __restrict__ mel_ptr, int n_mels,
+                                     const int32_t* __restrict__ seek, const int32_t* __restrict__ size, int B,
+                                     __nv_bfloat16* __restrict__ out, int64_t o_plane)
+{
+    const int b = blockIdx.y;
+    const float* mel = reinterpret_cast<const float*>(mel_ptr[b]);
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t per = (int64_t)3002 * n_mels;
+    if (i >= per) return;
+    const int r = (int)(i / n_mels), c = (int)(i - (int64_t)r * n_mels);
+    float v = 0.f;
+    const int t = r - 1;
+    if (t >= 0 && t < size[b]) v = mel[((int64_t)seek[b] + t) * n_mels + c];
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    out[b * per + i] = h;
+    out[b * per + i + o_plane] = l;
+}
+
+// ------------------------------------------------------------------------------------------- embed
+__global__ void embed_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ positions,
+                             const float* __restrict__ emb, const float* __restrict__ pos, int rows, int D,
+                             float* __restrict__ out)
+{
+    const int r = blockIdx.x;
+    if (r >= rows) return;
+    const float* e = emb + (int64_t)tokens[r] * D;
+    const float* p = pos + (int64_t)positions[r] * D;
+    for (int c = threadIdx.x; c < D; c += blockDim.x) out[(int64_t)r * D + c] = e[c] + p[c];
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ x, int64_t ldx, const int32_t* __restrict__ idx,
+                                   int rows, int D, float* __restrict__ out)
+{
+    const int r = blockIdx.x;
+    if (r >= rows) return;
+    const float* s = x + (int64_t)idx[r] * ldx;
+    for (int c = threadIdx.x; c < D; c += blockDim.x) out[(int64_t)r * D + c] = s[c];
+}
+
+// ----------------------------------------------------------------------------- decoder attention
+// One CTA (128 threads) per (query row, head); head_dim 64.  Scores, softmax and weighted sum in fp32.
+constexpr int DA_THREADS = 128;
+__global__ void __launch_bounds__(DA_THREADS)
+decoder_attention_kernel(const int kind, const float* __restrict__ q, int64_t ldq, const float* __restrict__ kc,
+                         const float* __restrict__ vc, int64_t seq_stride, int ctx,
+                         const int32_t* __restrict__ row_seq, const int32_t* __restrict__ row_pos, int H,
+                         __nv_bfloat16* __restrict__ o, int64_t ldo, int64_t o_plane, float* __restrict__ qk_out,
+                         const int32_t* __restrict__ head_slot, int n_slots, int qk_rows,
+                         const int32_t* __restrict__ qk_row)
+{
+    extern __shared__ float sm[];
+    float* sc = sm;                 // [ctx] scores
+    float* qs = sm + ctx;           // [64]
+    float* red = qs + 64;           // [32]
+    float* part = red + 32;         // [2][64]
+    const int r = blockIdx.x, h = blockIdx.y;
+    const int seq = row_seq[r];
+    const int nk = kind == 0 ? row_pos[r] + 1 : ctx;
+    const float* K = kc + (int64_t)seq * seq_stride + (int64_t)h * ctx * 64;
+    const float* V = vc + (int64_t)seq * seq_stride + (int64_t)h * ctx * 64;
+    if (threadIdx.x < 64) qs[threadIdx.x] = q[(int64_t)r * ldq + h * 64 + threadIdx.x];
+    __syncthreads();
+    float mx = -CUDART_INF_F;
+    for (int j = threadIdx.x; j < nk; j += DA_THREADS) {
+        const float4* kr = reinterpret_cast<const float4*>(K + (int64_t)j * 64);
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const float4 kv = kr[c];
+            acc += qs[4 * c] * kv.x + qs[4 * c + 1] * kv.y + qs[4 * c + 2] * kv.z + qs[4 * c + 3] * kv.w;
+        }
+        sc[j] = acc;
+        mx = fmaxf(mx, acc);
+    }
+    __syncthreads();
+    if (kind == 1 && qk_out != nullptr) {
+        const int slot = head_slot[h];
+        const int qr = qk_row[r];
+        if (slot >= 0 && qr >= 0) {
+            float* dst = qk_out + (((int64_t)seq * n_slots + slot) * qk_rows + qr) * (int64_t)ctx;
+            for (int j = threadIdx.x; j < nk; j += DA_THREADS) dst[j] = sc[j];
+        }
+    }
+    mx = block_reduce_max(mx, red);
+    float sum = 0.f;
+    for (int j = threadIdx.x; j < nk; j += DA_THREADS) {
+        const float e = expf(sc[j] - mx);
+        sc[j] = e;
+        sum += e;
+    }
+    sum = block_reduce_sum(sum, red);
+    const float inv = 1.0f / sum;
+    const int c = threadIdx.x & 63, g = threadIdx.x >> 6;
+    float acc = 0.f;
+    for (int j = g; j < nk; j += 2) acc += sc[j] * V[(int64_t)j * 64 + c];
+    part[g * 64 + c] = acc;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        const float y = (part[threadIdx.x] + part[64 + threadIdx.x]) * inv;
+        __nv_bfloat16 hi, lo;
+        split_bf16(y, hi, lo);
+        o[(int64_t)r * ldo + h * 64 + threadIdx.x] = hi;
+        o[(int64_t)r * ldo + h * 64 + threadIdx.x + o_plane] = lo;
+    }
+}
+
+__global__ void kv_append_kernel(const float* __restrict__ k, const float* __restrict__ v, int64_t ld,
+                                 const int32_t* __restrict__ row_seq, const int32_t* __restrict__ row_pos, int H,
+                                 int ctx, float* __restrict__ kc, float* __restrict__ vc, int64_t seq_stride)
+{
+    const int r = blockIdx.x;
+    const int seq = row_seq[r], pos = row_pos[r];
+    for (int c = threadIdx.x; c < H * 64; c += blockDim.x) {
+        const int h = c >> 6, d = c & 63;
+        const int64_t dst = (int64_t)seq * seq_stride + ((int64_t)h * ctx + pos) * 64 + d;
+        kc[dst] = k[(int64_t)r * ld + c];
+        vc[dst] = v[(int64_t)r * ld + c];
+    }
+}
+
+// ------------------------------------------------------------------------------------ decode select
+constexpr int DS_THREADS = 512;
+__global__ void __launch_bounds__(DS_THREADS)
+decode_select_kernel(float* __restrict__ logits, int64_t ldl, const WtsDecodeCfg cfg,
+                     const uint8_t* __restrict__ suppress, const uint8_t* __restrict__ blank,
+                     int32_t* __restrict__ tokens, int32_t* __restrict__ n_tokens,
+                     const int32_t* __restrict__ n_prompt, int32_t* __restrict__ done,
+                     float* __restrict__ logprobs, int lp_ld, float* __restrict__ full)
+{
+    __shared__ float red[32];
+    __shared__ int s_flags[8];
+    __shared__ float s_best[DS_THREADS / 32];
+    __shared__ int s_besti[DS_THREADS / 32];
+    const int b = blockIdx.x;
+    if (done[b]) return;
+    float* x = logits + (int64_t)b * ldl;
+    int32_t* tk = tokens + (int64_t)b * cfg.tokens_ld;
+    const int nt = n_tokens[b], np = n_prompt[b];
+    const int n = nt - np;                                   // sampled so far
+    const int V = cfg.n_vocab, tsb = cfg.timestamp_begin, eot = cfg.eot;
+    if (threadIdx.x == 0) {
+        const bool last_ts = n >= 1 && tk[nt - 1] >= tsb;
+        const bool pen_ts = n < 2 || tk[nt - 2] >= tsb;
+        int tl = -1;
+        for (int i = nt - 1; i >= np; --i) if (tk[i] >= tsb) { tl = tk[i]; break; }
+        int ts_limit = tsb;                                  // timestamps in [tsb, ts_limit) are forbidden
+        if (tl >= 0) ts_limit = (last_ts && !pen_ts) ? tl : tl + 1;
+        s_flags[0] = (n == 0);
+        s_flags[1] = last_ts && pen_ts;                      // forbid all timestamps
+        s_flags[2] = last_ts && !pen_ts;                     // forbid text below eot
+        s_flags[3] = ts_limit;
+    }
+    __syncthreads();
+    const bool first = s_flags[0], no_ts = s_flags[1], no_text = s_flags[2];
+    const int ts_limit = s_flags[3];
+    const int ts_max = (first && cfg.max_initial_ts >= 0) ? tsb + cfg.max_initial_ts : V;
+
+    auto allowed = [&](int v) -> bool {
+        if (suppress[v]) return false;
+        if (first && blank[v]) return false;
+        if (v == cfg.no_timestamps) return false;
+        if (v >= tsb) {
+            if (no_ts) return false;
+            if (v < ts_limit) return false;
+            if (v > ts_max) return false;
+        } else {
+            if (first) return false;
+            if (no_text && v < eot) return false;
+        }
+        return true;
+    };
+
+    // pass 1: maxima of the text range and of the timestamp range
+    float mt = -CUDART_INF_F, ms = -CUDART_INF_F;
+    for (int v = threadIdx.x; v < V; v += DS_THREADS) {
+        if (!allowed(v)) continue;
+        const float xv = x[v];
+        if (v >= tsb) ms = fmaxf(ms, xv); else mt = fmaxf(mt, xv);
+    }
+    mt = block_reduce_max(mt, red);
+    ms = block_reduce_max(ms, red);
+    // pass 2: sum of exp over timestamps (relative to ms) -> logsumexp of the timestamp range
+    float ss = 0.f;
+    if (ms > -CUDART_INF_F)
+        for (int v = tsb + threadIdx.x; v < V; v += DS_THREADS)
+            if (allowed(v)) ss += expf(x[v] - ms);
+    ss = block_reduce_sum(ss, red);
+    const float lse_ts = (ms > -CUDART_INF_F) ? ms + logf(ss) : -CUDART_INF_F;
+    const bool only_ts = lse_ts > mt;                        // "sum of timestamp probability beats any text token"
+    // pass 3: final normaliser + argmax over the allowed set
+    const float gm = only_ts ? ms : fmaxf(mt, ms);
+    float sum = 0.f, best = -CUDART_INF_F;
+    int besti = 0x7fffffff;
+    for (int v = threadIdx.x; v < V; v += DS_THREADS) {
+        if (!allowed(v) || (only_ts && v < tsb)) continue;
+        const float xv = x[v];
+        sum += expf(xv - gm);
+        if (xv > best) { best = xv; besti = v; }             // ascending v per thread: first max kept
+    }
+    sum = block_reduce_sum(sum, red);
+    // block argmax, lowest index on ties
+    {
+        float bv = best; int bi = besti;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(FULL_MASK, bv, o);
+            const int oi = __shfl_xor_sync(FULL_MASK, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if ((threadIdx.x & 31) == 0) { s_best[threadIdx.x >> 5] = bv; s_besti[threadIdx.x >> 5] = bi; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < DS_THREADS / 32; ++w)
+                if (s_best[w] > bv || (s_best[w] == bv && s_besti[w] < bi)) { bv = s_best[w]; bi = s_besti[w]; }
+            s_best[0] = bv; s_besti[0] = bi;
+        }
+        __syncthreads();
+    }
+    const float lse = gm + logf(sum);
+    const int chosen = s_besti[0];
+    if (full != nullptr) {
+        float* f = full + ((int64_t)b * lp_ld + n) * V;
+        for (int v = threadIdx.x; v < V; v += DS_THREADS)
+            f[v] = (allowed(v) && !(only_ts && v < tsb)) ? x[v] - lse : -CUDART_INF_F;
+    }
+    if (threadIdx.x == 0) {
+        logprobs[(int64_t)b * lp_ld + n] = s_best[0] - lse;
+        if (chosen == eot) {
+            done[b] = 1;
+        } else {
+            tk[nt] = chosen;
+            n_tokens[b] = nt + 1;
+            if (n + 1 >= cfg.sample_len || nt + 1 > cfg.n_ctx) done[b] = 2;   // decoding limit reached
+        }
+    }
+}
+
+__global__ void step_inputs_kernel(const int32_t* __restrict__ tokens, int ld, const int32_t* __restrict__ n_tokens,
+                                   const int32_t* __restrict__ n_prompt, const int32_t* __restrict__ done, int B,
+                                   int32_t* __restrict__ tok, int32_t* __restrict__ pos, int32_t* __restrict__ qk_row)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int nt = n_tokens[b];
+    tok[b] = tokens[(int64_t)b * ld + nt - 1];
+    pos[b] = nt - 1;
+    qk_row[b] = done[b] ? -1 : nt - n_prompt[b];
+}
+
+__global__ void softmax_pick_kernel(const float* __restrict__ logits, int64_t ldl, int n, int index,
+                                    float* __restrict__ out)
+{
+    __shared__ float red[32];
+    const float* x = logits + (int64_t)blockIdx.x * ldl;
+    float mx = -CUDART_INF_F;
+    for (int v = threadIdx.x; v < n; v += blockDim.x) mx = fmaxf(mx, x[v]);
+    mx = block_reduce_max(mx, red);
+    float s = 0.f;
+    for (int v = threadIdx.x; v < n; v += blockDim.x) s += expf(x[v] - mx);
+    s = block_reduce_sum(s, red);
+    if (threadIdx.x == 0) out[blockIdx.x] = expf(x[index] - mx) / s;
+}
+
+}  // namespace wts
+
+using namespace wts;
+
+static inline int grid_for(int64_t n, int block, int cap = 148 * 16)
+{
+    int64_t g = (n + block - 1) / block;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+extern "C" int wts_to_sb16(const float* d_x, int64_t n, void* d_hi, void* d_lo, void* stream)
+{
+    if (n <= 0) return 0;
+    to_sb16_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(d_x, n, (__nv_bfloat16*)d_hi, (__nv_bfloat16*)d_lo);
+    WTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int wts_layernorm(const float* d_x, int64_t ldx, const float* d_gamma, const float* d_beta, int32_t M,
+                             int32_t D, void* d_out_sb16, int64_t ldo, int64_t o_plane, float* d_out_f32,
+                             int64_t ldf, void* stream)
+{
+    if (M <= 0) return 0;
+    layernorm_kernel<<<(M + 3) / 4, 128, 0, (cudaStream_t)stream>>>(d_x, ldx, d_gamma, d_beta, M, D,
+                                                                   (__nv_bfloat16*)d_out_sb16, ldo, o_plane, d_out_f32, ldf);
+    WTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int wts_softmax_rows(const float* d_s, int64_t lds, int64_t rows, int32_t n, void* d_out_sb16,
+                                int64_t ldo, int64_t o_plane, void* stream)
+{
+    if (rows <= 0) return 0;
+    if (n > 2048) { set_error("wts_softmax_rows: n=%d > 2048", n); return -2; }
+    softmax_rows_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, (cudaStream_t)stream>>>(d_s, lds, rows, n,
+                                                                                     (__nv_bfloat16*)d_out_sb16, ldo, o_plane);
+    WTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int wts_frames(const float* d_audio, int64_t n_samples, int64_t n_total, int64_t n_frames, void* d_out,
+                          int64_t o_plane, void* stream)
+{
+    (void)o_plane;
+    if (n_frames <= 0) return 0;
+    frames_kernel<<<(unsigned)n_frames, 128, 0, (cudaStream_t)stream>>>(d_audio, n_samples, n_total, n_frames, (float*)d_out);
+    WTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int wts_power(const float* d_y, int64_t ldy, int64_t n_frames, void* d_out, int64_t ldo, int64_t o_plane,
+                         void* stream)
+{
+    (void)o_plane;
+    if (n_frames <= 0) return 0;
+    power_kernel<<<(unsigned)((n_frames * 208 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_y, ldy, n_frames, (float*)d_out, ldo);
+    WTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int wts_logmel_max(const float* d_m, int64_t n, float* d_max, void* stream)
+{
+    // d_max must be pre-set by the caller to the key of -inf (0x807fffff ^ 0x7fffffff = int min side): use -FLT_MAX key
+    logmel_max_kernel<<<grid_for(n, 256, 1024), 256, 0, (cudaStream_t)stream>>>(d_m, n, d_max);
+    WTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int wts_logmel_finish(const float* d_m, int64_t n_frames, int32_t n_mels, const float* d_max,
+                                 float* d_out_f32, void* stream)
+{
+    const int64_t n = n_frames * n_mels;
+    logmel_finish_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(d_m, n, d_max, d_out_f32);
+    WTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int wts_window_gather(const int64_t* d_mel_ptr, int32_t n_mels, const int32_t* d_seek,
+                                 const int32_t* d_size, int32_t B, void* d_out, int64_t o_plane, void* stream)
+{
+    if (B <= 0) return 0;
+    dim3 grid((unsigned)(((int64_t)3002 * n_mels + 255) / 256), B);
+    window_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_mel_ptr, n_mels, d_seek, d_size, B,
+                                                                 (__nv_bfloat16*)d_out, o_plane);
+    WTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int wts_embed(const int32_t* d_tokens, const int32_t* d_positions, const float* d_emb, const float* d_pos,
+                         int32_t rows, int32_t D, float* d_out, void* stream)
+{
+    if (rows <= 0) return 0;
+    embed_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(d_tokens, d_positions, d_emb, d_pos, rows, D, d_out);
+    WTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int wts_gather_rows(const float* d_x, int64_t ldx, const int32_t* d_idx, int32_t rows, int32_t D,
+                               float* d_out, void* stream)
+{
+    if (rows <= 0) return 0;
+    gather_rows_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(d_x, ldx, d_idx, rows, D, d_out);
+    WTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int wts_decoder_attention(int32_t kind, const float* d_q, int64_t ldq, const float* d_k, const float* d_v,
+                                     int64_t seq_stride, int32_t ctx, const int32_t* d_row_seq,
+                                     const int32_t* d_row_pos, int32_t rows, int32_t H, void* d_out_sb16, int64_t ldo,
+                                     int64_t o_plane, float* d_qk_out, const int32_t* d_head_slot, int32_t n_slots,
+                                     int32_t qk_rows, const int32_t* d_qk_row, void* stream)
+{
+    if (rows <= 0) return 0;
+    const size_t smem = ((size_t)ctx + 64 + 32 + 128) * sizeof(float);
+    dim3 grid(rows, H);
+    decoder_attention_kernel<<<grid, DA_THREADS, smem, (cudaStream_t)stream>>>(
+        kind, d_q, ldq, d_k, d_v, seq_stride, ctx, d_row_seq, d_row_pos, H, (__nv_bfloat16*)d_out_sb16, ldo, o_plane,
+        d_qk_out, d_head_slot, n_slots, qk_rows, d_qk_row);
+    WTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int wts_kv_append(const float* d_k, const float* d_v, int64_t ld, const int32_t* d_row_seq,
+                             const int32_t* d_row_pos, int32_t rows, int32_t H, int32_t ctx, float* d_kc, float* d_vc,
+                             int64_t seq_stride, void* stream)
+{
+    if (rows <= 0) return 0;
+    kv_append_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(d_k, d_v, ld, d_row_seq, d_row_pos, H, ctx, d_kc, d_vc, seq_stride);
+    WTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int wts_decode_select(float* d_logits, int64_t ldl, const WtsDecodeCfg* cfg, const uint8_t* d_suppress,
+                                 const uint8_t* d_blank, int32_t* d_tokens, int32_t* d_n_tokens,
+                                 const int32_t* d_n_prompt, int32_t* d_done, float* d_logprobs, int32_t lp_ld,
+                                 float* d_full_logprobs, int32_t B, void* stream)
+{
+    if (B <= 0) return 0;
+    decode_select_kernel<<<B, DS_THREADS, 0, (cudaStream_t)stream>>>(d_logits, ldl, *cfg, d_suppress, d_blank, d_tokens,
+                                                                    d_n_tokens, d_n_prompt, d_done, d_logprobs, lp_ld,
+                                                                    d_full_logprobs);
+    WTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int wts_step_inputs(const int32_t* d_tokens, int32_t tokens_ld, const int32_t* d_n_tokens,
+                               const int32_t* d_n_prompt, const int32_t* d_done, int32_t B, int32_t* d_tok,
+                               int32_t* d_pos, int32_t* d_qk_row, void* stream)
+{
+    if (B <= 0) return 0;
+    step_inputs_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_tokens, tokens_ld, d_n_tokens, d_n_prompt,
+                                                                         d_done, B, d_tok, d_pos, d_qk_row);
+    WTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int wts_softmax_pick(const float* d_logits, int64_t ldl, int32_t n, int32_t index, float* d_out,
+                                int32_t rows, void* stream)
+{
+    if (rows <= 0) return 0;
+    softmax_pick_kernel<<<rows, 512, 0, (cudaStream_t)stream>>>(d_logits, ldl, n, index, d_out);
+    WTS_LAUNCH_CHECK();
+    return 0;
+}

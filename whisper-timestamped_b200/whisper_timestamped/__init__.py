@@ -6,5 +6,9 @@ Same import name and API surface as the reference package
 behind the C-ABI of include/wts.h); importing this package fails if that library is missing.
 """
 from . import _native  # noqa: F401  (fails loudly when libwts.so is absent)
+from .model import load_model  # noqa: F401
+from .model_zoo import ModelDimensions  # noqa: F401
+from .transcribe import transcribe_timestamped  # noqa: F401
+from .transcribe import transcribe_timestamped as transcribe  # noqa: F401
 
 __version__ = "1.15.9+b200.r1"

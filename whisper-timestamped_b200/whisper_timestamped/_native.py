@@ -36,6 +36,29 @@ SEG_DTYPE = np.dtype([
 assert SEG_DTYPE.itemsize == ctypes.sizeof(SegDesc) == 64
 
 
+class Gemm(ctypes.Structure):
+    """Mirror of `WtsGemm` (include/wts.h)."""
+    _fields_ = [
+        ("a", ctypes.c_void_p), ("lda", ctypes.c_int64), ("a_plane", ctypes.c_int64), ("a_bo", ctypes.c_int64), ("a_bi", ctypes.c_int64),
+        ("b", ctypes.c_void_p), ("ldb", ctypes.c_int64), ("b_plane", ctypes.c_int64), ("b_bo", ctypes.c_int64), ("b_bi", ctypes.c_int64),
+        ("M", ctypes.c_int32), ("N", ctypes.c_int32), ("K", ctypes.c_int32), ("batch_outer", ctypes.c_int32), ("batch_inner", ctypes.c_int32),
+        ("alpha", ctypes.c_float),
+        ("bias", ctypes.c_void_p), ("bias_on_m", ctypes.c_int32), ("act", ctypes.c_int32),
+        ("residual", ctypes.c_void_p), ("ldr", ctypes.c_int64), ("r_bo", ctypes.c_int64), ("r_bi", ctypes.c_int64),
+        ("out_f32", ctypes.c_void_p), ("ldc", ctypes.c_int64), ("c_bo", ctypes.c_int64), ("c_bi", ctypes.c_int64),
+        ("out_sb16", ctypes.c_void_p), ("ldo", ctypes.c_int64), ("o_plane", ctypes.c_int64), ("o_bo", ctypes.c_int64), ("o_bi", ctypes.c_int64),
+        ("head_dim", ctypes.c_int32), ("head_stride", ctypes.c_int64),
+        ("backend", ctypes.c_int32), ("a_is_f32", ctypes.c_int32), ("b_is_f32", ctypes.c_int32),
+    ]
+
+
+class DecodeCfg(ctypes.Structure):
+    """Mirror of `WtsDecodeCfg`."""
+    _fields_ = [("n_vocab", ctypes.c_int32), ("eot", ctypes.c_int32), ("timestamp_begin", ctypes.c_int32),
+                ("no_timestamps", ctypes.c_int32), ("max_initial_ts", ctypes.c_int32), ("sample_len", ctypes.c_int32),
+                ("n_ctx", ctypes.c_int32), ("tokens_ld", ctypes.c_int32)]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -53,6 +76,29 @@ def _load():
     lib.wts_attn_prep_batch.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32, vp, vp]
     lib.wts_dtw_batch.restype = ctypes.c_int
     lib.wts_dtw_batch.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    i64, f32p = ctypes.c_int64, vp
+    lib.wts_gemm.restype = ctypes.c_int
+    lib.wts_gemm.argtypes = [ctypes.POINTER(Gemm), vp]
+    lib.wts_to_sb16.argtypes = [vp, i64, vp, vp, vp]
+    lib.wts_layernorm.argtypes = [vp, i64, vp, vp, i32, i32, vp, i64, i64, vp, i64, vp]
+    lib.wts_softmax_rows.argtypes = [vp, i64, i64, i32, vp, i64, i64, vp]
+    lib.wts_frames.argtypes = [vp, i64, i64, i64, vp, i64, vp]
+    lib.wts_power.argtypes = [vp, i64, i64, vp, i64, i64, vp]
+    lib.wts_logmel_max.argtypes = [vp, i64, vp, vp]
+    lib.wts_logmel_finish.argtypes = [vp, i64, i32, vp, vp, vp]
+    lib.wts_window_gather.argtypes = [vp, i32, vp, vp, i32, vp, i64, vp]
+    lib.wts_embed.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp]
+    lib.wts_gather_rows.argtypes = [vp, i64, vp, i32, i32, vp, vp]
+    lib.wts_decoder_attention.argtypes = [i32, vp, i64, vp, vp, i64, i32, vp, vp, i32, i32, vp, i64, i64, vp, vp, i32,
+                                          i32, vp, vp]
+    lib.wts_kv_append.argtypes = [vp, vp, i64, vp, vp, i32, i32, i32, vp, vp, i64, vp]
+    lib.wts_decode_select.argtypes = [vp, i64, ctypes.POINTER(DecodeCfg), vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, vp]
+    lib.wts_step_inputs.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp]
+    lib.wts_softmax_pick.argtypes = [vp, i64, i32, i32, vp, i32, vp]
+    for name in ("wts_to_sb16", "wts_layernorm", "wts_softmax_rows", "wts_frames", "wts_power", "wts_logmel_max",
+                 "wts_logmel_finish", "wts_window_gather", "wts_embed", "wts_gather_rows", "wts_decoder_attention",
+                 "wts_kv_append", "wts_decode_select", "wts_step_inputs", "wts_softmax_pick"):
+        getattr(lib, name).restype = ctypes.c_int
     return lib
 
 
@@ -60,7 +106,10 @@ lib = _load()
 
 EXPORTED_SYMBOLS = [
     "wts_version", "wts_last_error", "wts_dtw_dir_words", "wts_dtw_bnd_doubles",
-    "wts_attn_prep_batch", "wts_dtw_batch",
+    "wts_attn_prep_batch", "wts_dtw_batch", "wts_gemm", "wts_to_sb16", "wts_layernorm", "wts_softmax_rows",
+    "wts_frames", "wts_power", "wts_logmel_max", "wts_logmel_finish", "wts_window_gather", "wts_embed",
+    "wts_gather_rows", "wts_decoder_attention", "wts_kv_append", "wts_decode_select", "wts_step_inputs",
+    "wts_softmax_pick",
 ]
 
 

@@ -1,0 +1,466 @@
+"""CUDA engine: log-mel, batched encoder, batched greedy decoder and batched alignment on one B200.
+
+Everything on the device goes through libwts (hand-written sm_100a kernels behind the C-ABI of
+include/wts.h); PyTorch only owns the buffers and the stream.  Replaces, for whole batches of 30-s
+windows at a time, what the reference drives one window and one token at a time through upstream
+`model.transcribe` and its forward hooks (/root/reference/whisper_timestamped/transcribe.py:887-904):
+
+  log_mel()         whisper.log_mel_spectrogram                       (T.py:1213 / upstream transcribe)
+  decode_windows()  AudioEncoder.forward + DecodingTask._main_loop + hook_attention_weights (T.py:783-793)
+                    + hook_output_logits (T.py:849-881); cross-attention rows of the alignment heads are
+                    written by the attention kernel itself into the [window, head, row, frame] buffer the
+                    alignment kernels read — no hook, no device->host copy per token.
+  align()           the numerical part of perform_word_alignment (T.py:1510-1581, 1648-1652)
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from .alignment import attn_prep, dtw, plan_segments, split_jumps
+from .model import SB16
+from .windows import N_FRAMES, WindowRecord
+
+N_SAMPLES = 480000
+N_CTX_AUDIO = 1500
+KPAD = 1504      # key dimension of score rows, padded so SB16 rows stay 16-byte aligned
+
+
+def _i32(x, dev):
+    return torch.as_tensor(np.asarray(x, dtype=np.int32)).to(dev)
+
+
+class CudaEngine:
+    def __init__(self, model, max_batch=None, gemm_backend=None, keep_full_logprobs=False):
+        self.m = model
+        self.dev = model.device
+        self.w = model.w
+        self.dims = model.dims
+        self.max_batch = max_batch or int(os.environ.get("WTS_MAX_BATCH", "64"))
+        self.backend = int(os.environ.get("WTS_GEMM_BACKEND", "0")) if gemm_backend is None else gemm_backend
+        self.keep_full_logprobs = keep_full_logprobs
+        self.qk_buffers = []            # one [B, N, rows, 1500] float32 tensor per decode_windows call
+        self.window_index = []          # global window id -> (buffer idx, b)
+        self.full_logprobs = []         # per call (only when keep_full_logprobs)
+        self.launches = 0
+        self.use_graph = os.environ.get("WTS_CUDA_GRAPH", "1") != "0"
+        self._graphs = {}
+
+    # ------------------------------------------------------------------ helpers
+    def _st(self):
+        return nat.stream_ptr(self.dev)
+
+    def gemm(self, a, b, M, N, K, *, lda=None, ldb=None, a_plane=None, b_plane=None, a_off=0, b_off=0,
+             batch=(1, 1), a_b=(0, 0), b_b=(0, 0), alpha=1.0, bias=None, bias_on_m=False, act=0,
+             residual=None, ldr=0, r_b=(0, 0), out_f32=None, ldc=0, c_b=(0, 0), c_off=0,
+             out_sb=None, ldo=0, o_plane=0, o_b=(0, 0), o_off=0, head_dim=0, head_stride=0,
+             a_f32=False, b_f32=False, backend=None):
+        """a/b: SB16 objects (or float32 tensors with a_f32/b_f32).  Offsets/strides in elements."""
+        g = nat.Gemm()
+        if a_f32:
+            g.a, g.lda, g.a_plane = a.data_ptr() + 4 * a_off, lda, 0
+        else:
+            g.a, g.lda, g.a_plane = a.ptr + 2 * a_off, lda or a.ld, a_plane if a_plane is not None else a.plane
+        if b_f32:
+            g.b, g.ldb, g.b_plane = b.data_ptr() + 4 * b_off, ldb, 0
+        else:
+            g.b, g.ldb, g.b_plane = b.ptr + 2 * b_off, ldb or b.ld, b_plane if b_plane is not None else b.plane
+        g.a_bo, g.a_bi = a_b
+        g.b_bo, g.b_bi = b_b
+        g.M, g.N, g.K = M, N, K
+        g.batch_outer, g.batch_inner = batch
+        g.alpha = alpha
+        g.bias = bias.data_ptr() if bias is not None else None
+        g.bias_on_m = 1 if bias_on_m else 0
+        g.act = act
+        if residual is not None:
+            g.residual, g.ldr = residual.data_ptr(), ldr
+            g.r_bo, g.r_bi = r_b
+        if out_f32 is not None:
+            g.out_f32, g.ldc = out_f32.data_ptr() + 4 * c_off, ldc
+            g.c_bo, g.c_bi = c_b
+        if out_sb is not None:
+            g.out_sb16, g.ldo, g.o_plane = out_sb.ptr + 2 * o_off, ldo or out_sb.ld, o_plane or out_sb.plane
+            g.o_bo, g.o_bi = o_b
+        g.head_dim, g.head_stride = head_dim, head_stride
+        g.backend = self.backend if backend is None else backend
+        g.a_is_f32, g.b_is_f32 = int(a_f32), int(b_f32)
+        if a_f32 or b_f32:
+            g.backend = 1
+        nat.check(nat.lib.wts_gemm(ctypes.byref(g), self._st()), "wts_gemm")
+        self.launches += 1
+
+    def layernorm(self, x, gamma, beta, M, D, out_sb=None, out_f32=None):
+        nat.check(nat.lib.wts_layernorm(x.data_ptr(), D, gamma.data_ptr(), beta.data_ptr(), M, D,
+                                        out_sb.ptr if out_sb is not None else None,
+                                        out_sb.ld if out_sb is not None else 0,
+                                        out_sb.plane if out_sb is not None else 0,
+                                        out_f32.data_ptr() if out_f32 is not None else None, D, self._st()),
+                  "wts_layernorm")
+        self.launches += 1
+
+    # ------------------------------------------------------------------ audio / log-mel
+    def load_audio(self, audio):
+        if isinstance(audio, str):
+            import wave
+            with wave.open(audio, "rb") as wv:
+                if wv.getframerate() != 16000 or wv.getnchannels() != 1 or wv.getsampwidth() != 2:
+                    raise RuntimeError("only 16 kHz mono s16 .wav files can be read here (no ffmpeg in this environment)")
+                data = wv.readframes(wv.getnframes())
+            audio = np.frombuffer(data, np.int16).astype(np.float32) / 32768.0
+        if isinstance(audio, np.ndarray):
+            audio = torch.from_numpy(np.ascontiguousarray(audio, dtype=np.float32))
+        assert isinstance(audio, torch.Tensor), f"Got unexpected audio of type {type(audio)}"
+        audio = audio.float()
+        if audio.device != self.dev:
+            audio = (audio.pin_memory() if audio.device.type == "cpu" else audio).to(self.dev, non_blocking=True)
+        return audio.contiguous()
+
+    def log_mel(self, audio):
+        """float32 time-major log-mel [frames, n_mels] of `audio` + 30 s of zero padding (upstream
+        log_mel_spectrogram(audio, n_mels, padding=N_SAMPLES)); the -8 floor uses this stream's maximum."""
+        dev, st = self.dev, self._st()
+        n = int(audio.numel())
+        total = n + N_SAMPLES
+        nf = total // 160
+        C = self.dims.n_mels
+        frames = torch.empty((nf, 400), dtype=torch.float32, device=dev)
+        nat.check(nat.lib.wts_frames(audio.data_ptr(), n, total, nf, frames.data_ptr(), 0, st), "wts_frames")
+        y = torch.empty((nf, 416), dtype=torch.float32, device=dev)
+        self.gemm(frames, self.w.dft, nf, 416, 400, lda=400, ldb=400, a_f32=True, b_f32=True, out_f32=y, ldc=416)
+        p = torch.empty((nf, 208), dtype=torch.float32, device=dev)
+        nat.check(nat.lib.wts_power(y.data_ptr(), 416, nf, p.data_ptr(), 208, 0, st), "wts_power")
+        mel = torch.empty((nf, C), dtype=torch.float32, device=dev)
+        self.gemm(p, self.w.melfb, nf, C, 208, lda=208, ldb=208, a_f32=True, b_f32=True, out_f32=mel, ldc=C)
+        key = torch.full((1,), -2 ** 31, dtype=torch.int32, device=dev)
+        nat.check(nat.lib.wts_logmel_max(mel.data_ptr(), nf * C, key.data_ptr(), st), "wts_logmel_max")
+        out = torch.empty((nf, C), dtype=torch.float32, device=dev)
+        nat.check(nat.lib.wts_logmel_finish(mel.data_ptr(), nf, C, key.data_ptr(), out.data_ptr(), st), "wts_logmel_finish")
+        self.launches += 6
+        return out
+
+    def mel_frames(self, mel):
+        return int(mel.shape[0])
+
+    # ------------------------------------------------------------------ encoder
+    def encode(self, jobs):
+        """jobs -> (xa SB16 [B*1500, d]).  conv1/conv2 as GEMMs over overlapping rows, then the blocks."""
+        d, dev, st, w = self.dims, self.dev, self._st(), self.w
+        B, C, D, H = len(jobs), d.n_mels, d.n_audio_state, d.n_audio_head
+        ptrs = torch.as_tensor(np.array([j["mel"].data_ptr() for j in jobs], dtype=np.int64)).to(dev)
+        seek = _i32([j["seek"] for j in jobs], dev)
+        size = _i32([j["segment_size"] for j in jobs], dev)
+        x0 = SB16(B * 3002, C, dev)
+        nat.check(nat.lib.wts_window_gather(ptrs.data_ptr(), C, seek.data_ptr(), size.data_ptr(), B, x0.ptr, x0.plane, st),
+                  "wts_window_gather")
+        # conv1 (k=3, pad 1) + GELU: row t of the GEMM's A operand = padded rows t..t+2 (K = 3C, lda = C)
+        h1 = SB16(B * 3001, D, dev)            # row 0 of every window stays zero = conv2's left padding
+        self.gemm(x0, w.conv1, 3000, D, 3 * C, lda=C, batch=(B, 1), a_b=(3002 * C, 0), bias=w.conv1_b, act=1,
+                  out_sb=h1, ldo=D, o_b=(3001 * D, 0), o_off=D)
+        # conv2 (k=3, stride 2, pad 1) + GELU + positional embedding: A row t = padded rows 2t..2t+2
+        x = torch.empty((B * 1500, D), dtype=torch.float32, device=dev)
+        self.gemm(h1, w.conv2, 1500, D, 3 * D, lda=2 * D, batch=(B, 1), a_b=(3001 * D, 0), bias=w.conv2_b, act=1,
+                  residual=w.enc_pos, ldr=D, r_b=(0, 0), out_f32=x, ldc=D, c_b=(1500 * D, 0))
+        R = B * 1500
+        hs = SB16(R, D, dev)
+        qk = SB16(R, 2 * D, dev)
+        vt = SB16(B * D, KPAD, dev)
+        S = torch.empty((B * H * 1500, KPAD), dtype=torch.float32, device=dev)
+        P = SB16(B * H * 1500, KPAD, dev)
+        att = SB16(R, D, dev)
+        mid = SB16(R, 4 * D, dev)
+        for blk in w.enc:
+            a = blk.attn
+            self.layernorm(x, a.ln_g, a.ln_b, R, D, out_sb=hs)
+            self.gemm(hs, a.qk, R, 2 * D, D, bias=a.qk_b, out_sb=qk)
+            # V^T per window: [D, 1500] = Wv [D, D] x h^T  (swapped operands, bias along M)
+            self.gemm(a.v, hs, D, 1500, D, batch=(B, 1), b_b=(1500 * D, 0), bias=a.v_b, bias_on_m=True,
+                      out_sb=vt, ldo=KPAD, o_b=(D * KPAD, 0))
+            # scores[b, h] = q_h k_h^T  (scale folded into the weights)
+            self.gemm(qk, qk, 1500, 1500, 64, lda=2 * D, ldb=2 * D, b_off=D, batch=(B, H),
+                      a_b=(1500 * 2 * D, 64), b_b=(1500 * 2 * D, 64), out_f32=S, ldc=KPAD,
+                      c_b=(H * 1500 * KPAD, 1500 * KPAD))
+            nat.check(nat.lib.wts_softmax_rows(S.data_ptr(), KPAD, B * H * 1500, 1500, P.ptr, KPAD, P.plane, st),
+                      "wts_softmax_rows")
+            self.launches += 1
+            # out[b, :, h*64:(h+1)*64] = P[b, h] x V_h   (B operand = rows h*64.. of V^T)
+            self.gemm(P, vt, 1500, 64, 1500, lda=KPAD, ldb=KPAD, batch=(B, H),
+                      a_b=(H * 1500 * KPAD, 1500 * KPAD), b_b=(D * KPAD, 64 * KPAD), out_sb=att, ldo=D,
+                      o_b=(1500 * D, 64))
+            self.gemm(att, a.out, R, D, D, bias=a.out_b, residual=x, ldr=D, out_f32=x, ldc=D)
+            self.layernorm(x, blk.mlp_ln_g, blk.mlp_ln_b, R, D, out_sb=hs)
+            self.gemm(hs, blk.fc1, R, 4 * D, D, bias=blk.fc1_b, act=1, out_sb=mid)
+            self.gemm(mid, blk.fc2, R, D, 4 * D, bias=blk.fc2_b, residual=x, ldr=D, out_f32=x, ldc=D)
+        xa = SB16(R, D, dev)
+        self.layernorm(x, w.ln_post_g, w.ln_post_b, R, D, out_sb=xa)
+        return xa
+
+    # ------------------------------------------------------------------ decoder
+    def _decoder_rows(self, st8, x, R, row_seq, row_pos, qk_row, qk_buf):
+        """One pass of all decoder blocks over R query rows (ragged batch)."""
+        d, w, st = self.dims, self.w, self._st()
+        D, H, L = d.n_text_state, d.n_text_head, d.n_text_layer
+        hs, qkv, att, q, mid = st8["hs"], st8["qkv"], st8["att"], st8["q"], st8["mid"]
+        n_slots = len(self.m.heads)
+        for li, blk in enumerate(w.dec):
+            a, c = blk.attn, blk.cross
+            self.layernorm(x, a.ln_g, a.ln_b, R, D, out_sb=hs)
+            self.gemm(hs, a.qkv, R, 3 * D, D, bias=a.qkv_b, out_f32=qkv, ldc=3 * D)
+            nat.check(nat.lib.wts_kv_append(qkv.data_ptr() + 4 * D, qkv.data_ptr() + 8 * D, 3 * D, row_seq.data_ptr(),
+                                            row_pos.data_ptr(), R, H, d.n_text_ctx, st8["sk"][li].data_ptr(),
+                                            st8["sv"][li].data_ptr(), H * d.n_text_ctx * 64, st), "wts_kv_append")
+            nat.check(nat.lib.wts_decoder_attention(0, qkv.data_ptr(), 3 * D, st8["sk"][li].data_ptr(),
+                                                    st8["sv"][li].data_ptr(), H * d.n_text_ctx * 64, d.n_text_ctx,
+                                                    row_seq.data_ptr(), row_pos.data_ptr(), R, H, att.ptr, att.ld,
+                                                    att.plane, None, None, 0, 0, None, st), "wts_decoder_attention")
+            self.gemm(att, a.out, R, D, D, bias=a.out_b, residual=x, ldr=D, out_f32=x, ldc=D)
+            self.layernorm(x, c.ln_g, c.ln_b, R, D, out_sb=hs)
+            self.gemm(hs, c.q, R, D, D, bias=c.q_b, out_f32=q, ldc=D)
+            nat.check(nat.lib.wts_decoder_attention(1, q.data_ptr(), D, st8["ck"][li].data_ptr(), st8["cv"][li].data_ptr(),
+                                                    H * N_CTX_AUDIO * 64, N_CTX_AUDIO, row_seq.data_ptr(),
+                                                    row_pos.data_ptr(), R, H, att.ptr, att.ld, att.plane,
+                                                    qk_buf.data_ptr(), w.head_slot[li].data_ptr(), n_slots,
+                                                    qk_buf.shape[2], qk_row.data_ptr(), st), "wts_decoder_attention")
+            self.gemm(att, c.out, R, D, D, bias=c.out_b, residual=x, ldr=D, out_f32=x, ldc=D)
+            self.layernorm(x, blk.mlp_ln_g, blk.mlp_ln_b, R, D, out_sb=hs)
+            self.gemm(hs, blk.fc1, R, 4 * D, D, bias=blk.fc1_b, act=1, out_sb=mid)
+            self.gemm(mid, blk.fc2, R, D, 4 * D, bias=blk.fc2_b, residual=x, ldr=D, out_f32=x, ldc=D)
+            self.launches += 3
+
+    def _alloc_decoder_state(self, B, R):
+        d, dev = self.dims, self.dev
+        D, H, L = d.n_text_state, d.n_text_head, d.n_text_layer
+        f32 = dict(dtype=torch.float32, device=dev)
+        return dict(
+            hs=SB16(R, D, dev), att=SB16(R, D, dev), mid=SB16(R, 4 * D, dev),
+            qkv=torch.empty((R, 3 * D), **f32), q=torch.empty((R, D), **f32),
+            sk=[torch.zeros((B, H, d.n_text_ctx, 64), **f32) for _ in range(L)],
+            sv=[torch.zeros((B, H, d.n_text_ctx, 64), **f32) for _ in range(L)],
+            ck=[torch.empty((B, H, N_CTX_AUDIO, 64), **f32) for _ in range(L)],
+            cv=[torch.empty((B, H, N_CTX_AUDIO, 64), **f32) for _ in range(L)])
+
+    def _cross_kv(self, xa, st8, B):
+        d = self.dims
+        D, H = d.n_text_state, d.n_text_head
+        for li, blk in enumerate(self.w.dec):
+            c = blk.cross
+            for (wt, bias, dst) in ((c.k, None, st8["ck"][li]), (c.v, c.v_b, st8["cv"][li])):
+                self.gemm(xa, wt, 1500, D, D, batch=(B, 1), a_b=(1500 * D, 0), bias=bias, out_f32=dst, ldc=64,
+                          c_b=(H * 1500 * 64, 0), head_dim=64, head_stride=1500 * 64)
+
+    def _final_logits(self, x_rows, n_rows, logits):
+        """LN + tied-embedding projection of `n_rows` float32 rows -> logits [n_rows, V]."""
+        d, w = self.dims, self.w
+        D, V = d.n_text_state, d.n_vocab
+        hs = SB16(n_rows, D, self.dev)
+        self.layernorm(x_rows, w.ln_g, w.ln_b, n_rows, D, out_sb=hs)
+        self.gemm(hs, w.emb_sb, n_rows, V, D, out_f32=logits, ldc=V)
+
+    def decode_windows(self, jobs, setup):
+        out = []
+        for i in range(0, len(jobs), self.max_batch):
+            out.extend(self._decode_batch(jobs[i:i + self.max_batch], setup))
+        return out
+
+    @torch.no_grad()
+    def _decode_batch(self, jobs, setup):
+        d, dev, st, w = self.dims, self.dev, self._st(), self.w
+        tok = setup.tokenizer
+        B = len(jobs)
+        D, V = d.n_text_state, d.n_vocab
+        n_ctx = d.n_text_ctx
+        sample_len = setup.sample_len
+        qk_rows = sample_len + 1
+        n_slots = len(self.m.heads)
+        xa = self.encode(jobs)
+
+        prompts = [list(j["prompt"]) for j in jobs]
+        P = [len(p) for p in prompts]
+        R0 = sum(P)
+        st8 = self._alloc_decoder_state(B, max(R0, B))
+        self._cross_kv(xa, st8, B)
+        del xa
+        qk_buf = torch.zeros((B, n_slots, qk_rows, N_CTX_AUDIO), dtype=torch.float32, device=dev)
+
+        # ---- token state
+        tokens_h = np.zeros((B, n_ctx + 1), dtype=np.int32)
+        for b, p in enumerate(prompts):
+            tokens_h[b, :len(p)] = p
+        tokens = torch.from_numpy(tokens_h).to(dev)
+        n_tokens = _i32(P, dev)
+        n_prompt = _i32(P, dev)
+        done = torch.zeros(B, dtype=torch.int32, device=dev)
+        logprobs = torch.zeros((B, qk_rows), dtype=torch.float32, device=dev)
+        full = torch.empty((B, qk_rows, V), dtype=torch.float32, device=dev) if self.keep_full_logprobs else None
+        suppress = torch.zeros(V, dtype=torch.uint8, device=dev)
+        suppress[torch.as_tensor(list(setup.suppress_tokens), dtype=torch.long, device=dev)] = 1
+        blank = torch.zeros(V, dtype=torch.uint8, device=dev)
+        if setup.blank_tokens:
+            blank[torch.as_tensor(list(setup.blank_tokens), dtype=torch.long, device=dev)] = 1
+        cfg = nat.DecodeCfg(n_vocab=V, eot=tok.eot, timestamp_begin=tok.timestamp_begin,
+                            no_timestamps=tok.no_timestamps,
+                            max_initial_ts=-1 if setup.max_initial_timestamp_index is None else setup.max_initial_timestamp_index,
+                            sample_len=sample_len, n_ctx=n_ctx, tokens_ld=n_ctx + 1)
+
+        # ---- prefill: every prompt token of every window in one ragged batch
+        row_seq = _i32([b for b, p in enumerate(prompts) for _ in p], dev)
+        row_pos = _i32([i for p in prompts for i in range(len(p))], dev)
+        row_tok = _i32([t for p in prompts for t in p], dev)
+        qk_row = _i32([0 if i == len(p) - 1 else -1 for p in prompts for i in range(len(p))], dev)
+        x = torch.empty((max(R0, B), D), dtype=torch.float32, device=dev)
+        nat.check(nat.lib.wts_embed(row_tok.data_ptr(), row_pos.data_ptr(), w.emb.data_ptr(), w.dec_pos.data_ptr(), R0, D,
+                                    x.data_ptr(), st), "wts_embed")
+        self._decoder_rows(st8, x, R0, row_seq, row_pos, qk_row, qk_buf)
+        ends = np.cumsum(P) - 1
+        sot_rows = [int(ends[b] - P[b] + 1 + prompts[b].index(tok.sot)) for b in range(B)]
+        sel = _i32(list(ends) + sot_rows, dev)
+        xr = torch.empty((2 * B, D), dtype=torch.float32, device=dev)
+        nat.check(nat.lib.wts_gather_rows(x.data_ptr(), D, sel.data_ptr(), 2 * B, D, xr.data_ptr(), st), "wts_gather_rows")
+        logits2 = torch.empty((2 * B, V), dtype=torch.float32, device=dev)
+        self._final_logits(xr, 2 * B, logits2)
+        no_speech = torch.zeros(B, dtype=torch.float32, device=dev)
+        if tok.no_speech is not None:
+            nat.check(nat.lib.wts_softmax_pick(logits2.data_ptr() + 4 * B * V, V, V, tok.no_speech, no_speech.data_ptr(), B, st),
+                      "wts_softmax_pick")
+
+        def select(lg):
+            nat.check(nat.lib.wts_decode_select(lg.data_ptr(), V, ctypes.byref(cfg), suppress.data_ptr(), blank.data_ptr(),
+                                                tokens.data_ptr(), n_tokens.data_ptr(), n_prompt.data_ptr(),
+                                                done.data_ptr(), logprobs.data_ptr(), qk_rows,
+                                                full.data_ptr() if full is not None else None, B, st), "wts_decode_select")
+            self.launches += 1
+
+        select(logits2)
+
+        # ---- decode steps: one row per window, identical launch sequence every step (CUDA-graph friendly)
+        s_tok = torch.zeros(B, dtype=torch.int32, device=dev)
+        s_pos = torch.zeros(B, dtype=torch.int32, device=dev)
+        s_qkr = torch.zeros(B, dtype=torch.int32, device=dev)
+        seq_ids = _i32(list(range(B)), dev)
+        logits = torch.empty((B, V), dtype=torch.float32, device=dev)
+        xs = torch.empty((B, D), dtype=torch.float32, device=dev)
+
+        def step():
+            nat.check(nat.lib.wts_step_inputs(tokens.data_ptr(), n_ctx + 1, n_tokens.data_ptr(), n_prompt.data_ptr(),
+                                              done.data_ptr(), B, s_tok.data_ptr(), s_pos.data_ptr(), s_qkr.data_ptr(), st),
+                      "wts_step_inputs")
+            nat.check(nat.lib.wts_embed(s_tok.data_ptr(), s_pos.data_ptr(), w.emb.data_ptr(), w.dec_pos.data_ptr(), B, D,
+                                        xs.data_ptr(), st), "wts_embed")
+            self._decoder_rows(st8, xs, B, seq_ids, s_pos, s_qkr, qk_buf)
+            self._final_logits_static(xs, B, logits, st8)
+            select(logits)
+
+        st8["hs_fin"] = SB16(B, D, dev)
+        max_steps = sample_len - 1
+        steps_done = 0
+        graph = None
+        if self.use_graph and max_steps > 4:
+            step()                       # warm-up outside capture
+            steps_done = 1
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            cap_stream = torch.cuda.Stream(device=dev)
+            cap_stream.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(cap_stream):
+                st = self._st()
+                with torch.cuda.graph(graph, stream=cap_stream):
+                    step()               # recorded, not executed
+            st = self._st()
+            torch.cuda.current_stream(dev).wait_stream(cap_stream)
+        while steps_done < max_steps:
+            chunk = min(8, max_steps - steps_done)
+            for _ in range(chunk):
+                if graph is not None:
+                    graph.replay()
+                else:
+                    step()
+            steps_done += chunk
+            if bool((done != 0).all().item()):
+                break
+
+        # ---- collect
+        torch.cuda.synchronize(dev)
+        tokens_h = tokens.cpu().numpy()
+        n_tok_h = n_tokens.cpu().numpy()
+        done_h = done.cpu().numpy()
+        lp_h = logprobs.cpu().numpy()
+        ns_h = no_speech.cpu().numpy()
+        buf_idx = len(self.qk_buffers)
+        self.qk_buffers.append(qk_buf)
+        if full is not None:
+            self.full_logprobs.append(full)
+        records = []
+        for b, job in enumerate(jobs):
+            n = int(n_tok_h[b] - P[b])
+            ended = int(done_h[b]) == 1
+            rows = n + 1 if ended else n
+            sampled = tokens_h[b, P[b]:P[b] + n].tolist()
+            gid = len(self.window_index)
+            self.window_index.append((buf_idx, b))
+            last_lp = None
+            if full is not None:
+                last_lp = (lambda t, bb=b, rr=rows - 1, ff=full: float(ff[bb, rr, t].item()))
+            records.append(WindowRecord(seek=job["seek"], segment_size=job["segment_size"], prompt=prompts[b],
+                                        tokens=sampled, logprobs=lp_h[b, :rows].copy(), ended_by_eot=ended,
+                                        no_speech_prob=float(ns_h[b]), qk_window=gid, temperature=0.0,
+                                        language=tok.language, last_row_logprobs=last_lp))
+        return records
+
+    def _final_logits_static(self, x_rows, n_rows, logits, st8):
+        d, w = self.dims, self.w
+        hs = st8["hs_fin"]
+        self.layernorm(x_rows, w.ln_g, w.ln_b, n_rows, d.n_text_state, out_sb=hs)
+        self.gemm(hs, w.emb_sb, n_rows, d.n_vocab, d.n_text_state, out_f32=logits, ldc=d.n_vocab)
+
+    # ------------------------------------------------------------------ language detection
+    @torch.no_grad()
+    def detect_language(self, mel, tokenizer):
+        """Upstream detect_language on the first 30 s: logits at <|startoftranscript|>, softmax over the
+        language tokens (T.py:862-867 exposes the same numbers as language_probs)."""
+        d, dev, st, w = self.dims, self.dev, self._st(), self.w
+        size = min(N_FRAMES, int(mel.shape[0]))
+        job = dict(mel=mel, seek=0, segment_size=size)
+        xa = self.encode([job])
+        st8 = self._alloc_decoder_state(1, 1)
+        self._cross_kv(xa, st8, 1)
+        qk_buf = torch.zeros((1, max(1, len(self.m.heads)), 1, N_CTX_AUDIO), dtype=torch.float32, device=dev)
+        x = torch.empty((1, d.n_text_state), dtype=torch.float32, device=dev)
+        one = _i32([0], dev)
+        t = _i32([tokenizer.sot], dev)
+        nat.check(nat.lib.wts_embed(t.data_ptr(), one.data_ptr(), w.emb.data_ptr(), w.dec_pos.data_ptr(), 1, d.n_text_state,
+                                    x.data_ptr(), st), "wts_embed")
+        self._decoder_rows(st8, x, 1, one, one, _i32([-1], dev), qk_buf)
+        logits = torch.empty((1, d.n_vocab), dtype=torch.float32, device=dev)
+        self._final_logits(x, 1, logits)
+        lg = logits[0].cpu()
+        ids = list(tokenizer.all_language_tokens)
+        probs = torch.softmax(lg[ids].float(), dim=-1).tolist()
+        language_probs = dict(zip(tokenizer.all_language_codes, probs))
+        return max(language_probs, key=language_probs.get), language_probs
+
+    # ------------------------------------------------------------------ alignment
+    def align(self, items):
+        """items: dicts(window=global window id, row0, last_row, T, f0, F, max_dur) -> list of jumps arrays."""
+        out = [None] * len(items)
+        groups = {}
+        for i, it in enumerate(items):
+            buf, b = self.window_index[it["window"]]
+            groups.setdefault(buf, []).append((i, b, it))
+        for buf, lst in groups.items():
+            plan = plan_segments([(b, it["row0"], it["last_row"], it["T"], it["f0"], it["F"], it["max_dur"])
+                                  for (_, b, it) in lst])
+            qk = self.qk_buffers[buf]
+            cost = attn_prep(qk, plan)
+            res = dtw(cost, plan)
+            jumps = split_jumps(res["jumps"].cpu().numpy(), plan)
+            self.launches += 3
+            for (i, _, _), j in zip(lst, jumps):
+                out[i] = j
+        return out
+
+    def release(self):
+        self.qk_buffers.clear()
+        self.window_index.clear()
+        self.full_logprobs.clear()
