@@ -33,7 +33,7 @@ def run_case(path, **extra):
     return g, res
 
 
-def compare(res, ref, conf_tol=0.0015, time_tol=0.0):
+def compare(res, ref, conf_tol=0.0015, time_tol=0.0, prob_tol=1e-5):
     assert res["language"] == ref["language"]
     assert res["text"] == ref["text"]
     assert len(res["segments"]) == len(ref["segments"])
@@ -55,7 +55,7 @@ def compare(res, ref, conf_tol=0.0015, time_tol=0.0):
             assert abs(x["confidence"] - y["confidence"]) <= conf_tol, (a["id"], x, y)
     if "language_probs" in ref:
         for k, v in ref["language_probs"].items():
-            assert abs(res["language_probs"][k] - v) < 1e-5
+            assert abs(res["language_probs"][k] - v) < prob_tol
 
 
 @pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[4:-5] for p in CASES])

@@ -1,14 +1,322 @@
-// tcgen05 tensor-core GEMM (placeholder until the kernel lands: reports an error so that nothing
-// silently falls back).
+// tcgen05 tensor-core GEMM for sm_100a:  C = act(alpha * A * B^T + bias) + residual  on SB16 operands.
+//
+// Error-compensated bf16x3: every float32 operand value travels as hi + lo bfloat16 planes and each
+// k-step issues three UMMAs into the same TMEM accumulator:  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo
+// (the dropped lo*lo term is ~2^-16 relative).  That keeps logits and cross-attention scores within
+// the 1e-3 bar of the reference's float32 CPU path while running on the 5th-generation tensor cores.
+//
+// One CTA per 128x128 output tile, 192 threads, warp-specialised:
+//   warp 0 (one lane)  TMA producer: 4 boxes (A_hi, A_lo, B_hi, B_lo; 64 x 128 bf16, SWIZZLE_128B) per
+//                      k-block into a 3-stage shared-memory ring, completion on an mbarrier (expect_tx)
+//   warp 1 (one lane)  MMA issuer: tcgen05.mma.cta_group::1.kind::f16 M128 N128 K16, accumulator in TMEM
+//                      (128 lanes x 128 fp32 columns); tcgen05.commit releases ring slots / signals the epilogue
+//   warps 2..5         epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> alpha/bias/GELU/residual ->
+//                      float32 and/or SB16 stores (optionally head-major for the K/V caches)
+// Batched problems (two batch levels) are extra tensor-map dimensions; M/N/K tails rely on TMA zero fill.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
 #include "common.cuh"
 
 namespace wts {
 
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
+constexpr int TILE_BYTES = BM * BK * 2;                 // 16 KB: one 128 x 64 bf16 box
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;             // A_hi, A_lo, B_hi, B_lo
+constexpr int TC_THREADS = 192;
+constexpr int TC_SMEM = STAGES * STAGE_BYTES + 256 + 1024;   // ring + barriers + alignment slack
+constexpr int TMEM_COLS = 128;
+
+// ---------------------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset
+    d |= (uint64_t)1 << 46;                       // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+    return d;
+}
+
+__device__ __forceinline__ float gelu_erf_tc(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
+
+struct TcArgs {
+    WtsGemm g;
+    int a_has_bo, a_has_bi, b_has_bo, b_has_bi;   // 0 => that batch stride is 0 (operand shared): coordinate 0
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs args)
+{
+    extern __shared__ unsigned char smem_raw[];
+    const WtsGemm& g = args.g;
+    const uint32_t base = (smem_addr(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = base + STAGES * STAGE_BYTES;
+    // barriers: full[s] at +8s, empty[s] at +24+8s, tmem_full at +48, tmem pointer at +56
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int z = blockIdx.z, zo = z / g.batch_inner, zi = z - zo * g.batch_inner;
+    const int nkb = (g.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) { mbar_init(bar_base + 8 * s, 1); mbar_init(bar_base + 24 + 8 * s, 1); }
+            mbar_init(bar_base + 48, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bar_base + 56), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(bar_base + 56));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int azo = args.a_has_bo ? zo : 0, azi = args.a_has_bi ? zi : 0;
+            const int bzo = args.b_has_bo ? zo : 0, bzi = args.b_has_bi ? zi : 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES, u = kb / STAGES;
+                mbar_wait(bar_base + 24 + 8 * s, (u & 1) ^ 1);
+                const uint32_t full = bar_base + 8 * s;
+                mbar_expect_tx(full, STAGE_BYTES);
+                const uint32_t st = base + s * STAGE_BYTES;
+                tma_load_5d(st, &tmA, full, kb * BK, m0, azi, azo, 0);
+                tma_load_5d(st + TILE_BYTES, &tmA, full, kb * BK, m0, azi, azo, 1);
+                tma_load_5d(st + 2 * TILE_BYTES, &tmB, full, kb * BK, n0, bzi, bzo, 0);
+                tma_load_5d(st + 3 * TILE_BYTES, &tmB, full, kb * BK, n0, bzi, bzo, 1);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=bf16, both K-major, N=128, M=128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES, u = kb / STAGES;
+                mbar_wait(bar_base + 8 * s, u & 1);
+                tc_fence_after();
+                const uint32_t st = base + s * STAGE_BYTES;
+                const uint64_t a_hi = umma_desc(st), a_lo = umma_desc(st + TILE_BYTES);
+                const uint64_t b_hi = umma_desc(st + 2 * TILE_BYTES), b_lo = umma_desc(st + 3 * TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    const uint64_t adv = (uint64_t)(k * 2);       // 32 bytes per K=16 step, in 16-byte units
+                    umma_bf16(tmem_base, a_hi + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
+                    umma_bf16(tmem_base, a_lo + adv, b_hi + adv, idesc, 1u);
+                    umma_bf16(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
+                }
+                umma_commit(bar_base + 24 + 8 * s);                // frees the ring slot when the MMAs retire
+            }
+            umma_commit(bar_base + 48);                            // accumulator complete
+        }
+    } else {
+        // ---------------- epilogue: warp q = warp % 4 owns TMEM lanes 32q .. 32q+31 (rows of the tile)
+        const int q = warp & 3;
+        const int m = m0 + 32 * q + lane;
+        mbar_wait(bar_base + 48, 0);
+        tc_fence_after();
+        const bool row_ok = m < g.M;
+        const float* res = g.residual ? g.residual + (int64_t)zo * g.r_bo + (int64_t)zi * g.r_bi + (int64_t)m * g.ldr : nullptr;
+        float* of = g.out_f32 ? g.out_f32 + (int64_t)zo * g.c_bo + (int64_t)zi * g.c_bi : nullptr;
+        __nv_bfloat16* ob = g.out_sb16 ? reinterpret_cast<__nv_bfloat16*>(g.out_sb16) + (int64_t)zo * g.o_bo + (int64_t)zi * g.o_bi : nullptr;
+        const float bias_m = (g.bias && g.bias_on_m && row_ok) ? g.bias[m] : 0.f;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), v);
+            const int nb = n0 + 32 * c;
+            if (!row_ok || nb >= g.N) continue;
+            float y[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int n = nb + j;
+                float t = g.alpha * __uint_as_float(v[j]);
+                if (g.bias) t += g.bias_on_m ? bias_m : (n < g.N ? g.bias[n] : 0.f);
+                if (g.act == 1) t = gelu_erf_tc(t);
+                if (res && n < g.N) t += res[n];
+                y[j] = t;
+            }
+            const bool full = nb + 32 <= g.N;
+            if (of) {
+                const int64_t off = g.head_dim > 0 ? (int64_t)(nb / g.head_dim) * g.head_stride + (int64_t)m * g.ldc + (nb % g.head_dim)
+                                                   : (int64_t)m * g.ldc + nb;
+                float* dst = of + off;
+                if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (nb + j < g.N) dst[j] = y[j];
+                }
+            }
+            if (ob) {
+                const int64_t off = g.head_dim > 0 ? (int64_t)(nb / g.head_dim) * g.head_stride + (int64_t)m * g.ldo + (nb % g.head_dim)
+                                                   : (int64_t)m * g.ldo + nb;
+                __nv_bfloat16* dh = ob + off;
+                __nv_bfloat16* dl = dh + g.o_plane;
+                __align__(16) __nv_bfloat16 hi[32];
+                __align__(16) __nv_bfloat16 lo[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    hi[j] = __float2bfloat16_rn(y[j]);
+                    lo[j] = __float2bfloat16_rn(y[j] - __bfloat162float(hi[j]));
+                }
+                if (full && ((reinterpret_cast<uintptr_t>(dh) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dl) & 15) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        reinterpret_cast<uint4*>(dh)[j] = reinterpret_cast<const uint4*>(hi)[j];
+                        reinterpret_cast<uint4*>(dl)[j] = reinterpret_cast<const uint4*>(lo)[j];
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (nb + j < g.N) { dh[j] = hi[j]; dl[j] = lo[j]; }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------- host side
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode()
+{
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    });
+    return fn;
+}
+
+// 5-D bf16 map: (K, rows, inner batch, outer batch, plane); strides in ELEMENTS
+static int make_map(CUtensorMap* tm, const void* ptr, int64_t K, int64_t rows, int64_t ld, int64_t plane, int64_t n_bi,
+                    int64_t s_bi, int64_t n_bo, int64_t s_bo, const char* which)
+{
+    auto enc = get_encode();
+    if (!enc) { set_error("wts_gemm: cuTensorMapEncodeTiled entry point not available"); return -4; }
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld & 7) || (plane & 7) || (s_bi & 7) || (s_bo & 7)) {
+        set_error("wts_gemm(tc): operand %s not 16-byte aligned (ptr=%p ld=%lld plane=%lld bi=%lld bo=%lld)", which, ptr,
+                  (long long)ld, (long long)plane, (long long)s_bi, (long long)s_bo);
+        return -5;
+    }
+    const int64_t e_bi = s_bi ? n_bi : 1, e_bo = s_bo ? n_bo : 1;
+    cuuint64_t dims[5] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)e_bi, (cuuint64_t)e_bo, 2};
+    const cuuint64_t row_b = (cuuint64_t)ld * 2;
+    cuuint64_t strides[4] = {row_b, (cuuint64_t)(s_bi ? s_bi * 2 : row_b), (cuuint64_t)(s_bo ? s_bo * 2 : row_b),
+                             (cuuint64_t)plane * 2};
+    cuuint32_t box[5] = {BK, BM, 1, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("wts_gemm(tc): cuTensorMapEncodeTiled(%s) failed with %d (K=%lld rows=%lld ld=%lld plane=%lld)", which, (int)r,
+                  (long long)K, (long long)rows, (long long)ld, (long long)plane);
+        return -6;
+    }
+    return 0;
+}
+
 int gemm_tc_launch(const WtsGemm& g, cudaStream_t st)
 {
-    (void)g; (void)st;
-    set_error("wts_gemm: tcgen05 backend not built yet; pass backend=1");
-    return -3;
+    static bool attr_set = false;
+    if (!attr_set) {
+        WTS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+        attr_set = true;
+    }
+    alignas(64) CUtensorMap tmA, tmB;
+    int rc = make_map(&tmA, g.a, g.K, g.M, g.lda, g.a_plane, g.batch_inner, g.a_bi, g.batch_outer, g.a_bo, "A");
+    if (rc) return rc;
+    rc = make_map(&tmB, g.b, g.K, g.N, g.ldb, g.b_plane, g.batch_inner, g.b_bi, g.batch_outer, g.b_bo, "B");
+    if (rc) return rc;
+    TcArgs args;
+    args.g = g;
+    args.a_has_bo = g.a_bo != 0; args.a_has_bi = g.a_bi != 0;
+    args.b_has_bo = g.b_bo != 0; args.b_has_bi = g.b_bi != 0;
+    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.batch_outer * g.batch_inner);
+    gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(tmA, tmB, args);
+    WTS_LAUNCH_CHECK();
+    return 0;
 }
 
 }  // namespace wts

@@ -40,6 +40,8 @@ class CudaEngine:
         self.dims = model.dims
         self.max_batch = max_batch or int(os.environ.get("WTS_MAX_BATCH", "64"))
         self.backend = int(os.environ.get("WTS_GEMM_BACKEND", "0")) if gemm_backend is None else gemm_backend
+        # the conv GEMMs read overlapping rows (row stride < K); WTS_CONV_BACKEND picks their kernel separately
+        self.conv_backend = int(os.environ.get("WTS_CONV_BACKEND", str(self.backend)))
         self.keep_full_logprobs = keep_full_logprobs
         self.qk_buffers = []            # one [B, N, rows, 1500] float32 tensor per decode_windows call
         self.window_index = []          # global window id -> (buffer idx, b)
@@ -158,11 +160,11 @@ class CudaEngine:
         # conv1 (k=3, pad 1) + GELU: row t of the GEMM's A operand = padded rows t..t+2 (K = 3C, lda = C)
         h1 = SB16(B * 3001, D, dev)            # row 0 of every window stays zero = conv2's left padding
         self.gemm(x0, w.conv1, 3000, D, 3 * C, lda=C, batch=(B, 1), a_b=(3002 * C, 0), bias=w.conv1_b, act=1,
-                  out_sb=h1, ldo=D, o_b=(3001 * D, 0), o_off=D)
+                  out_sb=h1, ldo=D, o_b=(3001 * D, 0), o_off=D, backend=self.conv_backend)
         # conv2 (k=3, stride 2, pad 1) + GELU + positional embedding: A row t = padded rows 2t..2t+2
         x = torch.empty((B * 1500, D), dtype=torch.float32, device=dev)
         self.gemm(h1, w.conv2, 1500, D, 3 * D, lda=2 * D, batch=(B, 1), a_b=(3001 * D, 0), bias=w.conv2_b, act=1,
-                  residual=w.enc_pos, ldr=D, r_b=(0, 0), out_f32=x, ldc=D, c_b=(1500 * D, 0))
+                  residual=w.enc_pos, ldr=D, r_b=(0, 0), out_f32=x, ldc=D, c_b=(1500 * D, 0), backend=self.conv_backend)
         R = B * 1500
         hs = SB16(R, D, dev)
         qk = SB16(R, 2 * D, dev)
