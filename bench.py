@@ -3,11 +3,12 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload e2e|align] [--impl ours|reference]
 
 Workloads
+  e2e   : (default) BASELINE.json metric — audio-seconds/second of whisper_timestamped.transcribe() for
+          large-v3 on 1 h of synthetic 16 kHz audio cut into independent 30-s chunks (config 3), word
+          timestamps + confidences on; N GPUs shard the chunks (strong scaling) and gather the JSON.
   align : SURVEY.md §8(d) alignment micro-benchmark — a batch of synthetic alignment problems
           (N=10 heads, qk ~ 3*N(0,1) + monotone ridge) through wts_attn_prep_batch +
           wts_dtw_batch; reports the DTW kernel's algorithmic GB/s against the measured HBM peak.
-  e2e   : audio-seconds/second of transcribe() on synthetic audio (added once the model path
-          exists; until then `align` is the default).
 """
 import argparse
 import json
@@ -212,69 +213,276 @@ def cpu_baseline_align(args):
             "sample": f"{n} segments T={T} F={F} N={N}: scipy median + torch CPU softmax/mean/norm + oracle DTW (C)"}
 
 
+# ------------------------------------------------------------------------------- e2e workload
+
+def _dist_setup():
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    return rank, world, local
+
+
+def make_audio(seconds, seed=1234):
+    from whisper_timestamped.synthetic_audio import synthetic_speech
+    # built in 5-minute pieces so the generator stays cheap; deterministic for every rank
+    pieces = []
+    t, k = 0.0, 0
+    while t < seconds:
+        d = min(300.0, seconds - t)
+        pieces.append(synthetic_speech(d, seed=seed + k))
+        t += d
+        k += 1
+    return np.concatenate(pieces)
+
+
+def gemm_roofline(engine, peaks, reps=20):
+    """Dominant kernel = gemm_tc_kernel.  Times the encoder MLP up-projection shape (the largest FLOP share)
+    alone with CUDA events; algorithmic flops = 2*M*N*K (one float32-accurate product; the kernel issues three
+    bf16 UMMAs per product)."""
+    import torch
+    from whisper_timestamped.model import SB16
+    d = engine.dims
+    D = d.n_audio_state
+    M, N, K = 16 * 1500, 4 * D, D
+    dev = engine.dev
+    a = SB16(M, K, dev)
+    a.t.normal_()
+    blk = engine.w.enc[0]
+    out = SB16(M, N, dev)
+    for _ in range(3):
+        engine.gemm(a, blk.fc1, M, N, K, bias=blk.fc1_b, act=1, out_sb=out)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        engine.gemm(a, blk.fc1, M, N, K, bias=blk.fc1_b, act=1, out_sb=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    tf = 2.0 * M * N * K / (ms * 1e-3) / 1e12
+    return {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+            "frac": tf / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
+            "kernel": "gemm_tc_kernel (bf16x3: 3 UMMAs per float32-accurate product; tensor-pipe work = 3x achieved)",
+            "shape": [M, N, K], "ms": ms}
+
+
+def run_e2e(args, rank, world, local):
+    import torch
+    import whisper_timestamped as wt
+    from whisper_timestamped.engine import CudaEngine
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    model = wt.load_model(f"synthetic:{args.model}", device=dev)
+    eng = CudaEngine(model, max_batch=args.max_batch)
+    audio = make_audio(args.audio_seconds)
+    step_samples = int(args.chunk_seconds * 16000)
+    n_chunks = (len(audio) + step_samples - 1) // step_samples
+    lo, hi = rank * n_chunks // world, (rank + 1) * n_chunks // world
+    mine = audio[lo * step_samples: min(hi * step_samples, len(audio))]
+    offset = lo * args.chunk_seconds
+    host_audio = torch.from_numpy(mine).pin_memory()
+    dev_audio = host_audio.to(dev)
+    opts = dict(language="en", chunks=args.chunk_seconds, engine=eng)
+
+    def one(audio_in):
+        eng.release()
+        res = wt.transcribe(model, audio_in, **opts)
+        for s in res["segments"]:
+            s["start"] += offset
+            s["end"] += offset
+            for w in s.get("words", []):
+                w["start"] = round(w["start"] + offset, 2)
+                w["end"] = round(w["end"] + offset, 2)
+        if world > 1:
+            import torch.distributed as dist
+            gathered = [None] * world
+            dist.all_gather_object(gathered, json.dumps(res["segments"]))
+            if rank == 0:
+                segs = [s for g in gathered for s in json.loads(g)]
+                res = dict(res, segments=segs)
+        return res
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        res = one(dev_audio)
+    eng.profile = True
+    eng.stage_ms()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        res = one(dev_audio)
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    ms = e0.elapsed_time(e1)
+    stages = eng.stage_ms()
+    eng.profile = False
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.launches - launches0
+    # e2e through the public API with HOST audio (H2D inside) and the result dict back on the host
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        res = one(host_audio)
+    barrier()
+    e2e_wall = time.perf_counter() - t1
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms, e2e_wall * 1e3], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = t.tolist()
+    else:
+        e2e_ms = e2e_wall * 1e3
+    total_audio = float(len(audio)) / 16000.0
+    ntok = sum(len(s["tokens"]) for s in res["segments"])
+    nw = sum(len(s.get("words", [])) for s in res["segments"])
+    out = {"ms_per_step": ms / args.steps, "value": total_audio / (ms / args.steps * 1e-3),
+           "e2e_value": total_audio / (e2e_ms / args.steps * 1e-3), "stages_ms_per_step": {k: v / args.steps for k, v in stages.items()},
+           "clocks": clocks, "launches": launches, "segments": len(res["segments"]), "tokens": ntok, "words": nw,
+           "h2d": int(mine.nbytes), "d2h": int(len(json.dumps(res["segments"]))) if rank == 0 else 0, "wall_s": wall,
+           "decode_steps": getattr(eng, "decode_steps_run", 0)}
+    if rank == 0 and not args.no_roofline:
+        peaks = measured_peaks()
+        out["roofline"] = gemm_roofline(eng, peaks)
+    return out
+
+
+def cpu_baseline_e2e(args, seconds=None):
+    """The reference's CPU path (float32, batch 1, sequential windows) = oracle stand-ins for openai-whisper /
+    dtw-python driven through the same transcribe(); bounded sample, all host cores."""
+    import torch
+    from types import SimpleNamespace
+    from oracle.engine import OracleEngine, build_oracle_model
+    from whisper_timestamped import model_zoo as zoo
+    from whisper_timestamped.transcribe import transcribe_timestamped
+    seconds = seconds or args.cpu_seconds
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    dims = zoo.DIMS[args.model]
+    sd = zoo.synthetic_state_dict(dims, seed=1234)
+    heads = zoo.ALIGNMENT_HEADS[args.model]
+    om = build_oracle_model(dims, sd, heads)
+    del sd
+    eng = OracleEngine(om, heads)
+    shim = SimpleNamespace(dims=dims, is_multilingual=om.is_multilingual, num_languages=om.num_languages)
+    audio = make_audio(seconds)
+    t0 = time.perf_counter()
+    res = transcribe_timestamped(shim, audio, language="en", chunks=args.chunk_seconds, engine=eng)
+    dt = time.perf_counter() - t0
+    return {"value": seconds / dt, "unit": "audio-sec/s", "cores": cores, "kind": "port",
+            "sample": f"first {seconds:.0f} s of the same synthetic audio, {args.model} float32 on CPU "
+                      f"(oracle stand-in for openai-whisper + scipy/torch/oracle-DTW alignment), {dt:.1f} s wall, "
+                      f"{sum(len(s['tokens']) for s in res['segments'])} tokens"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="align", choices=["align"])
+    ap.add_argument("--workload", default="e2e", choices=["e2e", "align"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="large-v3")
+    ap.add_argument("--audio-seconds", type=float, default=3600.0)
+    ap.add_argument("--chunk-seconds", type=float, default=30.0)
+    ap.add_argument("--max-batch", type=int, default=128)
+    ap.add_argument("--cpu-seconds", type=float, default=60.0)
     ap.add_argument("--align-batch", type=int, default=16384)
     ap.add_argument("--align-T", type=int, default=24)
     ap.add_argument("--align-F", type=int, default=300)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    rank, world, local = _dist_setup()
 
-    rank = int(os.environ.get("RANK", 0))
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
-        dist.init_process_group("nccl")
-
+    workload_name = (f"{args.model}, {args.audio_seconds:.0f} s synthetic 16 kHz audio in independent "
+                     f"{args.chunk_seconds:.0f}-s chunks, greedy, word timestamps + confidences")
     if args.impl == "reference":
-        if rank == 0:
+        if rank != 0:
+            return
+        if args.workload == "align":
             cb = cpu_baseline_align(args)
-            print(json.dumps({"impl": "reference", "metric": "alignment segments/s (prep+DTW)", "value": cb["value"],
-                              "unit": cb["unit"], "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                              "higher_is_better": True, "cpu_baseline": cb,
-                              "config": {"workload": f"align T={args.align_T} F={args.align_F}"},
-                              "e2e": {"value": cb["value"], "unit": cb["unit"], "h2d_bytes_per_step": 0,
-                                      "d2h_bytes_per_step": 0}}))
+            metric, cfg = "alignment segments/s (prep+DTW)", {"workload": f"align T={args.align_T} F={args.align_F}"}
+        else:
+            cb = cpu_baseline_e2e(args)
+            metric, cfg = "audio-sec/s (RTF) large-v3 1h synthetic @1/2/4/8 B200; DTW GB/s vs HBM peak", {"workload": workload_name}
+        print(json.dumps({"impl": "reference", "metric": metric, "value": cb["value"], "unit": cb["unit"],
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+                          "cpu_baseline": cb, "config": cfg, "data": "synthetic", "dtype": "f32",
+                          "e2e": {"value": cb["value"], "unit": cb["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
-    res = run_align(args, rank, world)
-    vals = [res["segments_per_s"]]
-    ms = [res["ms_total"]]
     if world > 1:
         import torch
         import torch.distributed as dist
-        t = torch.tensor([res["ms_total"]], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = [t.item()]
-        vals = [args.align_batch * world / (ms[0] * 1e-3)]
-    if rank == 0:
-        peaks = res["peaks"]
-        line = {
-            "metric": "alignment segments/s (prep+DTW); DTW GB/s vs HBM peak", "value": vals[0], "unit": "segments/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms[0],
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 accumulate / f32 cost",
-            "data": "synthetic",
-            "config": {"workload": f"align: {args.align_batch} segments/GPU, T={args.align_T}, F={args.align_F}, N=10 heads",
-                       "l2": "inputs (qk %.1f GB) larger than L2" % (args.align_batch * 10 * args.align_T * 1500 * 4 / 1e9)},
-            "roofline": {"bound": "hbm", "achieved": res["dtw_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": res["dtw_gbs"] / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
-                         "kernel": "dtw_warp_kernel<float>", "ms": res["ms_dtw"]},
-            "prep": {"gbs": res["prep_gbs"], "ms": res["ms_prep"]},
-            "e2e": {"value": res["e2e_segments_per_s"], "unit": "segments/s", "h2d_bytes_per_step": res["h2d"],
-                    "d2h_bytes_per_step": res["d2h"]},
-            "gpu_launches": 3 * args.steps, "clocks": res["clocks"], "jumps_checksum": res["jumps_checksum"],
-        }
-        if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_align(args)
-        print(json.dumps(line))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl")
+
+    if args.workload == "e2e":
+        res = run_e2e(args, rank, world, local)
+        if rank == 0:
+            line = {
+                "metric": "audio-sec/s (RTF) large-v3 1h synthetic @1/2/4/8 B200; DTW GB/s vs HBM peak",
+                "value": res["value"], "unit": "audio-sec/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "bf16x3 tensor-core GEMMs (float32-accurate), f32 elsewhere, f64 DTW accumulate",
+                "data": "synthetic audio, synthetic (seeded) weights of the exact architecture",
+                "config": {"workload": workload_name, "max_batch": args.max_batch,
+                           "l2": "weights + KV caches + activations far larger than L2; every step re-reads them from HBM",
+                           "segments": res["segments"], "tokens": res["tokens"], "words": res["words"],
+                           "decode_steps": res["decode_steps"]},
+                "e2e": {"value": res["e2e_value"], "unit": "audio-sec/s", "h2d_bytes_per_step": res["h2d"],
+                        "d2h_bytes_per_step": res["d2h"]},
+                "gpu_launches": res["launches"], "clocks": res["clocks"], "stages_ms_per_step": res["stages_ms_per_step"],
+            }
+            if "roofline" in res:
+                line["roofline"] = res["roofline"]
+            if not args.no_cpu_baseline:
+                line["cpu_baseline"] = cpu_baseline_e2e(args)
+            print(json.dumps(line))
+    else:
+        res = run_align(args, rank, world)
+        vals = [res["segments_per_s"]]
+        ms = [res["ms_total"]]
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            t = torch.tensor([res["ms_total"]], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = [t.item()]
+            vals = [args.align_batch * world / (ms[0] * 1e-3)]
+        if rank == 0:
+            peaks = res["peaks"]
+            line = {
+                "metric": "alignment segments/s (prep+DTW); DTW GB/s vs HBM peak", "value": vals[0], "unit": "segments/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms[0],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 accumulate / f32 cost",
+                "data": "synthetic",
+                "config": {"workload": f"align: {args.align_batch} segments/GPU, T={args.align_T}, F={args.align_F}, N=10 heads",
+                           "l2": "inputs (qk %.1f GB) larger than L2" % (args.align_batch * 10 * args.align_T * 1500 * 4 / 1e9)},
+                "roofline": {"bound": "hbm", "achieved": res["dtw_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": res["dtw_gbs"] / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                             "kernel": "dtw_warp_kernel<float>", "ms": res["ms_dtw"]},
+                "prep": {"gbs": res["prep_gbs"], "ms": res["ms_prep"]},
+                "e2e": {"value": res["e2e_segments_per_s"], "unit": "segments/s", "h2d_bytes_per_step": res["h2d"],
+                        "d2h_bytes_per_step": res["d2h"]},
+                "gpu_launches": 3 * args.steps, "clocks": res["clocks"], "jumps_checksum": res["jumps_checksum"],
+            }
+            if not args.no_cpu_baseline:
+                line["cpu_baseline"] = cpu_baseline_align(args)
+            print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()

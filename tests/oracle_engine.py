@@ -1,135 +1,2 @@
-"""TEST-ONLY engine: implements the engine protocol of whisper_timestamped.transcribe with the
-oracle's CPU stand-in for openai-whisper (oracle/upstream/whisper) and the oracle alignment
-numerics.  It lets the product's HOST logic (windows.py, words.py, transcribe.py) run on the
-CPU-only build box and be compared with the golden outputs of the unmodified reference; the
-GPU tests use it as the per-window checker of the CUDA engine."""
-import os
-import sys
-
-import numpy as np
-import torch
-import torch.nn.functional as F
-
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-UP = os.path.join(ROOT, "oracle", "upstream")
-if UP not in sys.path:
-    sys.path.insert(0, UP)
-
-import whisper  # noqa: E402  (oracle stand-in)
-from whisper.model import disable_sdpa  # noqa: E402
-
-import oracle  # noqa: E402
-from oracle.prep import attn_cost  # noqa: E402
-from whisper_timestamped.windows import WindowRecord  # noqa: E402
-
-
-def build_oracle_model(dims, state_dict, alignment_heads):
-    m = whisper.Whisper(whisper.ModelDimensions(**dims.asdict()))
-    m.load_state_dict(state_dict)
-    mask = torch.zeros(dims.n_text_layer, dims.n_text_head, dtype=torch.bool)
-    for l, h in alignment_heads:
-        mask[l, h] = True
-    m.register_buffer("alignment_heads", mask.to_sparse(), persistent=False)
-    return m.eval()
-
-
-class _Recorder:
-    """Appended after the real logit filters: sees exactly what hook_output_logits computes
-    (T.py:871-875)."""
-
-    def __init__(self):
-        self.rows = []
-
-    def apply(self, logits, tokens):
-        self.rows.append(F.log_softmax(logits.float(), dim=-1).clone())
-
-
-class OracleEngine:
-    def __init__(self, model, alignment_heads, keep_logprobs=False):
-        self.model = model
-        self.heads = list(alignment_heads)
-        self.qk = []              # per window: float32 [N, rows, 1500]
-        self.full_logprobs = []   # per window: [rows, V] (only when keep_logprobs)
-        self.keep_logprobs = keep_logprobs
-
-    # ---- audio
-    def load_audio(self, audio):
-        if isinstance(audio, np.ndarray):
-            audio = torch.from_numpy(audio)
-        return audio.float()
-
-    def log_mel(self, audio):
-        return whisper.log_mel_spectrogram(audio, self.model.dims.n_mels, padding=whisper.audio.N_SAMPLES)
-
-    def mel_frames(self, mel):
-        return mel.shape[-1]
-
-    def detect_language(self, mel, tokenizer):
-        seg = whisper.pad_or_trim(mel, whisper.audio.N_FRAMES)
-        _, probs = self.model.detect_language(seg)
-        return max(probs, key=probs.get), probs
-
-    # ---- decode
-    @torch.no_grad()
-    def decode_windows(self, jobs, setup):
-        out = []
-        tok = setup.tokenizer
-        for job in jobs:
-            mel = job["mel"][:, job["seek"]: job["seek"] + job["segment_size"]]
-            mel = whisper.pad_or_trim(mel, whisper.audio.N_FRAMES)
-            prompt = job["prompt"]
-            ptoks = prompt[1:-len(tok.sot_sequence)] if prompt[0] == tok.sot_prev else None
-            opts = whisper.DecodingOptions(task=tok.task or "transcribe", language=tok.language or "en", temperature=0.0,
-                                           sample_len=setup.sample_len, prompt=ptoks or None, fp16=False,
-                                           suppress_tokens=list(setup.suppress_tokens) or None)
-            task = whisper.decoding.DecodingTask(self.model, opts)
-            # the product computed the suppress list itself; make the stand-in use exactly that list
-            for f in task.logit_filters:
-                if isinstance(f, whisper.decoding.SuppressTokens):
-                    f.suppress_tokens = list(setup.suppress_tokens)
-            assert list(task.initial_tokens) == list(prompt), (task.initial_tokens, prompt)
-            rec = _Recorder()
-            task.logit_filters.append(rec)
-            rows = [[] for _ in self.model.decoder.blocks]
-            hooks = []
-            for i, blk in enumerate(self.model.decoder.blocks):
-                hooks.append(blk.cross_attn.register_forward_hook(
-                    lambda layer, ins, outs, index=i: rows[index].append(outs[-1][:, :, -1:, :])))
-            try:
-                with disable_sdpa():
-                    res = task.run(mel.unsqueeze(0))[0]
-            finally:
-                for h in hooks:
-                    h.remove()
-            layers = [torch.cat(r, dim=-2)[0] for r in rows]                   # per layer [H, rows, 1500]
-            qk = torch.stack([layers[l][h] for (l, h) in self.heads]).float()  # [N, rows, 1500]
-            lp_rows = torch.cat(rec.rows, dim=0)                               # [rows, V]
-            tokens = list(res.tokens)
-            n_rows = lp_rows.shape[0]
-            ended = n_rows == len(tokens) + 1
-            chosen = tokens + ([tok.eot] if ended else [])
-            assert len(chosen) == n_rows, (len(chosen), n_rows)
-            lps = lp_rows[torch.arange(n_rows), torch.tensor(chosen)].numpy().astype(np.float32)
-            last = lp_rows[-1].clone()
-            self.qk.append(qk)
-            if self.keep_logprobs:
-                self.full_logprobs.append(lp_rows)
-            out.append(WindowRecord(seek=job["seek"], segment_size=job["segment_size"], prompt=list(prompt),
-                                    tokens=tokens, logprobs=lps, ended_by_eot=ended,
-                                    no_speech_prob=float(res.no_speech_prob), qk_window=len(self.qk) - 1,
-                                    temperature=0.0, language=tok.language,
-                                    last_row_logprobs=lambda t, last=last: float(last[t])))
-        return out
-
-    # ---- alignment numerics (oracle)
-    def align(self, items):
-        out = []
-        for it in items:
-            qk = self.qk[it["window"]]
-            T, row0, last_row = it["T"], it["row0"], it["last_row"]
-            rows = list(range(row0, row0 + T - 1)) + [last_row]
-            sel = qk[:, rows, :].numpy()
-            cost = attn_cost(sel, it["f0"], it["f0"] + it["F"], max_duration=it["max_dur"] or None)
-            _, _, jumps, _ = oracle.dtw_symmetric1(cost)
-            out.append(jumps)
-        return out
+"""Thin alias: the oracle engine lives in oracle/engine.py (test infrastructure)."""
+from oracle.engine import OracleEngine, build_oracle_model  # noqa: F401

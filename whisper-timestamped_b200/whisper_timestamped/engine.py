@@ -49,6 +49,36 @@ class CudaEngine:
         self.launches = 0
         self.use_graph = os.environ.get("WTS_CUDA_GRAPH", "1") != "0"
         self._graphs = {}
+        self.profile = False            # when set, phases are bracketed with CUDA events (stage_ms())
+        self._events = []
+
+    # ------------------------------------------------------------------ phase timers
+    class _Phase:
+        def __init__(self, eng, name):
+            self.eng, self.name = eng, name
+
+        def __enter__(self):
+            if self.eng.profile:
+                self.a = torch.cuda.Event(enable_timing=True)
+                self.b = torch.cuda.Event(enable_timing=True)
+                self.a.record(torch.cuda.current_stream(self.eng.dev))
+
+        def __exit__(self, *exc):
+            if self.eng.profile:
+                self.b.record(torch.cuda.current_stream(self.eng.dev))
+                self.eng._events.append((self.name, self.a, self.b))
+
+    def phase(self, name):
+        return CudaEngine._Phase(self, name)
+
+    def stage_ms(self, reset=True):
+        torch.cuda.synchronize(self.dev)
+        out = {}
+        for name, a, b in self._events:
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        if reset:
+            self._events = []
+        return out
 
     # ------------------------------------------------------------------ helpers
     def _st(self):
@@ -123,6 +153,10 @@ class CudaEngine:
     def log_mel(self, audio):
         """float32 time-major log-mel [frames, n_mels] of `audio` + 30 s of zero padding (upstream
         log_mel_spectrogram(audio, n_mels, padding=N_SAMPLES)); the -8 floor uses this stream's maximum."""
+        with self.phase("mel"):
+            return self._log_mel(audio)
+
+    def _log_mel(self, audio):
         dev, st = self.dev, self._st()
         n = int(audio.numel())
         total = n + N_SAMPLES
@@ -276,13 +310,15 @@ class CudaEngine:
         sample_len = setup.sample_len
         qk_rows = sample_len + 1
         n_slots = len(self.m.heads)
-        xa = self.encode(jobs)
+        with self.phase("encoder"):
+            xa = self.encode(jobs)
 
         prompts = [list(j["prompt"]) for j in jobs]
         P = [len(p) for p in prompts]
         R0 = sum(P)
         st8 = self._alloc_decoder_state(B, max(R0, B))
-        self._cross_kv(xa, st8, B)
+        with self.phase("cross_kv"):
+            self._cross_kv(xa, st8, B)
         del xa
         qk_buf = torch.zeros((B, n_slots, qk_rows, N_CTX_AUDIO), dtype=torch.float32, device=dev)
 
@@ -312,6 +348,8 @@ class CudaEngine:
         row_tok = _i32([t for p in prompts for t in p], dev)
         qk_row = _i32([0 if i == len(p) - 1 else -1 for p in prompts for i in range(len(p))], dev)
         x = torch.empty((max(R0, B), D), dtype=torch.float32, device=dev)
+        ph = self.phase("prefill")
+        ph.__enter__()
         nat.check(nat.lib.wts_embed(row_tok.data_ptr(), row_pos.data_ptr(), w.emb.data_ptr(), w.dec_pos.data_ptr(), R0, D,
                                     x.data_ptr(), st), "wts_embed")
         self._decoder_rows(st8, x, R0, row_seq, row_pos, qk_row, qk_buf)
@@ -335,6 +373,7 @@ class CudaEngine:
             self.launches += 1
 
         select(logits2)
+        ph.__exit__()
 
         # ---- decode steps: one row per window, identical launch sequence every step (CUDA-graph friendly)
         s_tok = torch.zeros(B, dtype=torch.int32, device=dev)
@@ -358,6 +397,8 @@ class CudaEngine:
         max_steps = sample_len - 1
         steps_done = 0
         graph = None
+        ph = self.phase("decode_steps")
+        ph.__enter__()
         if self.use_graph and max_steps > 4:
             step()                       # warm-up outside capture
             steps_done = 1
@@ -365,10 +406,13 @@ class CudaEngine:
             graph = torch.cuda.CUDAGraph()
             cap_stream = torch.cuda.Stream(device=dev)
             cap_stream.wait_stream(torch.cuda.current_stream(dev))
+            l0 = self.launches
             with torch.cuda.stream(cap_stream):
                 st = self._st()
                 with torch.cuda.graph(graph, stream=cap_stream):
                     step()               # recorded, not executed
+            per_step = self.launches - l0
+            self.launches = l0
             st = self._st()
             torch.cuda.current_stream(dev).wait_stream(cap_stream)
         while steps_done < max_steps:
@@ -376,12 +420,15 @@ class CudaEngine:
             for _ in range(chunk):
                 if graph is not None:
                     graph.replay()
+                    self.launches += per_step
                 else:
                     step()
             steps_done += chunk
             if bool((done != 0).all().item()):
                 break
 
+        ph.__exit__()
+        self.decode_steps_run = getattr(self, "decode_steps_run", 0) + steps_done
         # ---- collect
         torch.cuda.synchronize(dev)
         tokens_h = tokens.cpu().numpy()
@@ -454,8 +501,10 @@ class CudaEngine:
             plan = plan_segments([(b, it["row0"], it["last_row"], it["T"], it["f0"], it["F"], it["max_dur"])
                                   for (_, b, it) in lst])
             qk = self.qk_buffers[buf]
-            cost = attn_prep(qk, plan)
-            res = dtw(cost, plan)
+            with self.phase("align_prep"):
+                cost = attn_prep(qk, plan)
+            with self.phase("align_dtw"):
+                res = dtw(cost, plan)
             jumps = split_jumps(res["jumps"].cpu().numpy(), plan)
             self.launches += 3
             for (i, _, _), j in zip(lst, jumps):
