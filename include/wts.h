@@ -173,6 +173,18 @@ int wts_decoder_attention(int32_t kind, const float* d_q, int64_t ldq, const flo
                           float* d_qk_out, const int32_t* d_head_slot, int32_t n_slots, int32_t qk_rows,
                           const int32_t* d_qk_row, void* stream);
 
+/* Cross-attention with fp16 K/V caches (decode-time cross-attention is an HBM stream of K/V; fp16 halves
+ * it).  The alignment heads (d_head_slot[h] >= 0) read a float32 copy of K so the exported pre-softmax rows
+ * stay within 1e-3 of the reference; see csrc/ops.cu.
+ * wts_cross_kv_pack: float32 head-major [B][H][ctx][64] -> fp16 cache (+ float32 [B][n_slots][ctx][64] copy of
+ *                    the alignment heads when d_dst_align != NULL). */
+int wts_cross_kv_pack(const float* d_src, void* d_dst16, float* d_dst_align, const int32_t* d_head_slot,
+                      int32_t n_slots, int32_t B, int32_t H, int32_t ctx, void* stream);
+int wts_cross_attention_f16(const float* d_q, int64_t ldq, const void* d_k16, const void* d_v16,
+                            const float* d_k_align, const int32_t* d_head_slot, int32_t n_slots, int32_t ctx,
+                            const int32_t* d_row_seq, int32_t rows, int32_t H, void* d_out_sb16, int64_t ldo,
+                            int64_t o_plane, float* d_qk_out, int32_t qk_rows, const int32_t* d_qk_row, void* stream);
+
 /* Scatter new self-attention K/V rows (float32 [rows, D]) into the head-major caches at (seq, position). */
 int wts_kv_append(const float* d_k, const float* d_v, int64_t ld, const int32_t* d_row_seq,
                   const int32_t* d_row_pos, int32_t rows, int32_t H, int32_t ctx, float* d_kc, float* d_vc,

@@ -4,6 +4,7 @@
 // fused logit-filter / log-softmax / greedy-argmax step.  See include/wts.h for the reference
 // interfaces each entry replaces.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -287,6 +288,129 @@ decoder_attention_kernel(const int kind, const float* __restrict__ q, int64_t ld
     }
 }
 
+
+// -------------------------------------------------------------- cross attention, fp16 K/V caches
+// Decode-time cross-attention is a pure HBM stream of the window's K/V (1500 x 64 per head); storing
+// them in fp16 halves that stream.  Measured on the CPU oracle: fp16 K+V shift the logits by < 3e-4 but
+// the exported scores by 2.6e-3, so the ALIGNMENT heads keep a float32 copy of K (their pre-softmax
+// rows are the DTW input and must stay within 1e-3 of the reference); all other heads use fp16 K.
+__global__ void cross_kv_pack_kernel(const float* __restrict__ src, __half* __restrict__ dst16,
+                                     float* __restrict__ dst_align, const int32_t* __restrict__ head_slot,
+                                     int n_slots, int H, int ctx)
+{
+    const int bh = blockIdx.x;                      // b * H + h
+    const int b = bh / H, h = bh - b * H;
+    const float* s = src + (int64_t)bh * ctx * 64;
+    __half* d = dst16 + (int64_t)bh * ctx * 64;
+    const int slot = dst_align ? head_slot[h] : -1;
+    float* da = slot >= 0 ? dst_align + ((int64_t)b * n_slots + slot) * ctx * 64 : nullptr;
+    for (int i = threadIdx.x; i < ctx * 64; i += blockDim.x) {
+        const float v = s[i];
+        d[i] = __float2half_rn(v);
+        if (da) da[i] = v;
+    }
+}
+
+constexpr int CA_THREADS = 128;
+__global__ void __launch_bounds__(CA_THREADS)
+cross_attention_f16_kernel(const float* __restrict__ q, int64_t ldq, const __half* __restrict__ k16,
+                           const __half* __restrict__ v16, const float* __restrict__ k_align,
+                           const int32_t* __restrict__ head_slot, int n_slots, int ctx,
+                           const int32_t* __restrict__ row_seq, int H, __nv_bfloat16* __restrict__ o, int64_t ldo,
+                           int64_t o_plane, float* __restrict__ qk_out, int qk_rows, const int32_t* __restrict__ qk_row)
+{
+    extern __shared__ float sm[];
+    float* sc = sm;                 // [ctx]
+    float* qs = sm + ctx;           // [64]
+    float* red = qs + 64;           // [32]
+    float* part = red + 32;         // [16][64]
+    const int r = blockIdx.x, h = blockIdx.y;
+    const int seq = row_seq[r];
+    const int slot = head_slot[h];
+    if (threadIdx.x < 64) qs[threadIdx.x] = q[(int64_t)r * ldq + h * 64 + threadIdx.x];
+    __syncthreads();
+    float mx = -CUDART_INF_F;
+    if (slot >= 0) {
+        const float* K = k_align + ((int64_t)seq * n_slots + slot) * ctx * 64;
+        for (int j = threadIdx.x; j < ctx; j += CA_THREADS) {
+            const float4* kr = reinterpret_cast<const float4*>(K + (int64_t)j * 64);
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const float4 kv = kr[c];
+                acc += qs[4 * c] * kv.x + qs[4 * c + 1] * kv.y + qs[4 * c + 2] * kv.z + qs[4 * c + 3] * kv.w;
+            }
+            sc[j] = acc;
+            mx = fmaxf(mx, acc);
+        }
+    } else {
+        const __half* K = k16 + ((int64_t)seq * H + h) * ctx * 64;
+        for (int j = threadIdx.x; j < ctx; j += CA_THREADS) {
+            const uint4* kr = reinterpret_cast<const uint4*>(K + (int64_t)j * 64);
+            uint4 raw[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) raw[c] = kr[c];
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const __half2* h2 = reinterpret_cast<const __half2*>(&raw[c]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 f = __half22float2(h2[e]);
+                    acc += qs[8 * c + 2 * e] * f.x + qs[8 * c + 2 * e + 1] * f.y;
+                }
+            }
+            sc[j] = acc;
+            mx = fmaxf(mx, acc);
+        }
+    }
+    __syncthreads();
+    if (qk_out != nullptr && slot >= 0) {
+        const int qr = qk_row[r];
+        if (qr >= 0) {
+            float* dst = qk_out + (((int64_t)seq * n_slots + slot) * qk_rows + qr) * (int64_t)ctx;
+            for (int j = threadIdx.x; j < ctx; j += CA_THREADS) dst[j] = sc[j];
+        }
+    }
+    mx = block_reduce_max(mx, red);
+    float sum = 0.f;
+    for (int j = threadIdx.x; j < ctx; j += CA_THREADS) {
+        const float e = expf(sc[j] - mx);
+        sc[j] = e;
+        sum += e;
+    }
+    sum = block_reduce_sum(sum, red);
+    const float inv = 1.0f / sum;
+    // weighted sum of V: thread = (group g of keys, 8-channel slice c8); one 16-byte load per key
+    const int c8 = threadIdx.x & 7, g = threadIdx.x >> 3;
+    const __half* V = v16 + ((int64_t)seq * H + h) * ctx * 64 + c8 * 8;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int j = g; j < ctx; j += 16) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(V + (int64_t)j * 64);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+        const float p = sc[j];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(h2[e]);
+            acc[2 * e] += p * f.x;
+            acc[2 * e + 1] += p * f.y;
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) part[g * 64 + c8 * 8 + e] = acc[e];
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        float y = 0.f;
+#pragma unroll
+        for (int gg = 0; gg < 16; ++gg) y += part[gg * 64 + threadIdx.x];
+        y *= inv;
+        __nv_bfloat16 hi, lo;
+        split_bf16(y, hi, lo);
+        o[(int64_t)r * ldo + h * 64 + threadIdx.x] = hi;
+        o[(int64_t)r * ldo + h * 64 + threadIdx.x + o_plane] = lo;
+    }
+}
+
 __global__ void kv_append_kernel(const float* __restrict__ k, const float* __restrict__ v, int64_t ld,
                                  const int32_t* __restrict__ row_seq, const int32_t* __restrict__ row_pos, int H,
                                  int ctx, float* __restrict__ kc, float* __restrict__ vc, int64_t seq_stride)
@@ -562,6 +686,33 @@ extern "C" int wts_decoder_attention(int32_t kind, const float* d_q, int64_t ldq
     decoder_attention_kernel<<<grid, DA_THREADS, smem, (cudaStream_t)stream>>>(
         kind, d_q, ldq, d_k, d_v, seq_stride, ctx, d_row_seq, d_row_pos, H, (__nv_bfloat16*)d_out_sb16, ldo, o_plane,
         d_qk_out, d_head_slot, n_slots, qk_rows, d_qk_row);
+    WTS_LAUNCH_CHECK();
+    return 0;
+}
+
+
+extern "C" int wts_cross_kv_pack(const float* d_src, void* d_dst16, float* d_dst_align, const int32_t* d_head_slot,
+                                 int32_t n_slots, int32_t B, int32_t H, int32_t ctx, void* stream)
+{
+    if (B <= 0) return 0;
+    cross_kv_pack_kernel<<<B * H, 256, 0, (cudaStream_t)stream>>>(d_src, (__half*)d_dst16, d_dst_align, d_head_slot,
+                                                                 n_slots, H, ctx);
+    WTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int wts_cross_attention_f16(const float* d_q, int64_t ldq, const void* d_k16, const void* d_v16,
+                                       const float* d_k_align, const int32_t* d_head_slot, int32_t n_slots,
+                                       int32_t ctx, const int32_t* d_row_seq, int32_t rows, int32_t H,
+                                       void* d_out_sb16, int64_t ldo, int64_t o_plane, float* d_qk_out,
+                                       int32_t qk_rows, const int32_t* d_qk_row, void* stream)
+{
+    if (rows <= 0) return 0;
+    const size_t smem = ((size_t)ctx + 64 + 32 + 16 * 64) * sizeof(float);
+    dim3 grid(rows, H);
+    cross_attention_f16_kernel<<<grid, CA_THREADS, smem, (cudaStream_t)stream>>>(
+        d_q, ldq, (const __half*)d_k16, (const __half*)d_v16, d_k_align, d_head_slot, n_slots, ctx, d_row_seq, H,
+        (__nv_bfloat16*)d_out_sb16, ldo, o_plane, d_qk_out, qk_rows, d_qk_row);
     WTS_LAUNCH_CHECK();
     return 0;
 }

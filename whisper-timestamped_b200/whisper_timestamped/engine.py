@@ -254,11 +254,11 @@ class CudaEngine:
             self.gemm(att, a.out, R, D, D, bias=a.out_b, residual=x, ldr=D, out_f32=x, ldc=D)
             self.layernorm(x, c.ln_g, c.ln_b, R, D, out_sb=hs)
             self.gemm(hs, c.q, R, D, D, bias=c.q_b, out_f32=q, ldc=D)
-            nat.check(nat.lib.wts_decoder_attention(1, q.data_ptr(), D, st8["ck"][li].data_ptr(), st8["cv"][li].data_ptr(),
-                                                    H * N_CTX_AUDIO * 64, N_CTX_AUDIO, row_seq.data_ptr(),
-                                                    row_pos.data_ptr(), R, H, att.ptr, att.ld, att.plane,
-                                                    qk_buf.data_ptr(), w.head_slot[li].data_ptr(), n_slots,
-                                                    qk_buf.shape[2], qk_row.data_ptr(), st), "wts_decoder_attention")
+            nat.check(nat.lib.wts_cross_attention_f16(q.data_ptr(), D, st8["ck"][li].data_ptr(), st8["cv"][li].data_ptr(),
+                                                      st8["ckal"][li].data_ptr(), w.head_slot[li].data_ptr(), n_slots,
+                                                      N_CTX_AUDIO, row_seq.data_ptr(), R, H, att.ptr, att.ld, att.plane,
+                                                      qk_buf.data_ptr(), qk_buf.shape[2], qk_row.data_ptr(), st),
+                      "wts_cross_attention_f16")
             self.gemm(att, c.out, R, D, D, bias=c.out_b, residual=x, ldr=D, out_f32=x, ldc=D)
             self.layernorm(x, blk.mlp_ln_g, blk.mlp_ln_b, R, D, out_sb=hs)
             self.gemm(hs, blk.fc1, R, 4 * D, D, bias=blk.fc1_b, act=1, out_sb=mid)
@@ -274,17 +274,25 @@ class CudaEngine:
             qkv=torch.empty((R, 3 * D), **f32), q=torch.empty((R, D), **f32),
             sk=[torch.zeros((B, H, d.n_text_ctx, 64), **f32) for _ in range(L)],
             sv=[torch.zeros((B, H, d.n_text_ctx, 64), **f32) for _ in range(L)],
-            ck=[torch.empty((B, H, N_CTX_AUDIO, 64), **f32) for _ in range(L)],
-            cv=[torch.empty((B, H, N_CTX_AUDIO, 64), **f32) for _ in range(L)])
+            ck=[torch.empty((B, H, N_CTX_AUDIO, 64), dtype=torch.float16, device=dev) for _ in range(L)],
+            cv=[torch.empty((B, H, N_CTX_AUDIO, 64), dtype=torch.float16, device=dev) for _ in range(L)],
+            ckal=[torch.empty((B, max(1, len(self.m.heads)), N_CTX_AUDIO, 64), **f32) for _ in range(L)],
+            kvtmp=torch.empty((B, H, N_CTX_AUDIO, 64), **f32))
 
     def _cross_kv(self, xa, st8, B):
         d = self.dims
         D, H = d.n_text_state, d.n_text_head
         for li, blk in enumerate(self.w.dec):
             c = blk.cross
-            for (wt, bias, dst) in ((c.k, None, st8["ck"][li]), (c.v, c.v_b, st8["cv"][li])):
-                self.gemm(xa, wt, 1500, D, D, batch=(B, 1), a_b=(1500 * D, 0), bias=bias, out_f32=dst, ldc=64,
+            tmp = st8["kvtmp"]
+            n_slots = len(self.m.heads)
+            for (wt, bias, dst, al) in ((c.k, None, st8["ck"][li], st8["ckal"][li]), (c.v, c.v_b, st8["cv"][li], None)):
+                self.gemm(xa, wt, 1500, D, D, batch=(B, 1), a_b=(1500 * D, 0), bias=bias, out_f32=tmp, ldc=64,
                           c_b=(H * 1500 * 64, 0), head_dim=64, head_stride=1500 * 64)
+                nat.check(nat.lib.wts_cross_kv_pack(tmp.data_ptr(), dst.data_ptr(), al.data_ptr() if al is not None else None,
+                                                    self.w.head_slot[li].data_ptr(), n_slots, B, H, N_CTX_AUDIO, self._st()),
+                          "wts_cross_kv_pack")
+                self.launches += 1
 
     def _final_logits(self, x_rows, n_rows, logits):
         """LN + tied-embedding projection of `n_rows` float32 rows -> logits [n_rows, V]."""
