@@ -358,14 +358,33 @@ def run_e2e(args, rank, world, local):
     return out
 
 
+def _load_reference():
+    """The UNMODIFIED reference as installed by `pip install --no-deps --target baseline/_ref`,
+    imported under an alias over the oracle stand-ins for its two missing third-party dependencies."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref", "whisper_timestamped")
+    if not os.path.isdir(ref_dir):
+        return None
+    up = os.path.join(ROOT, "oracle", "upstream")
+    if up not in sys.path:
+        sys.path.insert(0, up)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("wts_reference_pkg", os.path.join(ref_dir, "__init__.py"),
+                                                  submodule_search_locations=[ref_dir])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["wts_reference_pkg"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def cpu_baseline_e2e(args, seconds=None):
-    """The reference's CPU path (float32, batch 1, sequential windows) = oracle stand-ins for openai-whisper /
-    dtw-python driven through the same transcribe(); bounded sample, all host cores."""
+    """The reference's CPU path (float32, batch 1, sequential windows, per-token hooks) on a bounded sample of the
+    same workload, all host cores.  kind "reference": the unmodified reference from baseline/_ref running over the
+    oracle stand-ins for openai-whisper / dtw-python; kind "port": the oracle engine behind the drop-in's
+    transcribe() when baseline/_ref is absent."""
     import torch
     from types import SimpleNamespace
     from oracle.engine import OracleEngine, build_oracle_model
     from whisper_timestamped import model_zoo as zoo
-    from whisper_timestamped.transcribe import transcribe_timestamped
     seconds = seconds or args.cpu_seconds
     cores = os.cpu_count()
     torch.set_num_threads(cores)
@@ -374,16 +393,29 @@ def cpu_baseline_e2e(args, seconds=None):
     heads = zoo.ALIGNMENT_HEADS[args.model]
     om = build_oracle_model(dims, sd, heads)
     del sd
-    eng = OracleEngine(om, heads)
-    shim = SimpleNamespace(dims=dims, is_multilingual=om.is_multilingual, num_languages=om.num_languages)
     audio = make_audio(seconds)
+    step = int(args.chunk_seconds * 16000)
+    ref = _load_reference()
     t0 = time.perf_counter()
-    res = transcribe_timestamped(shim, audio, language="en", chunks=args.chunk_seconds, engine=eng)
+    ntok = 0
+    if ref is not None:
+        kind = "reference"
+        for s in range(0, len(audio), step):
+            r = ref.transcribe(om, audio[s:s + step], language="en", condition_on_previous_text=False)
+            ntok += sum(len(x["tokens"]) for x in r["segments"])
+    else:
+        kind = "port"
+        from whisper_timestamped.transcribe import transcribe_timestamped
+        eng = OracleEngine(om, heads)
+        shim = SimpleNamespace(dims=dims, is_multilingual=om.is_multilingual, num_languages=om.num_languages)
+        r = transcribe_timestamped(shim, audio, language="en", chunks=args.chunk_seconds, engine=eng)
+        ntok = sum(len(x["tokens"]) for x in r["segments"])
     dt = time.perf_counter() - t0
-    return {"value": seconds / dt, "unit": "audio-sec/s", "cores": cores, "kind": "port",
-            "sample": f"first {seconds:.0f} s of the same synthetic audio, {args.model} float32 on CPU "
-                      f"(oracle stand-in for openai-whisper + scipy/torch/oracle-DTW alignment), {dt:.1f} s wall, "
-                      f"{sum(len(s['tokens']) for s in res['segments'])} tokens"}
+    how = ("unmodified reference (baseline/_ref) over the oracle stand-ins for openai-whisper/dtw-python" if kind == "reference"
+           else "oracle engine (stand-in for openai-whisper + scipy/torch/oracle-DTW alignment)")
+    return {"value": seconds / dt, "unit": "audio-sec/s", "cores": cores, "kind": kind,
+            "sample": f"first {seconds:.0f} s of the same synthetic audio in {args.chunk_seconds:.0f}-s chunks, {args.model} "
+                      f"float32 on CPU, {how}; {dt:.1f} s wall, {ntok} tokens"}
 
 
 def main():

@@ -12,7 +12,8 @@ oracle.  It is a test helper, not product code.
 import numpy as np
 
 RS = 31
-PITCH = 65
+RING = 128
+PITCH = RING + 1
 
 
 def niter_of(F):
@@ -45,21 +46,16 @@ def model_dtw(cost):
         else:
             cur[0] = bnd[0]
         acc = np.zeros(32, dtype=np.uint32)
-        a = np.zeros((16, 32), dtype=cost.dtype)
-        b = np.zeros((16, 32), dtype=cost.dtype)
         base = row0 * F
 
-        # prologue
-        off = np.minimum(lanes, F - 1).astype(np.int64)
-        for k in range(16):
-            v = flat[base + off]
-            tile[k, (lanes + k - 1) & 63] = v
-            if 1 <= k < Ts:
-                off = off + F
-        for k in range(16, 32):
-            b[k - 16] = flat[base + off]
-            if k < Ts:
-                off = off + F
+        def issue_tile(u, rows):
+            # cp.async of tile u (columns 32u..32u+31), strip rows in `rows` (tile-row k <-> strip row k-1)
+            col = np.minimum(32 * u + lanes, F - 1)
+            for k in rows:
+                tile[k, (lanes + 32 * u + k - 1) & (RING - 1)] = flat[base + (k - 1) * F + col]
+
+        issue_tile(0, range(1, Ts + 1))
+        issue_tile(1, range(1, Ts + 1))
         bndnext = np.full(32, INF)
         if not first:
             idx = 1 + lanes
@@ -70,18 +66,10 @@ def model_dtw(cost):
                 bndreg = bndnext
                 idx = 32 * (t + 1) + 1 + lanes
                 bndnext = np.where(idx < F, bnd[np.minimum(idx, F + 3)], INF)
-            off = np.minimum(32 * (t + 1) + lanes, F - 1).astype(np.int64)
-            cb = (t & 1) * 32
-            nb = 32 - cb
+            cb = (32 * t) & (RING - 1)
             for k in range(32):
-                if k < 16:
-                    tile[16 + k, (cb + 63 + lanes + 16 + k) & 63] = b[k]
-                    a[k] = flat[base + off]
-                else:
-                    tile[k - 16, (nb + 63 + lanes + k - 16) & 63] = a[k - 16]
-                    b[k - 16] = flat[base + off]
-                if 1 <= k < Ts:
-                    off = off + F
+                if 1 <= k <= Ts:
+                    issue_tile(t + 2, [k])
                 s = 32 * t + k
                 l = tile[lanes, cb + k].astype(np.float64)
                 # staging check: every active cell must see its own cost value

@@ -14,12 +14,12 @@
 // warp sweeps anti-diagonals.  Lane 0 plays the row above the strip (+inf for the first strip,
 // the previous strip's last row otherwise), so `up` is one shfl_up and `diag` is last step's
 // `up`; +inf stands for dtw-python's NaN "no predecessor" (never wins a strict '<').
-// Local costs are staged through shared memory: each 32-column tile is read from HBM with
-// fully coalesced 128-byte row segments 16..32 steps before it is consumed and parked in a
-// 64-slot circular row buffer, SKEWED by the row index: element (row L, column j) lives in slot
-// (j+L-1)&63 = s&63, so the read of step s is `row_base + 4*(s&63)` for every lane (an immediate
-// offset, no address arithmetic in the dependent chain) and the odd row pitch of 65 words puts
-// the 32 lanes on 32 distinct banks.  Directions are packed 2 bits/cell in "skewed" words (field = step index),
+// Local costs are staged through shared memory: each 32-column tile is fetched from HBM with
+// fully coalesced 128-byte row segments by cp.async (LDGSTS) two tiles (>= 63 steps) before it is
+// consumed and parked in a 128-slot circular row buffer, SKEWED by the row index: element
+// (row L, column j) lives in slot (j+L-1)&127 = s&127, so the read of step s is
+// `row_base + 4*(s&127)` for every lane (an immediate offset, no address arithmetic in the
+// dependent chain) and the odd row pitch of 129 words puts the 32 lanes on 32 distinct banks.  Directions are packed 2 bits/cell in "skewed" words (field = step index),
 // one coalesced 128-byte store per 16 steps.  The backtrack then needs one step per TOKEN ROW
 // (not per path cell): find the previous non-horizontal move with a clz on the packed words.
 #include "common.cuh"
@@ -27,11 +27,13 @@
 namespace wts {
 
 constexpr int RS = 31;         // matrix rows per strip (lanes 1..31)
-constexpr int DTW_WARPS = 4;   // warps (= matrices) per CTA
-constexpr int PITCH = 65;      // shared-memory words per lane row (64 slots + 1 pad: odd pitch)
-constexpr int TILE_WORDS = 33 * 64;           // per-warp staging buffer (32 rows x 65), multiple of 64 elements
+constexpr int DTW_WARPS = 2;   // warps (= matrices) per CTA
+constexpr int DS_WORDS = 24;   // direction words per lane row kept in shared memory (covers F <= 354 single-strip)
+constexpr int RING = 128;      // slots per lane row: 4 tiles of 32 columns
+constexpr int PITCH = RING + 1; // odd row pitch (words): the 32 lanes of a diagonal read hit 32 banks
+constexpr int TILE_WORDS = 33 * 128;          // per-warp staging buffer (32 rows x 129 <= 33*128), 512-B multiple
 #ifndef DTW_MIN_CTAS
-#define DTW_MIN_CTAS 5
+#define DTW_MIN_CTAS 3
 #endif
 
 __host__ __device__ inline int dtw_nstrips(int T) { return (T + RS - 1) / RS; }
@@ -41,59 +43,60 @@ __host__ __device__ inline int dtw_wpr(int F) { return 2 * dtw_niter(F); }   // 
 __device__ __forceinline__ double dinf() { return __longlong_as_double(0x7ff0000000000000LL); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-template <typename TIn> __device__ __forceinline__ void sts(uint32_t addr, TIn v);
-template <> __device__ __forceinline__ void sts<float>(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
-template <> __device__ __forceinline__ void sts<double>(uint32_t addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
 template <typename TIn> __device__ __forceinline__ TIn lds(uint32_t addr);
 template <> __device__ __forceinline__ float lds<float>(uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory"); return v; }
 template <> __device__ __forceinline__ double lds<double>(uint32_t addr) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory"); return v; }
+template <int BYTES> __device__ __forceinline__ void cp_async(uint32_t dst, const void* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst), "l"(src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// One 31-row strip.  `tile_a` is the shared-memory byte address of this warp's staging buffer
-// (aligned to 64*sizeof(TIn) so the slot index can be OR-ed in).
+// One 31-row strip.  Staging: 32-column tiles are fetched with cp.async (LDGSTS) TWO tiles (>= 63 steps) ahead
+// of their first use into a 128-slot ring per row, skewed by the row index: element (row L, column j) lives in
+// slot (j+L-1)&127 = step&127, so step s reads `row_base + (s&127)*ES` for every lane (immediate offsets, and an
+// odd row pitch => 32 distinct banks).  Loads are clamped (column to F-1, rows beyond the strip are skipped) so
+// every issued address is valid; cells outside the matrix only ever see finite values and are never consumed.
 template <typename TIn, bool FIRST, bool WRITE_BND>
 __device__ __forceinline__ void dtw_fill_strip(const TIn* __restrict__ C, const int F, const int row0,
                                                const int Ts, const int niter, const uint32_t tile_a,
                                                uint32_t* __restrict__ dirs_strip,
                                                double* __restrict__ bnd, const int lane)
 {
-    constexpr uint32_t ES = sizeof(TIn);             // element size
-    constexpr uint32_t ROWB = PITCH * ES;            // row pitch in bytes
-    constexpr uint32_t SLOTMASK = 63u * ES;
+    constexpr uint32_t ES = sizeof(TIn);
+    constexpr uint32_t ROWB = PITCH * ES;
+    constexpr uint32_t SLOTMASK = (RING - 1) * ES;
     const double INF = dinf();
     double cur = INF, upprev = INF;
     if (FIRST && lane == 1) upprev = 0.0;            // seeds cm[0,0] = 0 + lm[0,0]
     if (!FIRST && lane == 0) cur = __ldcg(bnd);      // cm[row0-1, 0]
     uint32_t acc = 0;
-    const uint32_t myrow_a = tile_a + lane * ROWB;   // this lane's row
+    const uint32_t myrow_a = tile_a + lane * ROWB;
     const uint32_t laneb = lane * ES;
-    TIn a[16], b[16];
-
-    // All staging loads are unconditional: rows are clamped to the strip's last row and columns
-    // to F-1, so out-of-range cells see finite duplicates (their results are never consumed).
-    const char* Cb = reinterpret_cast<const char*>(C + (int64_t)row0 * F);   // warp-uniform
+    const char* Cb = reinterpret_cast<const char*>(C + (int64_t)row0 * F);   // strip row 0 (= tile row 1)
     const uint32_t Fb = (uint32_t)F * ES;
 
-    // prologue: tile 0 (columns 0..31): rows 0..15 go straight to smem, rows 16..31 wait in b[]
-    {
-        uint32_t off = (uint32_t)min(lane, F - 1) * ES;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const TIn v = *reinterpret_cast<const TIn*>(Cb + off);
-            sts<TIn>((tile_a | ((laneb + (k - 1) * ES) & SLOTMASK)) + k * ROWB, v);
-            off += (k >= 1 && k < Ts) ? Fb : 0u;
-        }
-#pragma unroll
-        for (int k = 16; k < 32; ++k) {
-            b[k - 16] = *reinterpret_cast<const TIn*>(Cb + off);
-            off += (k < Ts) ? Fb : 0u;
-        }
+    // issue tile `u` (columns 32u..32u+31) of strip rows 0..Ts-1: one warp-wide 4/8-byte cp.async per row
+    auto issue_row = [&](int u, int k, uint32_t roff) {
+        // tile row k (1..Ts) <-> strip row k-1; destination slot (col + k - 1) & (RING-1)
+        const uint32_t col = (uint32_t)min(32 * u + lane, F - 1);
+        const uint32_t slotb = (laneb + (uint32_t)(32 * u + k - 1) * ES) & SLOTMASK;
+        cp_async<ES>(tile_a + k * ROWB + slotb, Cb + roff + col * ES);
+    };
+
+    // prologue: tiles 0 and 1
+#pragma unroll 1
+    for (int u = 0; u < 2; ++u) {
+        uint32_t roff = 0;
+        for (int k = 1; k <= Ts; ++k) { issue_row(u, k, roff); roff += Fb; }
+        cp_async_commit();
     }
     double bndreg = INF, bndnext = INF;
     if (!FIRST) {
         const int idx = 1 + lane;
         bndnext = idx < F ? __ldcg(bnd + idx) : INF;
     }
-    __syncwarp();
 
     for (int t = 0; t < niter; ++t) {
         if (!FIRST) {
@@ -101,22 +104,19 @@ __device__ __forceinline__ void dtw_fill_strip(const TIn* __restrict__ C, const 
             const int idx = 32 * (t + 1) + 1 + lane;
             bndnext = idx < F ? __ldcg(bnd + idx) : INF;
         }
-        uint32_t off = (uint32_t)min(32 * (t + 1) + lane, F - 1) * ES;   // tile-row 1 (= strip row 0)
-        const uint32_t cb = (t & 1) * 32, nb = 32 - cb;
-        const uint32_t rd_a = myrow_a + cb * ES;      // slot (s & 63) of step k is rd_a + k*ES
-        const uint32_t wcur = laneb + (cb + 63) * ES, wnext = laneb + (nb + 63) * ES;   // (+63 == -1 mod 64)
+        cp_async_wait<1>();                          // tile t has landed (tile t+1 may still be in flight)
+        __syncwarp();
+        const uint32_t rd_a = myrow_a + (uint32_t)((32 * t) & (RING - 1)) * ES;
+        // tile t+2 goes out during this iteration, one row per step
+        const uint32_t colb = (uint32_t)min(32 * (t + 2) + lane, F - 1) * ES;
+        const uint32_t slot0 = laneb + (uint32_t)(32 * (t + 2) + RING - 1) * ES;   // (+RING-1 == -1 mod RING)
+        const char* src = Cb + colb;
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
-            // ---- software-pipelined prefetch of tile t+1 (loads issued 16 steps before the store)
-            if (k < 16) {
-                sts<TIn>((tile_a | ((wcur + (16 + k) * ES) & SLOTMASK)) + (16 + k) * ROWB, b[k]);
-                a[k] = *reinterpret_cast<const TIn*>(Cb + off);
-            } else {
-                sts<TIn>((tile_a | ((wnext + (k - 16) * ES) & SLOTMASK)) + (k - 16) * ROWB, a[k - 16]);
-                b[k - 16] = *reinterpret_cast<const TIn*>(Cb + off);
+            if (k >= 1 && k <= Ts) {
+                cp_async<ES>(tile_a + k * ROWB + ((slot0 + k * ES) & SLOTMASK), src);
+                src += Fb;
             }
-            off += (k >= 1 && k < Ts) ? Fb : 0u;
-            __syncwarp();
             // ---- one anti-diagonal
             const int s = 32 * t + k;
             const double l = (double)lds<TIn>(rd_a + k * ES);
@@ -142,7 +142,9 @@ __device__ __forceinline__ void dtw_fill_strip(const TIn* __restrict__ C, const 
                 if (lane == 0) cur = ub;             // cm[row0-1, s+1]
             }
         }
+        cp_async_commit();
     }
+    cp_async_wait<0>();
 }
 
 // Direction fields (2 bits per cell, field index = step & 15): bit0 = "left beats diag",
@@ -158,7 +160,7 @@ __device__ __forceinline__ uint32_t dtw_dir_at(const uint32_t* dirs, int W, int 
 {
     const int strip = i / RS, ln = i - strip * RS + 1;
     const int s = j + ln - 1;
-    const uint32_t x = __ldcg(dirs + ((int64_t)strip * W + (s >> 4)) * 32 + ln);
+    const uint32_t x = dirs[((int64_t)strip * W + (s >> 4)) * 32 + ln];
     const uint32_t f = (x >> (2 * (s & 15))) & 3u;
     return (f & 2u) ? 3u : ((f & 1u) ? 2u : 1u);
 }
@@ -174,19 +176,22 @@ dtw_warp_kernel(const TIn* __restrict__ cost, const WtsSegDesc* __restrict__ seg
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     TIn* tile = reinterpret_cast<TIn*>(smem_raw) + warp * TILE_WORDS;
     const uint32_t tile_a = smem_u32(tile);
+    uint32_t* dirs_sm = reinterpret_cast<uint32_t*>(smem_raw + (size_t)DTW_WARPS * TILE_WORDS * sizeof(TIn)) + warp * (DS_WORDS * 32);
     const int seg = blockIdx.x * DTW_WARPS + warp;
     if (seg >= nseg) return;
 
     const WtsSegDesc sd = segs[seg];
     const int T = sd.T, F = sd.F;
     const TIn* C = cost + sd.cost_off;
-    uint32_t* dirs = dir_ws + sd.dir_off;
+    // directions live in shared memory when the whole matrix fits one strip and DS_WORDS words per row
+    // (the typical alignment problem): the row-wise backtrack then never waits on L2
+    uint32_t* dirs = (sd.T <= RS && dtw_wpr(sd.F) <= DS_WORDS) ? dirs_sm : dir_ws + sd.dir_off;
     double* bnd = bnd_ws + sd.bnd_off;
     int32_t* jumps = jumps_out + sd.jumps_off;
     if (T <= 0 || F <= 0) return;
 
     // zero the staging buffer once: cells read before their tile arrives (j < 0) must be finite
-    for (int k = lane; k < 32 * PITCH; k += 32) tile[k] = TIn(0);
+    for (int k = lane; k < TILE_WORDS; k += 32) tile[k] = TIn(0);
     __syncwarp();
 
     const int niter = dtw_niter(F);
@@ -220,7 +225,7 @@ dtw_warp_kernel(const TIn* __restrict__ cost, const WtsSegDesc* __restrict__ seg
             int w = s >> 4, pos = s & 15, kf = 0;
             uint32_t x = 0;
             while (true) {
-                x = __ldcg(base + w * 32);
+                x = base[w * 32];
                 const uint32_t m = dtw_nonleft_mask(x) & (0xffffffffu >> (30 - 2 * pos));
                 if (m) { kf = (31 - __clz(m)) >> 1; break; }
                 if (w == 0) { kf = 0; break; }
@@ -305,14 +310,15 @@ extern "C" int wts_dtw_batch(const void* d_cost, int32_t cost_is_f64, const WtsS
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = (nseg + DTW_WARPS - 1) / DTW_WARPS;
     if (cost_is_f64) {
-        const size_t smem = (size_t)DTW_WARPS * TILE_WORDS * sizeof(double);
+        const size_t smem = (size_t)DTW_WARPS * (TILE_WORDS * sizeof(double) + DS_WORDS * 32 * sizeof(uint32_t));
         WTS_CUDA_CHECK(cudaFuncSetAttribute(dtw_warp_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dtw_warp_kernel<double><<<grid, DTW_WARPS * 32, smem, st>>>(
             (const double*)d_cost, d_segs, nseg, d_dir_ws, d_bnd_ws, d_jumps, d_path, d_path_off, d_path_len);
         WTS_LAUNCH_CHECK();
         if (d_status) { dtw_status_kernel<double><<<nseg, 128, 0, st>>>((const double*)d_cost, d_segs, nseg, d_status); WTS_LAUNCH_CHECK(); }
     } else {
-        const size_t smem = (size_t)DTW_WARPS * TILE_WORDS * sizeof(float);
+        const size_t smem = (size_t)DTW_WARPS * (TILE_WORDS * sizeof(float) + DS_WORDS * 32 * sizeof(uint32_t));
+        WTS_CUDA_CHECK(cudaFuncSetAttribute(dtw_warp_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dtw_warp_kernel<float><<<grid, DTW_WARPS * 32, smem, st>>>(
             (const float*)d_cost, d_segs, nseg, d_dir_ws, d_bnd_ws, d_jumps, d_path, d_path_off, d_path_len);
         WTS_LAUNCH_CHECK();

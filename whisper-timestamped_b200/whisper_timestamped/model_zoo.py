@@ -151,6 +151,7 @@ def synthetic_state_dict(dims: ModelDimensions, seed: int = 1234, logit_spread: 
     emb[ts_begin:, 0] = ts_offset
     emb[eot, :] = 0.0
     emb[eot, 0] = eot_logit
+    emb[eot + 1:ts_begin, 0] = -30.0        # language / task / control tokens are never produced as text
     sd["decoder.token_embedding.weight"] = emb
     sd["decoder.positional_embedding"] = rnd(dims.n_text_ctx, d_t, std=logit_spread / math.sqrt(d_t - 1))
     for i in range(dims.n_text_layer):

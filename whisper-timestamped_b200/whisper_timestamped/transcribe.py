@@ -227,20 +227,31 @@ def transcribe_timestamped(
     for st in streams:
         for wi, rec in enumerate(st.records):
             nxt = st.records[wi + 1].prompt if wi + 1 < len(st.records) else None
-            plans, info = plan_window_alignment(rec, setup, nxt)
-            per_window[(st.index, wi)] = (plans, info)
-            for plan in plans:
+            reqs = {}
+
+            def yields_words(plan, reqs=reqs):
+                # T.py:540-559: `ws` is empty when there is nothing between the timestamps or every word is a
+                # special token; this only depends on the tokens, so it is known before the DTW runs
                 req = None
                 if len(plan.tokens) > 1:
                     req = W.prepare_alignment(plan.tokens, plan.n_rows, tokenizer, use_space=use_space,
                                               refine_nframes=refine_nframes,
                                               remove_punctuation_from_words=remove_punctuation_from_words,
                                               unfinished_decoding=plan.unfinished)
-                    if req is not None:
-                        for msg in req.warnings:
-                            logger.warning(msg)
-                        if rec.max_duration and req.f0 >= rec.max_duration:
-                            logger.warning("Got start time outside of audio boundary")
+                reqs[id(plan)] = req
+                if req is None:
+                    return False
+                kept = req.words[1:] if req.unfinished else req.words[1:-1]
+                return any(not w.startswith("<|") for w in kept)
+
+            plans, info = plan_window_alignment(rec, setup, nxt, yields_words)
+            per_window[(st.index, wi)] = (plans, info)
+            for plan in plans:
+                req = reqs[id(plan)]
+                for msg in req.warnings:
+                    logger.warning(msg)
+                if rec.max_duration and req.f0 >= rec.max_duration:
+                    logger.warning("Got start time outside of audio boundary")
                 pending.append((st, wi, plan, req))
     items = []
     for (st, wi, plan, req) in pending:
@@ -269,12 +280,9 @@ def transcribe_timestamped(
             ws_of_window, kept_plans = [], []
             for (_, _, plan, req) in by_window.get(wi, []):
                 ws = W.words_from_jumps(req, next(jit)) if req is not None else []
-                if ws:
-                    ws_of_window.append(ws)
-                    kept_plans.append(plan)
-                else:
-                    raise RuntimeError("a flushed segment produced no word; this path of the reference's state "
-                                       "machine (T.py:559-564 reset without segment) is not restated")
+                assert ws, "plan_window_alignment only keeps segments that yield words"
+                ws_of_window.append(ws)
+                kept_plans.append(plan)
             # chunk-level log-probs and the silence rule (T.py:712-748)
             should_skip = False
             if compute_word_confidence or no_speech_threshold is not None:

@@ -158,9 +158,16 @@ class AlignedSegmentPlan:
     appended_token: Optional[int] = None     # eot / fallback token appended by the flush logic
 
 
-def plan_window_alignment(rec: WindowRecord, setup: DecodeSetup, next_prompt: Optional[List[int]]):
+def plan_window_alignment(rec: WindowRecord, setup: DecodeSetup, next_prompt: Optional[List[int]],
+                          yields_words=None):
     """Offline equivalent of must_flush_segment / align_last_segment / reset (T.py:427-566) with
-    trust_whisper_timestamps=True.  Returns (plans, chunk_info)."""
+    trust_whisper_timestamps=True.  Returns (plans, chunk_info).
+
+    `yields_words(plan) -> bool` tells whether perform_word_alignment would return at least one word for
+    the flushed tokens (it depends on the tokens only).  When it would not, the reference does not add the
+    segment and resets its token list to EMPTY instead of keeping the closing timestamp (T.py:559-564,
+    427-442), which is replayed here — including the RuntimeError("Missing start token") the reference then
+    raises at the next flush of the same window."""
     tok = setup.tokenizer
     ts0 = tok.timestamp_begin
     S = list(rec.tokens)
@@ -188,9 +195,11 @@ def plan_window_alignment(rec: WindowRecord, setup: DecodeSetup, next_prompt: Op
                 plan = _flush(cur, rows, unfinished, rec, setup, None, mid_chunk=True)
             else:
                 plan = AlignedSegmentPlan(tokens=seg_tokens, row0=rows[0], n_rows=len(rows) - 1, unfinished=False)
-            plans.append(plan)
-            cur, rows = [cur[-1]], [rows[-1]]
-            # (a segment that yields no words resets to an empty list instead, see below)
+            if yields_words is None or yields_words(plan):
+                plans.append(plan)
+                cur, rows = [cur[-1]], [rows[-1]]
+            else:
+                cur, rows = [], []
         cur.append(t)
         rows.append(k + 1)
 
@@ -206,7 +215,10 @@ def plan_window_alignment(rec: WindowRecord, setup: DecodeSetup, next_prompt: Op
     final_plan = None
     if must_flush:
         final_plan = _flush(cur, rows, reached, rec, setup, next_prompt, last_chunk_token=last_chunk_token)
-        plans.append(final_plan)
+        if yields_words is None or yields_words(final_plan):
+            plans.append(final_plan)
+        else:
+            final_plan = None
     info = dict(n_fed=n_fed, reached=reached, last_chunk_token=last_chunk_token,
                 final_unfinished=bool(final_plan and final_plan.unfinished))
     return plans, info
