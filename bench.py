@@ -128,7 +128,7 @@ def run_align(args, rank, world):
     torch.cuda.set_device(dev)
     T, F, N, nseg = args.align_T, args.align_F, 10, args.align_batch
     qk, items = make_align_batch(nseg, T, F, N, 1234 + rank, dev)
-    plan = plan_segments(items)
+    plan = plan_segments(items, nonpositive=True)
     d_segs = _segs_to_device(plan.segs, dev)
     cost = torch.empty(plan.cost_elems, dtype=torch.float32, device=dev)
     ws = (torch.empty(plan.dir_words, dtype=torch.int32, device=dev),

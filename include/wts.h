@@ -36,7 +36,8 @@ typedef struct WtsSegDesc {
     int32_t F;         /* number of frames in the slice (= end_token - start_token)             */
     int32_t max_dur;   /* padding limit in frames (find_start_padding(mfcc)//2, T.py:1556-1558),
                           <=0 when there is no padding                                          */
-    int32_t flags;     /* reserved, 0                                                           */
+    int32_t flags;     /* bit 0: the float32 cost matrix is <= 0 everywhere with cost[0,0] < 0 (true for the
+                          output of wts_attn_prep_batch): enables the integer-compare DTW fast path  */
     int64_t cost_off;  /* element offset of this segment's [T,F] matrix in the cost buffer      */
     int64_t jumps_off; /* element offset of this segment's T+1 jumps in the jumps buffer        */
     int64_t dir_off;   /* uint32 offset of this segment's direction words in the DTW workspace  */
@@ -166,12 +167,13 @@ int wts_gather_rows(const float* d_x, int64_t ldx, const int32_t* d_idx, int32_t
  * kind 1: cross-attention over the 1500 encoder positions; when d_qk_out != NULL the PRE-softmax
  *         scores of head `h` are written to d_qk_out[(seq*N + slot)*qk_rows + qk_row[r]] for every head
  *         whose d_head_slot[h] >= 0 (= the alignment heads; replaces hook_attention_weights T.py:783-793).
- * q: float32 [rows, D] (ldq); K/V caches float32 head-major [seq][H][ctx][64]. */
+ * q: float32 [rows, D] (ldq); K/V caches float32 head-major [seq][H][ctx][64].
+ * d_row_active (may be NULL): rows with 0 are skipped (finished sequences stop streaming their K/V). */
 int wts_decoder_attention(int32_t kind, const float* d_q, int64_t ldq, const float* d_k, const float* d_v,
                           int64_t seq_stride, int32_t ctx, const int32_t* d_row_seq, const int32_t* d_row_pos,
                           int32_t rows, int32_t H, void* d_out_sb16, int64_t ldo, int64_t o_plane,
                           float* d_qk_out, const int32_t* d_head_slot, int32_t n_slots, int32_t qk_rows,
-                          const int32_t* d_qk_row, void* stream);
+                          const int32_t* d_qk_row, const int32_t* d_row_active, void* stream);
 
 /* Cross-attention with fp16 K/V caches (decode-time cross-attention is an HBM stream of K/V; fp16 halves
  * it).  The alignment heads (d_head_slot[h] >= 0) read a float32 copy of K so the exported pre-softmax rows
@@ -183,7 +185,8 @@ int wts_cross_kv_pack(const float* d_src, void* d_dst16, float* d_dst_align, con
 int wts_cross_attention_f16(const float* d_q, int64_t ldq, const void* d_k16, const void* d_v16,
                             const float* d_k_align, const int32_t* d_head_slot, int32_t n_slots, int32_t ctx,
                             const int32_t* d_row_seq, int32_t rows, int32_t H, void* d_out_sb16, int64_t ldo,
-                            int64_t o_plane, float* d_qk_out, int32_t qk_rows, const int32_t* d_qk_row, void* stream);
+                            int64_t o_plane, float* d_qk_out, int32_t qk_rows, const int32_t* d_qk_row,
+                            const int32_t* d_row_active, void* stream);
 
 /* Scatter new self-attention K/V rows (float32 [rows, D]) into the head-major caches at (seq, position). */
 int wts_kv_append(const float* d_k, const float* d_v, int64_t ld, const int32_t* d_row_seq,
@@ -206,7 +209,7 @@ int wts_decode_select(float* d_logits, int64_t ldl, const WtsDecodeCfg* cfg, con
  * qk_row[b] = number of tokens sampled so far (row that the step predicts), or -1 when the sequence is done. */
 int wts_step_inputs(const int32_t* d_tokens, int32_t tokens_ld, const int32_t* d_n_tokens, const int32_t* d_n_prompt,
                     const int32_t* d_done, int32_t B, int32_t* d_tok, int32_t* d_pos, int32_t* d_qk_row,
-                    void* stream);
+                    int32_t* d_active, void* stream);
 
 /* probability of <|nospeech|> at the <|startoftranscript|> position (T.py:856-859). */
 int wts_softmax_pick(const float* d_logits, int64_t ldl, int32_t n, int32_t index, float* d_out, int32_t rows,

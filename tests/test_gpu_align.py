@@ -128,6 +128,33 @@ def test_dtw_full_size_batch_properties():
         assert np.array_equal(res["jumps"][n], j)
 
 
+def test_dtw_nonpositive_fast_path_vs_oracle():
+    """Integer-compare fast path (flags bit 0) on strictly negative costs, incl. multi-strip and worst-case sizes."""
+    from whisper_timestamped.alignment import plan_segments, dtw, split_jumps
+    rng = np.random.default_rng(17)
+    shapes = [(1, 5), (2, 9), (24, 300), (31, 64), (32, 70), (63, 200), (100, 380), (224, 1500), (12, 12)]
+    mats = []
+    for (T, F) in shapes:
+        for kind in range(3):
+            if kind == 0:
+                c = -(rng.random((T, F), dtype=np.float32) + 1e-3)
+            elif kind == 1:
+                c = -np.ones((T, F), np.float32)                      # all ties
+            else:
+                c = -(rng.integers(1, 4, (T, F)).astype(np.float32))   # many ties
+            mats.append(c)
+    plan = plan_segments([(0, 0, None, m.shape[0], 0, m.shape[1], 0) for m in mats], nonpositive=True)
+    host = np.zeros(plan.cost_elems, dtype=np.float32)
+    for s, m in zip(plan.segs, mats):
+        host[s["cost_off"]: s["cost_off"] + m.size] = m.reshape(-1)
+    out = dtw(torch.from_numpy(host).to(_dev()), plan)
+    torch.cuda.synchronize()
+    jl = split_jumps(out["jumps"].cpu().numpy(), plan)
+    for n, m in enumerate(mats):
+        _, _, j, _ = oracle.dtw_symmetric1(m.astype(np.float64))
+        assert np.array_equal(jl[n], j), (n, m.shape)
+
+
 def test_dtw_status_flags_non_finite():
     a = -np.ones((4, 9), np.float32)
     b = a.copy()
@@ -137,15 +164,20 @@ def test_dtw_status_flags_non_finite():
 
 
 def _prep_case(qk_full, N, T, F, f0, max_dur, last_row=None):
-    """qk_full [N, Trows, 1500] float32 -> (gpu cost [T,F] float32, gpu jumps)."""
+    """qk_full [N, Trows, 1500] float32 -> (gpu cost [T,F] float32, gpu jumps).  The DTW runs twice — generic
+    float64 compares and the integer-compare fast path for non-positive costs — and both must agree."""
     from whisper_timestamped.alignment import plan_segments, attn_prep, dtw, split_jumps
     qk = torch.from_numpy(qk_full[None]).to(_dev()).contiguous()
     plan = plan_segments([(0, 0, last_row, T, f0, F, max_dur)])
     cost = attn_prep(qk, plan)
     out = dtw(cost, plan)
+    plan_fast = plan_segments([(0, 0, last_row, T, f0, F, max_dur)], nonpositive=True)
+    out_fast = dtw(cost, plan_fast)
     torch.cuda.synchronize()
     c = cost.cpu().numpy()[: T * F].reshape(T, F)
-    return c, split_jumps(out["jumps"].cpu().numpy(), plan)[0]
+    j = split_jumps(out["jumps"].cpu().numpy(), plan)[0]
+    assert np.array_equal(j, split_jumps(out_fast["jumps"].cpu().numpy(), plan_fast)[0])
+    return c, j
 
 
 def test_prep_golden_vectors():
@@ -198,7 +230,7 @@ def test_prep_batch_many_segments_one_launch():
         f0 = int(rng.integers(0, 1500 - F))
         md = int(rng.integers(1, F + 60)) if k % 3 == 0 else 0
         items.append((k % W, row0, None, T, f0, F, md))
-    plan = plan_segments(items)
+    plan = plan_segments(items, nonpositive=True)
     d_qk = torch.from_numpy(qk).to(_dev())
     cost = attn_prep(d_qk, plan)
     out = dtw(cost, plan)

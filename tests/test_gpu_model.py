@@ -67,6 +67,29 @@ def test_gemm_backends_vs_torch(backend):
         assert (osb.to_f32().double() - ref).abs().max().item() <= 3e-4 * max(1.0, scale)
 
 
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_gemm_skinny_inplace_residual(backend):
+    """Decode-time shape: one M tile, x += A W^T + b in place (the tensor-core path narrows the N tile and
+    splits K with float32 atomics)."""
+    from whisper_timestamped.model import SB16
+    from whisper_timestamped.engine import CudaEngine
+    dev = torch.device("cuda:0")
+    eng = CudaEngine.__new__(CudaEngine)
+    eng.dev, eng.backend, eng.launches = dev, backend, 0
+    g = torch.Generator(device="cpu").manual_seed(9)
+    for (M, N, K) in [(20, 1280, 5120), (120, 1280, 1280), (3, 384, 1536), (128, 3840, 1280)]:
+        a = torch.randn(M, K, generator=g).to(dev)
+        b = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev)
+        bias = torch.randn(N, generator=g).to(dev)
+        x = torch.randn(M, N, generator=g).to(dev)
+        A, Bm = SB16.from_f32(a), SB16.from_f32(b)
+        ref = x.double() + A.to_f32().double() @ Bm.to_f32().double().T + bias.double()
+        eng.gemm(A, Bm, M, N, K, bias=bias, residual=x, ldr=N, out_f32=x, ldc=N)
+        torch.cuda.synchronize()
+        err = (x.double() - ref).abs().max().item()
+        assert err <= 2e-4 * max(1.0, ref.abs().max().item()), (M, N, K, err)
+
+
 @pytest.mark.parametrize("backend", BACKENDS[:1])
 def test_log_mel_matches_oracle(tiny, backend):
     from whisper_timestamped.synthetic_audio import synthetic_speech

@@ -15,11 +15,11 @@
 // the previous strip's last row otherwise), so `up` is one shfl_up and `diag` is last step's
 // `up`; +inf stands for dtw-python's NaN "no predecessor" (never wins a strict '<').
 // Local costs are staged through shared memory: each 32-column tile is fetched from HBM with
-// fully coalesced 128-byte row segments by cp.async (LDGSTS) two tiles (>= 63 steps) before it is
-// consumed and parked in a 128-slot circular row buffer, SKEWED by the row index: element
-// (row L, column j) lives in slot (j+L-1)&127 = s&127, so the read of step s is
-// `row_base + 4*(s&127)` for every lane (an immediate offset, no address arithmetic in the
-// dependent chain) and the odd row pitch of 129 words puts the 32 lanes on 32 distinct banks.  Directions are packed 2 bits/cell in "skewed" words (field = step index),
+// fully coalesced 128-byte row segments by cp.async (LDGSTS) 31 steps before it is consumed and
+// parked in a 64-slot circular row buffer, SKEWED by the row index: element (row L, column j)
+// lives in slot (j+L-1)&63 = s&63, so the read of step s is `row_base + 4*(s&63)` for every lane
+// (an immediate offset, no address arithmetic in the dependent chain) and the odd row pitch of 65
+// words puts the 32 lanes on 32 distinct banks.  Directions are packed 2 bits/cell in "skewed" words (field = step index),
 // one coalesced 128-byte store per 16 steps.  The backtrack then needs one step per TOKEN ROW
 // (not per path cell): find the previous non-horizontal move with a clz on the packed words.
 #include "common.cuh"
@@ -29,11 +29,11 @@ namespace wts {
 constexpr int RS = 31;         // matrix rows per strip (lanes 1..31)
 constexpr int DTW_WARPS = 2;   // warps (= matrices) per CTA
 constexpr int DS_WORDS = 24;   // direction words per lane row kept in shared memory (covers F <= 354 single-strip)
-constexpr int RING = 128;      // slots per lane row: 4 tiles of 32 columns
+constexpr int RING = 64;       // slots per lane row: 2 tiles of 32 columns
 constexpr int PITCH = RING + 1; // odd row pitch (words): the 32 lanes of a diagonal read hit 32 banks
-constexpr int TILE_WORDS = 33 * 128;          // per-warp staging buffer (32 rows x 129 <= 33*128), 512-B multiple
+constexpr int TILE_WORDS = 33 * 64;           // per-warp staging buffer (32 rows x 65 <= 33*64), 256-B multiple
 #ifndef DTW_MIN_CTAS
-#define DTW_MIN_CTAS 3
+#define DTW_MIN_CTAS 9
 #endif
 
 __host__ __device__ inline int dtw_nstrips(int T) { return (T + RS - 1) / RS; }
@@ -53,12 +53,18 @@ template <int BYTES> __device__ __forceinline__ void cp_async(uint32_t dst, cons
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// One 31-row strip.  Staging: 32-column tiles are fetched with cp.async (LDGSTS) TWO tiles (>= 63 steps) ahead
-// of their first use into a 128-slot ring per row, skewed by the row index: element (row L, column j) lives in
-// slot (j+L-1)&127 = step&127, so step s reads `row_base + (s&127)*ES` for every lane (immediate offsets, and an
-// odd row pitch => 32 distinct banks).  Loads are clamped (column to F-1, rows beyond the strip are skipped) so
-// every issued address is valid; cells outside the matrix only ever see finite values and are never consumed.
-template <typename TIn, bool FIRST, bool WRITE_BND>
+// One 31-row strip.  Staging: row k of the next 32-column tile is fetched with one warp-wide cp.async (LDGSTS)
+// at step k of the current tile, i.e. 31 steps before its first use, into a 64-slot ring per row, skewed by the
+// row index: element (row L, column j) lives in slot (j+L-1)&63 = step&63, so step s reads
+// `row_base + (s&63)*ES` for every lane (immediate offsets; the odd row pitch gives 32 distinct banks).  The slot a
+// row overwrites was last read two steps earlier.  Two commit groups per tile (rows 1-15, rows 16-31) keep every
+// wait_group at least 16 steps behind its loads.  Loads are clamped (column to F-1, rows beyond the strip skipped)
+// so every issued address is valid; cells outside the matrix only see finite values and are never consumed.
+//
+// NEG: all local costs are <= 0 and cost[0,0] < 0 (what the attention post-processing produces), hence every
+// accumulated cost is a strictly negative double (or +inf for "no predecessor") and  a < b  <=>  bits(a) >u bits(b).
+// The two fp64 compares of the dependent chain become integer compares (same results bit for bit).
+template <typename TIn, bool FIRST, bool WRITE_BND, bool NEG>
 __device__ __forceinline__ void dtw_fill_strip(const TIn* __restrict__ C, const int F, const int row0,
                                                const int Ts, const int niter, const uint32_t tile_a,
                                                uint32_t* __restrict__ dirs_strip,
@@ -77,19 +83,13 @@ __device__ __forceinline__ void dtw_fill_strip(const TIn* __restrict__ C, const 
     const char* Cb = reinterpret_cast<const char*>(C + (int64_t)row0 * F);   // strip row 0 (= tile row 1)
     const uint32_t Fb = (uint32_t)F * ES;
 
-    // issue tile `u` (columns 32u..32u+31) of strip rows 0..Ts-1: one warp-wide 4/8-byte cp.async per row
-    auto issue_row = [&](int u, int k, uint32_t roff) {
-        // tile row k (1..Ts) <-> strip row k-1; destination slot (col + k - 1) & (RING-1)
-        const uint32_t col = (uint32_t)min(32 * u + lane, F - 1);
-        const uint32_t slotb = (laneb + (uint32_t)(32 * u + k - 1) * ES) & SLOTMASK;
-        cp_async<ES>(tile_a + k * ROWB + slotb, Cb + roff + col * ES);
-    };
-
-    // prologue: tiles 0 and 1
-#pragma unroll 1
-    for (int u = 0; u < 2; ++u) {
-        uint32_t roff = 0;
-        for (int k = 1; k <= Ts; ++k) { issue_row(u, k, roff); roff += Fb; }
+    // prologue: tile 0 (all rows), one group
+    {
+        const char* src = Cb + (uint32_t)min(lane, F - 1) * ES;
+        for (int k = 1; k <= Ts; ++k) {
+            cp_async<ES>(tile_a + k * ROWB + ((laneb + (uint32_t)(k - 1) * ES) & SLOTMASK), src);
+            src += Fb;
+        }
         cp_async_commit();
     }
     double bndreg = INF, bndnext = INF;
@@ -104,19 +104,19 @@ __device__ __forceinline__ void dtw_fill_strip(const TIn* __restrict__ C, const 
             const int idx = 32 * (t + 1) + 1 + lane;
             bndnext = idx < F ? __ldcg(bnd + idx) : INF;
         }
-        cp_async_wait<1>();                          // tile t has landed (tile t+1 may still be in flight)
+        // tile t: rows 1..15 were committed >= 16 steps ago (group A), rows 16..31 are group B (waited at k = 15)
+        if (t == 0) cp_async_wait<0>(); else cp_async_wait<1>();
         __syncwarp();
         const uint32_t rd_a = myrow_a + (uint32_t)((32 * t) & (RING - 1)) * ES;
-        // tile t+2 goes out during this iteration, one row per step
-        const uint32_t colb = (uint32_t)min(32 * (t + 2) + lane, F - 1) * ES;
-        const uint32_t slot0 = laneb + (uint32_t)(32 * (t + 2) + RING - 1) * ES;   // (+RING-1 == -1 mod RING)
-        const char* src = Cb + colb;
+        const uint32_t slot0 = laneb + (uint32_t)(32 * (t + 1) + RING - 1) * ES;   // (+RING-1 == -1 mod RING)
+        const char* src = Cb + (uint32_t)min(32 * (t + 1) + lane, F - 1) * ES;
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
-            if (k >= 1 && k <= Ts) {
+            if (k >= 1 && k <= Ts) {                  // row k of tile t+1; its slot was last read at step k-2
                 cp_async<ES>(tile_a + k * ROWB + ((slot0 + k * ES) & SLOTMASK), src);
                 src += Fb;
             }
+            if (k == 15) { cp_async_commit(); cp_async_wait<1>(); __syncwarp(); }   // group A out; tile t group B landed
             // ---- one anti-diagonal
             const int s = 32 * t + k;
             const double l = (double)lds<TIn>(rd_a + k * ES);
@@ -124,10 +124,19 @@ __device__ __forceinline__ void dtw_fill_strip(const TIn* __restrict__ C, const 
             const double diag = upprev;
             upprev = up;
             const double c1 = diag + l, c2 = cur + l, c3 = up + l;
-            const bool p2 = c2 < c1;                  // left beats diag
-            const double m = p2 ? c2 : c1;
-            const bool p3 = c3 < m;                   // up beats both
-            const double best = p3 ? c3 : m;
+            bool p2, p3;
+            double m, best;
+            if (NEG) {
+                p2 = (unsigned long long)__double_as_longlong(c2) > (unsigned long long)__double_as_longlong(c1);
+                m = p2 ? c2 : c1;
+                p3 = (unsigned long long)__double_as_longlong(c3) > (unsigned long long)__double_as_longlong(m);
+                best = p3 ? c3 : m;
+            } else {
+                p2 = c2 < c1;                         // left beats diag
+                m = p2 ? c2 : c1;
+                p3 = c3 < m;                          // up beats both
+                best = p3 ? c3 : m;
+            }
             cur = best;
             if ((k & 15) == 0) acc = 0;
             if (p2) acc |= 1u << (2 * (k & 15));
@@ -142,7 +151,7 @@ __device__ __forceinline__ void dtw_fill_strip(const TIn* __restrict__ C, const 
                 if (lane == 0) cur = ub;             // cm[row0-1, s+1]
             }
         }
-        cp_async_commit();
+        cp_async_commit();                            // group B of tile t+1
     }
     cp_async_wait<0>();
 }
@@ -202,12 +211,21 @@ dtw_warp_kernel(const TIn* __restrict__ cost, const WtsSegDesc* __restrict__ seg
         const int Ts = min(RS, T - row0);
         uint32_t* ds = dirs + (int64_t)strip * W * 32;
         const bool more = strip + 1 < nstrips;
-        if (strip == 0) {
-            if (more) dtw_fill_strip<TIn, true, true>(C, F, row0, Ts, niter, tile_a, ds, bnd, lane);
-            else      dtw_fill_strip<TIn, true, false>(C, F, row0, Ts, niter, tile_a, ds, bnd, lane);
+        const bool neg = (sizeof(TIn) == 4) && (sd.flags & 1);
+        if (neg) {
+            if (strip == 0) {
+                if (more) dtw_fill_strip<TIn, true, true, true>(C, F, row0, Ts, niter, tile_a, ds, bnd, lane);
+                else      dtw_fill_strip<TIn, true, false, true>(C, F, row0, Ts, niter, tile_a, ds, bnd, lane);
+            } else {
+                if (more) dtw_fill_strip<TIn, false, true, true>(C, F, row0, Ts, niter, tile_a, ds, bnd, lane);
+                else      dtw_fill_strip<TIn, false, false, true>(C, F, row0, Ts, niter, tile_a, ds, bnd, lane);
+            }
+        } else if (strip == 0) {
+            if (more) dtw_fill_strip<TIn, true, true, false>(C, F, row0, Ts, niter, tile_a, ds, bnd, lane);
+            else      dtw_fill_strip<TIn, true, false, false>(C, F, row0, Ts, niter, tile_a, ds, bnd, lane);
         } else {
-            if (more) dtw_fill_strip<TIn, false, true>(C, F, row0, Ts, niter, tile_a, ds, bnd, lane);
-            else      dtw_fill_strip<TIn, false, false>(C, F, row0, Ts, niter, tile_a, ds, bnd, lane);
+            if (more) dtw_fill_strip<TIn, false, true, false>(C, F, row0, Ts, niter, tile_a, ds, bnd, lane);
+            else      dtw_fill_strip<TIn, false, false, false>(C, F, row0, Ts, niter, tile_a, ds, bnd, lane);
         }
         __syncwarp();
     }

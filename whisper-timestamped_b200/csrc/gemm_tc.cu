@@ -18,17 +18,24 @@
 #include <cudaTypedefs.h>
 
 #include <mutex>
+#include <stdlib.h>
 
 #include "common.cuh"
 
 namespace wts {
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
-constexpr int TILE_BYTES = BM * BK * 2;                 // 16 KB: one 128 x 64 bf16 box
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;             // A_hi, A_lo, B_hi, B_lo
+constexpr int BM = 128, BK = 64;
+constexpr int TILE_BYTES = BM * BK * 2;                 // 16 KB: one 128 x 64 bf16 box (A planes)
 constexpr int TC_THREADS = 192;
-constexpr int TC_SMEM = STAGES * STAGE_BYTES + 256 + 1024;   // ring + barriers + alignment slack
-constexpr int TMEM_COLS = 128;
+// Two instantiations: BN = 128 (3-stage ring) for the big encoder GEMMs, BN = 32 (5-stage ring, optional
+// split-K) for the skinny decode GEMMs (M <= 128) where the CTA count, not the tensor pipe, limits throughput.
+template <int BN> struct TcCfg {
+    static constexpr int STAGES = BN >= 128 ? 3 : 5;
+    static constexpr int B_TILE = BN * BK * 2;
+    static constexpr int STAGE_BYTES = 2 * TILE_BYTES + 2 * B_TILE;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 256 + 1024;
+    static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+};
 
 // ---------------------------------------------------------------------------------------------- PTX
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -107,20 +114,30 @@ __device__ __forceinline__ float gelu_erf_tc(float v) { return 0.5f * v * (1.0f 
 struct TcArgs {
     WtsGemm g;
     int a_has_bo, a_has_bi, b_has_bo, b_has_bi;   // 0 => that batch stride is 0 (operand shared): coordinate 0
+    int split_k;                                  // > 1: blockIdx.z is a K split (batch must be 1); partial sums
+                                                  // are reduced with float32 atomics into out_f32 (which already
+                                                  // holds the residual)
 };
 
+template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs args)
 {
+    using Cfg = TcCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES, STAGE_BYTES = Cfg::STAGE_BYTES, B_TILE = Cfg::B_TILE, TMEM_COLS = Cfg::TMEM_COLS;
     extern __shared__ unsigned char smem_raw[];
     const WtsGemm& g = args.g;
     const uint32_t base = (smem_addr(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = base + STAGES * STAGE_BYTES;
-    // barriers: full[s] at +8s, empty[s] at +24+8s, tmem_full at +48, tmem pointer at +56
+    // barriers: full[s] at +8s, empty[s] at +64+8s, tmem_full at +128, tmem pointer at +136
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int z = blockIdx.z, zo = z / g.batch_inner, zi = z - zo * g.batch_inner;
-    const int nkb = (g.K + BK - 1) / BK;
+    const bool split = args.split_k > 1;
+    const int z = split ? 0 : blockIdx.z, zo = z / g.batch_inner, zi = z - zo * g.batch_inner;
+    const int nkb_all = (g.K + BK - 1) / BK;
+    const int kb0 = split ? (int)((int64_t)blockIdx.z * nkb_all / args.split_k) : 0;
+    const int kb1 = split ? (int)((int64_t)(blockIdx.z + 1) * nkb_all / args.split_k) : nkb_all;
+    const int nkb = kb1 - kb0;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -128,19 +145,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < STAGES; ++s) { mbar_init(bar_base + 8 * s, 1); mbar_init(bar_base + 24 + 8 * s, 1); }
-            mbar_init(bar_base + 48, 1);
+            for (int s = 0; s < STAGES; ++s) { mbar_init(bar_base + 8 * s, 1); mbar_init(bar_base + 64 + 8 * s, 1); }
+            mbar_init(bar_base + 128, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bar_base + 56), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bar_base + 136), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     uint32_t tmem_base;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(bar_base + 56));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(bar_base + 136));
 
     if (warp == 0) {
         if (lane == 0) {
@@ -148,14 +165,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int bzo = args.b_has_bo ? zo : 0, bzi = args.b_has_bi ? zi : 0;
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES, u = kb / STAGES;
-                mbar_wait(bar_base + 24 + 8 * s, (u & 1) ^ 1);
+                mbar_wait(bar_base + 64 + 8 * s, (u & 1) ^ 1);
                 const uint32_t full = bar_base + 8 * s;
                 mbar_expect_tx(full, STAGE_BYTES);
                 const uint32_t st = base + s * STAGE_BYTES;
-                tma_load_5d(st, &tmA, full, kb * BK, m0, azi, azo, 0);
-                tma_load_5d(st + TILE_BYTES, &tmA, full, kb * BK, m0, azi, azo, 1);
-                tma_load_5d(st + 2 * TILE_BYTES, &tmB, full, kb * BK, n0, bzi, bzo, 0);
-                tma_load_5d(st + 3 * TILE_BYTES, &tmB, full, kb * BK, n0, bzi, bzo, 1);
+                const int kc = (kb0 + kb) * BK;
+                tma_load_5d(st, &tmA, full, kc, m0, azi, azo, 0);
+                tma_load_5d(st + TILE_BYTES, &tmA, full, kc, m0, azi, azo, 1);
+                tma_load_5d(st + 2 * TILE_BYTES, &tmB, full, kc, n0, bzi, bzo, 0);
+                tma_load_5d(st + 2 * TILE_BYTES + B_TILE, &tmB, full, kc, n0, bzi, bzo, 1);
             }
         }
     } else if (warp == 1) {
@@ -168,7 +186,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_after();
                 const uint32_t st = base + s * STAGE_BYTES;
                 const uint64_t a_hi = umma_desc(st), a_lo = umma_desc(st + TILE_BYTES);
-                const uint64_t b_hi = umma_desc(st + 2 * TILE_BYTES), b_lo = umma_desc(st + 3 * TILE_BYTES);
+                const uint64_t b_hi = umma_desc(st + 2 * TILE_BYTES), b_lo = umma_desc(st + 2 * TILE_BYTES + B_TILE);
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k) {
                     const uint64_t adv = (uint64_t)(k * 2);       // 32 bytes per K=16 step, in 16-byte units
@@ -176,15 +194,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     umma_bf16(tmem_base, a_lo + adv, b_hi + adv, idesc, 1u);
                     umma_bf16(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
                 }
-                umma_commit(bar_base + 24 + 8 * s);                // frees the ring slot when the MMAs retire
+                umma_commit(bar_base + 64 + 8 * s);                // frees the ring slot when the MMAs retire
             }
-            umma_commit(bar_base + 48);                            // accumulator complete
+            umma_commit(bar_base + 128);                           // accumulator complete
         }
     } else {
         // ---------------- epilogue: warp q = warp % 4 owns TMEM lanes 32q .. 32q+31 (rows of the tile)
         const int q = warp & 3;
         const int m = m0 + 32 * q + lane;
-        mbar_wait(bar_base + 48, 0);
+        mbar_wait(bar_base + 128, 0);
         tc_fence_after();
         const bool row_ok = m < g.M;
         const float* res = g.residual ? g.residual + (int64_t)zo * g.r_bo + (int64_t)zi * g.r_bi + (int64_t)m * g.ldr : nullptr;
@@ -198,6 +216,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int nb = n0 + 32 * c;
             if (!row_ok || nb >= g.N) continue;
             float y[32];
+            if (split) {
+                // split-K partial: out_f32 already holds the residual; the first split also adds the bias
+                float* dst = of + (int64_t)m * g.ldc + nb;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int n = nb + j;
+                    float t = g.alpha * __uint_as_float(v[j]);
+                    if (g.bias && blockIdx.z == 0) t += g.bias_on_m ? bias_m : (n < g.N ? g.bias[n] : 0.f);
+                    if (n < g.N) atomicAdd(dst + j, t);
+                }
+                continue;
+            }
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const int n = nb + j;
@@ -270,7 +300,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode()
 
 // 5-D bf16 map: (K, rows, inner batch, outer batch, plane); strides in ELEMENTS
 static int make_map(CUtensorMap* tm, const void* ptr, int64_t K, int64_t rows, int64_t ld, int64_t plane, int64_t n_bi,
-                    int64_t s_bi, int64_t n_bo, int64_t s_bo, const char* which)
+                    int64_t s_bi, int64_t n_bo, int64_t s_bo, int box_rows, const char* which)
 {
     auto enc = get_encode();
     if (!enc) { set_error("wts_gemm: cuTensorMapEncodeTiled entry point not available"); return -4; }
@@ -284,7 +314,7 @@ static int make_map(CUtensorMap* tm, const void* ptr, int64_t K, int64_t rows, i
     const cuuint64_t row_b = (cuuint64_t)ld * 2;
     cuuint64_t strides[4] = {row_b, (cuuint64_t)(s_bi ? s_bi * 2 : row_b), (cuuint64_t)(s_bo ? s_bo * 2 : row_b),
                              (cuuint64_t)plane * 2};
-    cuuint32_t box[5] = {BK, BM, 1, 1, 1};
+    cuuint32_t box[5] = {BK, (cuuint32_t)box_rows, 1, 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -297,26 +327,49 @@ static int make_map(CUtensorMap* tm, const void* ptr, int64_t K, int64_t rows, i
     return 0;
 }
 
-int gemm_tc_launch(const WtsGemm& g, cudaStream_t st)
+template <int BN>
+static int launch_bn(const WtsGemm& g, cudaStream_t st, int split_k)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        WTS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+        WTS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM));
         attr_set = true;
     }
     alignas(64) CUtensorMap tmA, tmB;
-    int rc = make_map(&tmA, g.a, g.K, g.M, g.lda, g.a_plane, g.batch_inner, g.a_bi, g.batch_outer, g.a_bo, "A");
+    int rc = make_map(&tmA, g.a, g.K, g.M, g.lda, g.a_plane, g.batch_inner, g.a_bi, g.batch_outer, g.a_bo, BM, "A");
     if (rc) return rc;
-    rc = make_map(&tmB, g.b, g.K, g.N, g.ldb, g.b_plane, g.batch_inner, g.b_bi, g.batch_outer, g.b_bo, "B");
+    rc = make_map(&tmB, g.b, g.K, g.N, g.ldb, g.b_plane, g.batch_inner, g.b_bi, g.batch_outer, g.b_bo, BN, "B");
     if (rc) return rc;
     TcArgs args;
     args.g = g;
     args.a_has_bo = g.a_bo != 0; args.a_has_bi = g.a_bi != 0;
     args.b_has_bo = g.b_bo != 0; args.b_has_bi = g.b_bi != 0;
-    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.batch_outer * g.batch_inner);
-    gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(tmA, tmB, args);
+    args.split_k = split_k;
+    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, split_k > 1 ? split_k : g.batch_outer * g.batch_inner);
+    gemm_tc_kernel<BN><<<grid, TC_THREADS, TcCfg<BN>::SMEM, st>>>(tmA, tmB, args);
     WTS_LAUNCH_CHECK();
     return 0;
+}
+
+int gemm_tc_launch(const WtsGemm& g, cudaStream_t st)
+{
+    static const int skinny = []{ const char* e = getenv("WTS_SKINNY_GEMM"); return e ? atoi(e) : 1; }();
+    static const int splitk = []{ const char* e = getenv("WTS_SPLITK"); return e ? atoi(e) : 1; }();
+    const bool one_batch = g.batch_outer * g.batch_inner == 1;
+    if (skinny && g.M <= BM && one_batch) {
+        // decode-time GEMM: one M tile.  Narrow N tiles for CTA count; split K when the epilogue is the linear
+        // in-place residual update (x += A W^T + b), reduced with float32 atomics.
+        int split = 1;
+        const int tiles = (g.N + 31) / 32, nkb = (g.K + BK - 1) / BK;
+        if (splitk && g.out_f32 && g.residual == g.out_f32 && g.act == 0 && !g.out_sb16 && g.head_dim == 0 && tiles < 148) {
+            split = (148 + tiles - 1) / tiles;
+            if (split > nkb / 4) split = nkb / 4;
+            if (split > 8) split = 8;
+            if (split < 1) split = 1;
+        }
+        return launch_bn<32>(g, st, split);
+    }
+    return launch_bn<128>(g, st, 1);
 }
 
 }  // namespace wts

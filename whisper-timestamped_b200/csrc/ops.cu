@@ -55,7 +55,9 @@ __global__ void to_sb16_kernel(const float* __restrict__ x, int64_t n, __nv_bflo
 }
 
 // ---------------------------------------------------------------------------------------- layernorm
-// one warp per row; float32 statistics (mean, biased variance), eps = 1e-5
+// one warp per row; float32 statistics (mean, biased variance), eps = 1e-5.  The row is read once into
+// registers (D <= 1280), so a LayerNorm is a single memory round trip.
+constexpr int LN_MAXV = 40;
 __global__ void __launch_bounds__(128)
 layernorm_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ gamma,
                  const float* __restrict__ beta, int M, int D, __nv_bfloat16* __restrict__ o, int64_t ldo,
@@ -64,21 +66,36 @@ layernorm_kernel(const float* __restrict__ x, int64_t ldx, const float* __restri
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= M) return;
     const float* xr = x + (int64_t)row * ldx;
+    float v[LN_MAXV];
     float s = 0.f;
-    for (int c = lane; c < D; c += 32) s += xr[c];
+#pragma unroll
+    for (int k = 0; k < LN_MAXV; ++k) {
+        const int c = lane + 32 * k;
+        v[k] = c < D ? xr[c] : 0.f;
+        s += v[k];
+    }
     const float mean = warp_sum(s) / (float)D;
-    float v = 0.f;
-    for (int c = lane; c < D; c += 32) { const float d = xr[c] - mean; v += d * d; }
-    const float rstd = 1.0f / sqrtf(warp_sum(v) / (float)D + 1e-5f);
-    for (int c = lane; c < D; c += 32) {
-        const float y = (xr[c] - mean) * rstd * gamma[c] + beta[c];
-        if (o) {
-            __nv_bfloat16 h, l;
-            split_bf16(y, h, l);
-            o[(int64_t)row * ldo + c] = h;
-            o[(int64_t)row * ldo + c + o_plane] = l;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_MAXV; ++k) {
+        const int c = lane + 32 * k;
+        const float d = c < D ? v[k] - mean : 0.f;
+        q += d * d;
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)D + 1e-5f);
+#pragma unroll
+    for (int k = 0; k < LN_MAXV; ++k) {
+        const int c = lane + 32 * k;
+        if (c < D) {
+            const float y = (v[k] - mean) * rstd * gamma[c] + beta[c];
+            if (o) {
+                __nv_bfloat16 h, l;
+                split_bf16(y, h, l);
+                o[(int64_t)row * ldo + c] = h;
+                o[(int64_t)row * ldo + c + o_plane] = l;
+            }
+            if (of) of[(int64_t)row * ldf + c] = y;
         }
-        if (of) of[(int64_t)row * ldf + c] = y;
     }
 }
 
@@ -230,7 +247,7 @@ decoder_attention_kernel(const int kind, const float* __restrict__ q, int64_t ld
                          const int32_t* __restrict__ row_seq, const int32_t* __restrict__ row_pos, int H,
                          __nv_bfloat16* __restrict__ o, int64_t ldo, int64_t o_plane, float* __restrict__ qk_out,
                          const int32_t* __restrict__ head_slot, int n_slots, int qk_rows,
-                         const int32_t* __restrict__ qk_row)
+                         const int32_t* __restrict__ qk_row, const int32_t* __restrict__ row_active)
 {
     extern __shared__ float sm[];
     float* sc = sm;                 // [ctx] scores
@@ -238,6 +255,7 @@ decoder_attention_kernel(const int kind, const float* __restrict__ q, int64_t ld
     float* red = qs + 64;           // [32]
     float* part = red + 32;         // [2][64]
     const int r = blockIdx.x, h = blockIdx.y;
+    if (row_active != nullptr && !row_active[r]) return;
     const int seq = row_seq[r];
     const int nk = kind == 0 ? row_pos[r] + 1 : ctx;
     const float* K = kc + (int64_t)seq * seq_stride + (int64_t)h * ctx * 64;
@@ -317,7 +335,8 @@ cross_attention_f16_kernel(const float* __restrict__ q, int64_t ldq, const __hal
                            const __half* __restrict__ v16, const float* __restrict__ k_align,
                            const int32_t* __restrict__ head_slot, int n_slots, int ctx,
                            const int32_t* __restrict__ row_seq, int H, __nv_bfloat16* __restrict__ o, int64_t ldo,
-                           int64_t o_plane, float* __restrict__ qk_out, int qk_rows, const int32_t* __restrict__ qk_row)
+                           int64_t o_plane, float* __restrict__ qk_out, int qk_rows, const int32_t* __restrict__ qk_row,
+                           const int32_t* __restrict__ row_active)
 {
     extern __shared__ float sm[];
     float* sc = sm;                 // [ctx]
@@ -325,6 +344,7 @@ cross_attention_f16_kernel(const float* __restrict__ q, int64_t ldq, const __hal
     float* red = qs + 64;           // [32]
     float* part = red + 32;         // [16][64]
     const int r = blockIdx.x, h = blockIdx.y;
+    if (row_active != nullptr && !row_active[r]) return;   // finished sequence: skip its K/V stream
     const int seq = row_seq[r];
     const int slot = head_slot[h];
     if (threadIdx.x < 64) qs[threadIdx.x] = q[(int64_t)r * ldq + h * 64 + threadIdx.x];
@@ -544,7 +564,8 @@ decode_select_kernel(float* __restrict__ logits, int64_t ldl, const WtsDecodeCfg
 
 __global__ void step_inputs_kernel(const int32_t* __restrict__ tokens, int ld, const int32_t* __restrict__ n_tokens,
                                    const int32_t* __restrict__ n_prompt, const int32_t* __restrict__ done, int B,
-                                   int32_t* __restrict__ tok, int32_t* __restrict__ pos, int32_t* __restrict__ qk_row)
+                                   int32_t* __restrict__ tok, int32_t* __restrict__ pos, int32_t* __restrict__ qk_row,
+                                   int32_t* __restrict__ active)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
@@ -552,6 +573,7 @@ __global__ void step_inputs_kernel(const int32_t* __restrict__ tokens, int ld, c
     tok[b] = tokens[(int64_t)b * ld + nt - 1];
     pos[b] = nt - 1;
     qk_row[b] = done[b] ? -1 : nt - n_prompt[b];
+    if (active) active[b] = done[b] ? 0 : 1;
 }
 
 __global__ void softmax_pick_kernel(const float* __restrict__ logits, int64_t ldl, int n, int index,
@@ -591,6 +613,7 @@ extern "C" int wts_layernorm(const float* d_x, int64_t ldx, const float* d_gamma
                              int64_t ldf, void* stream)
 {
     if (M <= 0) return 0;
+    if (D > 32 * LN_MAXV) { set_error("wts_layernorm: D=%d > %d", D, 32 * LN_MAXV); return -2; }
     layernorm_kernel<<<(M + 3) / 4, 128, 0, (cudaStream_t)stream>>>(d_x, ldx, d_gamma, d_beta, M, D,
                                                                    (__nv_bfloat16*)d_out_sb16, ldo, o_plane, d_out_f32, ldf);
     WTS_LAUNCH_CHECK();
@@ -678,14 +701,14 @@ extern "C" int wts_decoder_attention(int32_t kind, const float* d_q, int64_t ldq
                                      int64_t seq_stride, int32_t ctx, const int32_t* d_row_seq,
                                      const int32_t* d_row_pos, int32_t rows, int32_t H, void* d_out_sb16, int64_t ldo,
                                      int64_t o_plane, float* d_qk_out, const int32_t* d_head_slot, int32_t n_slots,
-                                     int32_t qk_rows, const int32_t* d_qk_row, void* stream)
+                                     int32_t qk_rows, const int32_t* d_qk_row, const int32_t* d_row_active, void* stream)
 {
     if (rows <= 0) return 0;
     const size_t smem = ((size_t)ctx + 64 + 32 + 128) * sizeof(float);
     dim3 grid(rows, H);
     decoder_attention_kernel<<<grid, DA_THREADS, smem, (cudaStream_t)stream>>>(
         kind, d_q, ldq, d_k, d_v, seq_stride, ctx, d_row_seq, d_row_pos, H, (__nv_bfloat16*)d_out_sb16, ldo, o_plane,
-        d_qk_out, d_head_slot, n_slots, qk_rows, d_qk_row);
+        d_qk_out, d_head_slot, n_slots, qk_rows, d_qk_row, d_row_active);
     WTS_LAUNCH_CHECK();
     return 0;
 }
@@ -705,14 +728,15 @@ extern "C" int wts_cross_attention_f16(const float* d_q, int64_t ldq, const void
                                        const float* d_k_align, const int32_t* d_head_slot, int32_t n_slots,
                                        int32_t ctx, const int32_t* d_row_seq, int32_t rows, int32_t H,
                                        void* d_out_sb16, int64_t ldo, int64_t o_plane, float* d_qk_out,
-                                       int32_t qk_rows, const int32_t* d_qk_row, void* stream)
+                                       int32_t qk_rows, const int32_t* d_qk_row, const int32_t* d_row_active,
+                                       void* stream)
 {
     if (rows <= 0) return 0;
     const size_t smem = ((size_t)ctx + 64 + 32 + 16 * 64) * sizeof(float);
     dim3 grid(rows, H);
     cross_attention_f16_kernel<<<grid, CA_THREADS, smem, (cudaStream_t)stream>>>(
         d_q, ldq, (const __half*)d_k16, (const __half*)d_v16, d_k_align, d_head_slot, n_slots, ctx, d_row_seq, H,
-        (__nv_bfloat16*)d_out_sb16, ldo, o_plane, d_qk_out, qk_rows, d_qk_row);
+        (__nv_bfloat16*)d_out_sb16, ldo, o_plane, d_qk_out, qk_rows, d_qk_row, d_row_active);
     WTS_LAUNCH_CHECK();
     return 0;
 }
@@ -742,11 +766,11 @@ extern "C" int wts_decode_select(float* d_logits, int64_t ldl, const WtsDecodeCf
 
 extern "C" int wts_step_inputs(const int32_t* d_tokens, int32_t tokens_ld, const int32_t* d_n_tokens,
                                const int32_t* d_n_prompt, const int32_t* d_done, int32_t B, int32_t* d_tok,
-                               int32_t* d_pos, int32_t* d_qk_row, void* stream)
+                               int32_t* d_pos, int32_t* d_qk_row, int32_t* d_active, void* stream)
 {
     if (B <= 0) return 0;
     step_inputs_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_tokens, tokens_ld, d_n_tokens, d_n_prompt,
-                                                                         d_done, B, d_tok, d_pos, d_qk_row);
+                                                                         d_done, B, d_tok, d_pos, d_qk_row, d_active);
     WTS_LAUNCH_CHECK();
     return 0;
 }

@@ -90,12 +90,12 @@ def _load():
     lib.wts_embed.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp]
     lib.wts_gather_rows.argtypes = [vp, i64, vp, i32, i32, vp, vp]
     lib.wts_decoder_attention.argtypes = [i32, vp, i64, vp, vp, i64, i32, vp, vp, i32, i32, vp, i64, i64, vp, vp, i32,
-                                          i32, vp, vp]
+                                          i32, vp, vp, vp]
     lib.wts_cross_kv_pack.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
-    lib.wts_cross_attention_f16.argtypes = [vp, i64, vp, vp, vp, vp, i32, i32, vp, i32, i32, vp, i64, i64, vp, i32, vp, vp]
+    lib.wts_cross_attention_f16.argtypes = [vp, i64, vp, vp, vp, vp, i32, i32, vp, i32, i32, vp, i64, i64, vp, i32, vp, vp, vp]
     lib.wts_kv_append.argtypes = [vp, vp, i64, vp, vp, i32, i32, i32, vp, vp, i64, vp]
     lib.wts_decode_select.argtypes = [vp, i64, ctypes.POINTER(DecodeCfg), vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, vp]
-    lib.wts_step_inputs.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp]
+    lib.wts_step_inputs.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp]
     lib.wts_softmax_pick.argtypes = [vp, i64, i32, i32, vp, i32, vp]
     for name in ("wts_to_sb16", "wts_layernorm", "wts_softmax_rows", "wts_frames", "wts_power", "wts_logmel_max",
                  "wts_logmel_finish", "wts_window_gather", "wts_embed", "wts_gather_rows", "wts_decoder_attention",

@@ -28,10 +28,12 @@ class AlignPlan:
         return len(self.segs)
 
 
-def plan_segments(items) -> AlignPlan:
+def plan_segments(items, nonpositive=False) -> AlignPlan:
     """items: iterable of dicts/tuples (window, row0, last_row, T, f0, F, max_dur).
 
-    Lays the per-segment cost matrices, jumps and DTW workspaces back to back."""
+    Lays the per-segment cost matrices, jumps and DTW workspaces back to back.
+    nonpositive=True promises that the float32 costs are <= 0 with cost[0,0] < 0 — what wts_attn_prep_batch
+    produces — and lets the DTW kernel use integer compares in its dependent chain (flags bit 0)."""
     items = list(items)
     segs = np.zeros(len(items), dtype=nat.SEG_DTYPE)
     cost = jumps = dirw = bnd = 0
@@ -49,6 +51,7 @@ def plan_segments(items) -> AlignPlan:
         s = segs[i]
         s["window"], s["row0"], s["last_row"], s["T"], s["f0"], s["F"] = window, row0, last_row, T, f0, F
         s["max_dur"] = max_dur or 0
+        s["flags"] = 1 if nonpositive else 0
         s["cost_off"], s["jumps_off"], s["dir_off"], s["bnd_off"] = cost, jumps, dirw, bnd
         cost += T * F
         cost = (cost + 3) & ~3                      # keep every matrix 16-byte aligned
@@ -124,7 +127,7 @@ def split_jumps(jumps_host: np.ndarray, plan: AlignPlan):
 
 def align(qk: torch.Tensor, items):
     """prep + DTW + one D2H copy.  Returns (list of jumps arrays, plan, cost buffer)."""
-    plan = plan_segments(items)
+    plan = plan_segments(items, nonpositive=True)
     cost = attn_prep(qk, plan)
     out = dtw(cost, plan)
     jumps = out["jumps"].cpu().numpy()

@@ -234,7 +234,7 @@ class CudaEngine:
         return xa
 
     # ------------------------------------------------------------------ decoder
-    def _decoder_rows(self, st8, x, R, row_seq, row_pos, qk_row, qk_buf):
+    def _decoder_rows(self, st8, x, R, row_seq, row_pos, qk_row, qk_buf, active=None):
         """One pass of all decoder blocks over R query rows (ragged batch)."""
         d, w, st = self.dims, self.w, self._st()
         D, H, L = d.n_text_state, d.n_text_head, d.n_text_layer
@@ -250,14 +250,17 @@ class CudaEngine:
             nat.check(nat.lib.wts_decoder_attention(0, qkv.data_ptr(), 3 * D, st8["sk"][li].data_ptr(),
                                                     st8["sv"][li].data_ptr(), H * d.n_text_ctx * 64, d.n_text_ctx,
                                                     row_seq.data_ptr(), row_pos.data_ptr(), R, H, att.ptr, att.ld,
-                                                    att.plane, None, None, 0, 0, None, st), "wts_decoder_attention")
+                                                    att.plane, None, None, 0, 0, None,
+                                                    active.data_ptr() if active is not None else None, st),
+                      "wts_decoder_attention")
             self.gemm(att, a.out, R, D, D, bias=a.out_b, residual=x, ldr=D, out_f32=x, ldc=D)
             self.layernorm(x, c.ln_g, c.ln_b, R, D, out_sb=hs)
             self.gemm(hs, c.q, R, D, D, bias=c.q_b, out_f32=q, ldc=D)
             nat.check(nat.lib.wts_cross_attention_f16(q.data_ptr(), D, st8["ck"][li].data_ptr(), st8["cv"][li].data_ptr(),
                                                       st8["ckal"][li].data_ptr(), w.head_slot[li].data_ptr(), n_slots,
                                                       N_CTX_AUDIO, row_seq.data_ptr(), R, H, att.ptr, att.ld, att.plane,
-                                                      qk_buf.data_ptr(), qk_buf.shape[2], qk_row.data_ptr(), st),
+                                                      qk_buf.data_ptr(), qk_buf.shape[2], qk_row.data_ptr(),
+                                                      active.data_ptr() if active is not None else None, st),
                       "wts_cross_attention_f16")
             self.gemm(att, c.out, R, D, D, bias=c.out_b, residual=x, ldr=D, out_f32=x, ldc=D)
             self.layernorm(x, blk.mlp_ln_g, blk.mlp_ln_b, R, D, out_sb=hs)
@@ -387,17 +390,18 @@ class CudaEngine:
         s_tok = torch.zeros(B, dtype=torch.int32, device=dev)
         s_pos = torch.zeros(B, dtype=torch.int32, device=dev)
         s_qkr = torch.zeros(B, dtype=torch.int32, device=dev)
+        s_act = torch.ones(B, dtype=torch.int32, device=dev)
         seq_ids = _i32(list(range(B)), dev)
         logits = torch.empty((B, V), dtype=torch.float32, device=dev)
         xs = torch.empty((B, D), dtype=torch.float32, device=dev)
 
         def step():
             nat.check(nat.lib.wts_step_inputs(tokens.data_ptr(), n_ctx + 1, n_tokens.data_ptr(), n_prompt.data_ptr(),
-                                              done.data_ptr(), B, s_tok.data_ptr(), s_pos.data_ptr(), s_qkr.data_ptr(), st),
-                      "wts_step_inputs")
+                                              done.data_ptr(), B, s_tok.data_ptr(), s_pos.data_ptr(), s_qkr.data_ptr(),
+                                              s_act.data_ptr(), st), "wts_step_inputs")
             nat.check(nat.lib.wts_embed(s_tok.data_ptr(), s_pos.data_ptr(), w.emb.data_ptr(), w.dec_pos.data_ptr(), B, D,
                                         xs.data_ptr(), st), "wts_embed")
-            self._decoder_rows(st8, xs, B, seq_ids, s_pos, s_qkr, qk_buf)
+            self._decoder_rows(st8, xs, B, seq_ids, s_pos, s_qkr, qk_buf, active=s_act)
             self._final_logits_static(xs, B, logits, st8)
             select(logits)
 
@@ -507,7 +511,7 @@ class CudaEngine:
             groups.setdefault(buf, []).append((i, b, it))
         for buf, lst in groups.items():
             plan = plan_segments([(b, it["row0"], it["last_row"], it["T"], it["f0"], it["F"], it["max_dur"])
-                                  for (_, b, it) in lst])
+                                  for (_, b, it) in lst], nonpositive=True)
             qk = self.qk_buffers[buf]
             with self.phase("align_prep"):
                 cost = attn_prep(qk, plan)

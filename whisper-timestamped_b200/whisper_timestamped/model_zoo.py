@@ -152,6 +152,8 @@ def synthetic_state_dict(dims: ModelDimensions, seed: int = 1234, logit_spread: 
     emb[eot, :] = 0.0
     emb[eot, 0] = eot_logit
     emb[eot + 1:ts_begin, 0] = -30.0        # language / task / control tokens are never produced as text
+    emb[128:256, 0] = -30.0                 # lone UTF-8 continuation bytes of the synthetic vocabulary: a real model
+                                            # never emits an undecodable tail (the reference raises on it, T.py:1471)
     sd["decoder.token_embedding.weight"] = emb
     sd["decoder.positional_embedding"] = rnd(dims.n_text_ctx, d_t, std=logit_spread / math.sqrt(d_t - 1))
     for i in range(dims.n_text_layer):
