@@ -123,7 +123,7 @@ def bytes_prep(N, T, F):
 
 def run_align(args, rank, world):
     import torch
-    from whisper_timestamped.alignment import plan_segments, attn_prep, dtw, _segs_to_device
+    from whisper_timestamped.alignment import plan_segments, attn_prep, dtw, dtw_descriptors, _segs_to_device
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
     torch.cuda.set_device(dev)
     T, F, N, nseg = args.align_T, args.align_F, 10, args.align_batch
@@ -135,12 +135,14 @@ def run_align(args, rank, world):
           torch.empty(plan.bnd_doubles, dtype=torch.float64, device=dev))
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     t_prep, t_dtw = [], []
+    d_segs_dtw = dtw_descriptors(plan, dev)          # descriptors are resident: the events bracket kernels only
+    jumps_buf = torch.empty(plan.jumps_elems, dtype=torch.int32, device=dev)
 
     def step(record):
         ev[0].record()
         attn_prep(qk, plan, cost=cost, d_segs=d_segs)
         ev[1].record()
-        out = dtw(cost, plan, workspace=ws)
+        out = dtw(cost, plan, workspace=ws, d_segs=d_segs_dtw, jumps=jumps_buf)
         ev[2].record()
         if record:
             torch.cuda.synchronize()

@@ -27,6 +27,21 @@ void median_rows(const float* x, int rows, int n, float* out) {{
         out[r * n + c] = wts_median9(p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8]);
     }}
 }}
+void median_rows_pair(const float* x, int rows, int n, float* out) {{
+    /* same data flow as the CUDA prep kernel: halo-padded row, two outputs per step */
+    float xb[4096];
+    for (int r = 0; r < rows; ++r) {{
+        for (int c = 0; c < n; ++c) xb[c + 4] = x[r * n + c];
+        for (int k = 0; k < 4; ++k) {{ xb[3 - k] = xb[4 + wts_reflect_index(-1 - k, n)]; xb[n + 4 + k] = xb[4 + wts_reflect_index(n + k, n)]; }}
+        xb[n + 8] = 0.f;
+        for (int c = 0; c < n; c += 2) {{
+            float m0, m1;
+            wts_median9_pair(xb + c, &m0, &m1);
+            out[r * n + c] = m0;
+            if (c + 1 < n) out[r * n + c + 1] = m1;
+        }}
+    }}
+}}
 int reflect_index(int p, int n) {{ return wts_reflect_index(p, n); }}
 ''')
     so = d / "med.so"
@@ -43,6 +58,9 @@ def test_median9_matches_scipy(medlib, n):
     medlib.median_rows(x.ctypes.data_as(ctypes.c_void_p), 7, n, out.ctypes.data_as(ctypes.c_void_p))
     ref = median_filter(x, (1, 9))               # same call as transcribe.py:1546 (mode='reflect')
     assert np.array_equal(out, ref)
+    out2 = np.empty_like(x)
+    medlib.median_rows_pair(x.ctypes.data_as(ctypes.c_void_p), 7, n, out2.ctypes.data_as(ctypes.c_void_p))
+    assert np.array_equal(out2, ref)
 
 
 def test_reflect_index_is_numpy_symmetric(medlib):

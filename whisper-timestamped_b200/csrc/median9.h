@@ -27,6 +27,21 @@ WTS_HD float wts_median9(float p0, float p1, float p2, float p3, float p4, float
     return p4;
 }
 
+// Two adjacent medians of 9 share 8 of their samples: with s3 <= s4 the two middle order statistics of the
+// shared samples x[c-3 .. c+4], median9(x[c-4 .. c+4]) = clamp(x[c-4], s3, s4) and
+// median9(x[c-3 .. c+5]) = clamp(x[c+5], s3, s4).  17 compare-exchanges (Batcher's 8-sorter pruned to ranks
+// 3 and 4, checked exhaustively with the 0-1 principle) + 2 clamps for TWO outputs.
+WTS_HD void wts_median9_pair(const float* v /* 10 samples x[c-4 .. c+5] */, float* m0, float* m1)
+{
+    float a0 = v[1], a1 = v[2], a2 = v[3], a3 = v[4], a4 = v[5], a5 = v[6], a6 = v[7], a7 = v[8];
+    WTS_CE(a0, a1); WTS_CE(a2, a3); WTS_CE(a0, a2); WTS_CE(a1, a3); WTS_CE(a1, a2);
+    WTS_CE(a4, a5); WTS_CE(a6, a7); WTS_CE(a4, a6); WTS_CE(a5, a7); WTS_CE(a5, a6);
+    WTS_CE(a0, a4); WTS_CE(a2, a6); WTS_CE(a2, a4); WTS_CE(a1, a5); WTS_CE(a3, a7); WTS_CE(a3, a5);
+    WTS_CE(a3, a4);
+    *m0 = fmaxf(a3, fminf(v[0], a4));
+    *m1 = fmaxf(a3, fminf(v[9], a4));
+}
+
 // index of the sample that position p (may be < 0 or >= n) maps to under symmetric reflection
 WTS_HD int wts_reflect_index(int p, int n)
 {

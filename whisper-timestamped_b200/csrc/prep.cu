@@ -12,8 +12,10 @@
 //   1561-1565 padding mask, 1568 weights[0,0] = weights.min()
 //
 // Kernel A (rows): one warp per (segment, token) row; for each head: coalesced load of the F-frame
-// slice into shared memory, median-of-9 selection network, numerically stable softmax, accumulate
-// the head mean in shared memory; the N*T*F*4 input bytes are read exactly once.
+// slice into shared memory (with a reflected 4-sample halo so the filter loop is branch-free), medians
+// of 9 computed two adjacent outputs at a time (they share 8 samples: one pruned 8-sorter + two clamps),
+// numerically stable softmax (ex2.approx), accumulate the head mean in shared memory; the N*T*F*4 input
+// bytes are read exactly once.
 // Kernel B (cols): one CTA per segment; per frame column: L2 norm over tokens, divide, negate,
 // padding mask, running minimum; finally cost[0,0] = min.  Reads the [T,F] mean twice (L2-hot).
 #include "common.cuh"
@@ -25,7 +27,7 @@ constexpr int PREP_WARPS = 4;
 
 __global__ void __launch_bounds__(PREP_WARPS * 32)
 prep_rows_kernel(const float* __restrict__ qk, const int N, const int Tmax, const int Fmax,
-                 const WtsSegDesc* __restrict__ segs, const int max_F, float* __restrict__ cost)
+                 const WtsSegDesc* __restrict__ segs, const int pitch, float* __restrict__ cost)
 {
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -33,45 +35,49 @@ prep_rows_kernel(const float* __restrict__ qk, const int N, const int Tmax, cons
     const int t = blockIdx.y * PREP_WARPS + warp;
     if (t >= sd.T) return;
     const int F = sd.F;
-    float* xbuf = smem + (size_t)warp * 3 * max_F;   // raw slice of one head
-    float* mbuf = xbuf + max_F;                      // median-filtered -> exp
-    float* acc = mbuf + max_F;                       // sum over heads of the softmax rows
+    float* xb = smem + (size_t)warp * 3 * pitch;     // raw slice with a 4-sample reflected halo: xb[i+4] = x[i]
+    float* mbuf = xb + pitch;                        // median-filtered -> exp
+    float* acc = mbuf + pitch;                       // sum over heads of the softmax rows
 
     const int row = (t == sd.T - 1) ? sd.last_row : sd.row0 + t;
     const float* src0 = qk + (((int64_t)sd.window * N) * Tmax + row) * (int64_t)Fmax + sd.f0;
     const int64_t head_stride = (int64_t)Tmax * Fmax;
+    const int npair = (F + 1) >> 1;
 
     for (int n = 0; n < N; ++n) {
         const float* src = src0 + n * head_stride;
-        for (int c = lane; c < F; c += 32) xbuf[c] = __ldg(src + c);
+        for (int c = lane; c < F; c += 32) xb[c + 4] = __ldg(src + c);
+        __syncwarp();
+        if (lane < 4) {                               // scipy 'reflect' halo (periodic for tiny F)
+            xb[3 - lane] = xb[4 + wts_reflect_index(-1 - lane, F)];
+            xb[F + 4 + lane] = xb[4 + wts_reflect_index(F + lane, F)];
+        }
+        if (lane == 4) xb[F + 8] = 0.f;
         __syncwarp();
         float mx = -INFINITY;
-        for (int c = lane; c < F; c += 32) {
-            float m;
-            if (c >= 4 && c + 4 < F) {
-                m = wts_median9(xbuf[c - 4], xbuf[c - 3], xbuf[c - 2], xbuf[c - 1], xbuf[c],
-                                xbuf[c + 1], xbuf[c + 2], xbuf[c + 3], xbuf[c + 4]);
-            } else {
-                float p[9];
+        for (int p = lane; p < npair; p += 32) {
+            const int c = 2 * p;
+            float v[10];
+            const float2* x2 = reinterpret_cast<const float2*>(xb + c);
 #pragma unroll
-                for (int k = 0; k < 9; ++k) p[k] = xbuf[wts_reflect_index(c - 4 + k, F)];
-                m = wts_median9(p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8]);
-            }
-            mbuf[c] = m;
-            mx = fmaxf(mx, m);
+            for (int k = 0; k < 5; ++k) { const float2 q = x2[k]; v[2 * k] = q.x; v[2 * k + 1] = q.y; }
+            float m0, m1;
+            wts_median9_pair(v, &m0, &m1);
+            mbuf[c] = m0;
+            mx = fmaxf(mx, m0);
+            if (c + 1 < F) { mbuf[c + 1] = m1; mx = fmaxf(mx, m1); }
         }
         mx = warp_max(mx);
         float sum = 0.f;
         for (int c = lane; c < F; c += 32) {
-            const float e = expf(mbuf[c] - mx);
+            const float e = __expf(mbuf[c] - mx);
             mbuf[c] = e;
             sum += e;
         }
         sum = warp_sum(sum);
-        for (int c = lane; c < F; c += 32) {
-            const float p = mbuf[c] / sum;
-            acc[c] = (n == 0) ? p : acc[c] + p;
-        }
+        const float inv = 1.0f / sum;
+        if (n == 0) { for (int c = lane; c < F; c += 32) acc[c] = mbuf[c] * inv; }
+        else        { for (int c = lane; c < F; c += 32) acc[c] += mbuf[c] * inv; }
         __syncwarp();
     }
     float* dst = cost + sd.cost_off + (int64_t)t * F;
@@ -127,11 +133,12 @@ extern "C" int wts_attn_prep_batch(const float* d_qk, int32_t N, int32_t Tmax, i
         return -2;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = (size_t)PREP_WARPS * 3 * max_F * sizeof(float);
+    const int pitch = (max_F + 10 + 1) & ~1;            // halo + even pitch so float2 reads stay aligned
+    const size_t smem = (size_t)PREP_WARPS * 3 * pitch * sizeof(float);
     if (smem > 48 * 1024)
         WTS_CUDA_CHECK(cudaFuncSetAttribute(prep_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(nseg, (max_T + PREP_WARPS - 1) / PREP_WARPS);
-    prep_rows_kernel<<<grid, PREP_WARPS * 32, smem, st>>>(d_qk, N, Tmax, Fmax, d_segs, max_F, d_cost);
+    prep_rows_kernel<<<grid, PREP_WARPS * 32, smem, st>>>(d_qk, N, Tmax, Fmax, d_segs, pitch, d_cost);
     WTS_LAUNCH_CHECK();
     prep_cols_kernel<<<nseg, 256, 0, st>>>(d_segs, d_cost);
     WTS_LAUNCH_CHECK();

@@ -87,19 +87,27 @@ def attn_prep(qk: torch.Tensor, plan: AlignPlan, cost: torch.Tensor = None,
     return cost
 
 
-def dtw(cost: torch.Tensor, plan: AlignPlan, want_path=False, want_status=False, workspace=None):
+def dtw_descriptors(plan: AlignPlan, device) -> torch.Tensor:
+    """Device copy of the descriptors in DTW launch order (largest matrices first)."""
+    return _segs_to_device(plan.segs[plan.dtw_order], device)
+
+
+def dtw(cost: torch.Tensor, plan: AlignPlan, want_path=False, want_status=False, workspace=None, d_segs=None,
+        jumps=None):
     """cost: float32 or float64 buffer laid out by `plan`.  Returns dict with device tensors
     `jumps` (int32, plan.jumps_elems) and optionally `path`, `path_off`, `path_len`, `status`."""
     nat.require_cuda(cost, "cost")
     assert cost.dtype in (torch.float32, torch.float64)
     dev = cost.device
     segs_sorted = plan.segs[plan.dtw_order]
-    d_segs = _segs_to_device(segs_sorted, dev)
+    if d_segs is None:
+        d_segs = _segs_to_device(segs_sorted, dev)
     if workspace is None:
         workspace = (torch.empty(plan.dir_words, dtype=torch.int32, device=dev),
                      torch.empty(plan.bnd_doubles, dtype=torch.float64, device=dev))
     d_dir, d_bnd = workspace
-    jumps = torch.empty(plan.jumps_elems, dtype=torch.int32, device=dev)
+    if jumps is None:
+        jumps = torch.empty(plan.jumps_elems, dtype=torch.int32, device=dev)
     out = {"jumps": jumps}
     d_path = d_poff = d_plen = d_status = None
     if want_path:
