@@ -330,6 +330,9 @@ def run_e2e(args, rank, world, local):
     ms = e0.elapsed_time(e1)
     stages = eng.stage_ms()
     eng.profile = False
+    if rank == 0 and os.environ.get("WTS_BENCH_VERBOSE"):
+        print("decode batches (B, steps, ms, ms/step):", [(b, s_, round(m, 1), round(m / max(s_, 1), 2)) for (b, s_, m) in eng.batch_ms],
+              file=sys.stderr)
     clocks = sampler.stop() if rank == 0 else None
     launches = eng.launches - launches0
     # e2e through the public API with HOST audio (H2D inside) and the result dict back on the host

@@ -55,37 +55,37 @@ __global__ void to_sb16_kernel(const float* __restrict__ x, int64_t n, __nv_bflo
 }
 
 // ---------------------------------------------------------------------------------------- layernorm
-// one warp per row; float32 statistics (mean, biased variance), eps = 1e-5.  The row is read once into
-// registers (D <= 1280), so a LayerNorm is a single memory round trip.
-constexpr int LN_MAXV = 40;
-__global__ void __launch_bounds__(128)
+// one CTA (128 threads) per row; float32 statistics (mean, biased variance), eps = 1e-5.  The row is read once
+// into registers (D <= 2048), two block reductions, one write: a single memory round trip per LayerNorm.
+constexpr int LN_THREADS = 128, LN_MAXV = 16;
+__global__ void __launch_bounds__(LN_THREADS)
 layernorm_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ gamma,
                  const float* __restrict__ beta, int M, int D, __nv_bfloat16* __restrict__ o, int64_t ldo,
                  int64_t o_plane, float* __restrict__ of, int64_t ldf)
 {
-    const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (row >= M) return;
+    __shared__ float red[32];
+    const int row = blockIdx.x;
     const float* xr = x + (int64_t)row * ldx;
     float v[LN_MAXV];
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < LN_MAXV; ++k) {
-        const int c = lane + 32 * k;
+        const int c = threadIdx.x + LN_THREADS * k;
         v[k] = c < D ? xr[c] : 0.f;
         s += v[k];
     }
-    const float mean = warp_sum(s) / (float)D;
+    const float mean = block_reduce_sum(s, red) / (float)D;
     float q = 0.f;
 #pragma unroll
     for (int k = 0; k < LN_MAXV; ++k) {
-        const int c = lane + 32 * k;
+        const int c = threadIdx.x + LN_THREADS * k;
         const float d = c < D ? v[k] - mean : 0.f;
         q += d * d;
     }
-    const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)D + 1e-5f);
+    const float rstd = 1.0f / sqrtf(block_reduce_sum(q, red) / (float)D + 1e-5f);
 #pragma unroll
     for (int k = 0; k < LN_MAXV; ++k) {
-        const int c = lane + 32 * k;
+        const int c = threadIdx.x + LN_THREADS * k;
         if (c < D) {
             const float y = (v[k] - mean) * rstd * gamma[c] + beta[c];
             if (o) {
@@ -613,8 +613,8 @@ extern "C" int wts_layernorm(const float* d_x, int64_t ldx, const float* d_gamma
                              int64_t ldf, void* stream)
 {
     if (M <= 0) return 0;
-    if (D > 32 * LN_MAXV) { set_error("wts_layernorm: D=%d > %d", D, 32 * LN_MAXV); return -2; }
-    layernorm_kernel<<<(M + 3) / 4, 128, 0, (cudaStream_t)stream>>>(d_x, ldx, d_gamma, d_beta, M, D,
+    if (D > LN_THREADS * LN_MAXV) { set_error("wts_layernorm: D=%d > %d", D, LN_THREADS * LN_MAXV); return -2; }
+    layernorm_kernel<<<M, LN_THREADS, 0, (cudaStream_t)stream>>>(d_x, ldx, d_gamma, d_beta, M, D,
                                                                    (__nv_bfloat16*)d_out_sb16, ldo, o_plane, d_out_f32, ldf);
     WTS_LAUNCH_CHECK();
     return 0;

@@ -74,6 +74,9 @@ class CudaEngine:
     def stage_ms(self, reset=True):
         torch.cuda.synchronize(self.dev)
         out = {}
+        self.batch_ms = [(B, steps, self._events[i][1].elapsed_time(self._events[i][2]))
+                         for (B, steps, i) in getattr(self, "batch_log", [])]
+        self.batch_log = []
         for name, a, b in self._events:
             out[name] = out.get(name, 0.0) + a.elapsed_time(b)
         if reset:
@@ -441,6 +444,9 @@ class CudaEngine:
 
         ph.__exit__()
         self.decode_steps_run = getattr(self, "decode_steps_run", 0) + steps_done
+        if self.profile:
+            self.batch_log = getattr(self, "batch_log", [])
+            self.batch_log.append((B, steps_done, len(self._events) - 1))
         # ---- collect
         torch.cuda.synchronize(dev)
         tokens_h = tokens.cpu().numpy()
