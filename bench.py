@@ -370,6 +370,25 @@ def run_e2e(args, rank, world, local):
     return out
 
 
+def usable_cores():
+    """Host cores this process may really use: affinity mask and cgroup CPU quota (a container can see 128 CPUs
+    and own far fewer; oversubscribing torch's thread pool then makes the CPU arm pathologically slow)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except Exception:
+        try:
+            quota = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if quota > 0:
+                n = min(n, max(1, quota // period))
+        except Exception:
+            pass
+    return max(1, min(n, int(os.environ.get("WTS_CPU_THREADS", "64"))))
+
+
 def _load_reference():
     """The UNMODIFIED reference as installed by `pip install --no-deps --target baseline/_ref`,
     imported under an alias over the oracle stand-ins for its two missing third-party dependencies."""
@@ -398,7 +417,7 @@ def cpu_baseline_e2e(args, seconds=None):
     from oracle.engine import OracleEngine, build_oracle_model
     from whisper_timestamped import model_zoo as zoo
     seconds = seconds or args.cpu_seconds
-    cores = os.cpu_count()
+    cores = usable_cores()
     torch.set_num_threads(cores)
     dims = zoo.DIMS[args.model]
     sd = zoo.synthetic_state_dict(dims, seed=1234, **SYNTH_KW)
