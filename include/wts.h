@@ -132,6 +132,13 @@ int wts_layernorm(const float* d_x, int64_t ldx, const float* d_gamma, const flo
 int wts_softmax_rows(const float* d_s, int64_t lds, int64_t rows, int32_t n, void* d_out_sb16, int64_t ldo,
                      int64_t o_plane, void* stream);
 
+/* Fused encoder self-attention (tcgen05): out = softmax(q k^T) v per (window, head), head dim 64; the score matrix
+ * stays on the SM (TMEM / shared memory).  d_qk: SB16 [B*n_ctx, 2D] (q | k, scale already folded in);
+ * d_vt: SB16 V^T [B*D, ld_vt] (row = channel, column = key); d_out: SB16 [B*n_ctx, D]. */
+int wts_enc_attention(const void* d_qk, int64_t ld_qk, int64_t qk_plane, const void* d_vt, int64_t ld_vt,
+                      int64_t vt_plane, int32_t B, int32_t H, int32_t D, int32_t n_ctx, void* d_out, int64_t ldo,
+                      int64_t o_plane, void* stream);
+
 /* Log-mel front end — replaces whisper.log_mel_spectrogram (T.py:1213; upstream transcribe()).
  * wts_frames:  audio [n] -> Hann-windowed, reflect-padded frames float32 [n_frames, 400] (hop 160).
  * (DFT as a float32 GEMM against the [2*208, 400] cos|-sin basis, wts_gemm with a_is_f32/b_is_f32.)

@@ -90,6 +90,29 @@ def test_gemm_skinny_inplace_residual(backend):
         assert err <= 2e-4 * max(1.0, ref.abs().max().item()), (M, N, K, err)
 
 
+def test_enc_attention_fused_vs_torch():
+    """wts_enc_attention (tcgen05, scores on-chip) against float64 softmax(q k^T) v of the same SB16 values."""
+    from whisper_timestamped import _native as nat
+    from whisper_timestamped.model import SB16
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(3)
+    B, H, n_ctx, KP = 2, 3, 1500, 1504
+    D = H * 64
+    qk = SB16.from_f32((torch.randn(B * n_ctx, 2 * D, generator=g) * 0.6).to(dev))
+    vt = SB16.from_f32(torch.randn(B * D, KP, generator=g).to(dev))
+    out = SB16(B * n_ctx, D, dev)
+    rc = nat.lib.wts_enc_attention(qk.ptr, 2 * D, qk.plane, vt.ptr, KP, vt.plane, B, H, D, n_ctx, out.ptr, D, out.plane,
+                                   nat.stream_ptr(dev))
+    nat.check(rc, "wts_enc_attention")
+    torch.cuda.synchronize()
+    qkf = qk.to_f32().double().reshape(B, n_ctx, 2, H, 64)
+    q, k = qkf[:, :, 0].permute(0, 2, 1, 3), qkf[:, :, 1].permute(0, 2, 1, 3)          # [B,H,n,64]
+    v = vt.to_f32().double().reshape(B, H, 64, KP)[..., :n_ctx].permute(0, 1, 3, 2)     # [B,H,n,64]
+    ref = (torch.softmax(q @ k.transpose(-1, -2), dim=-1) @ v).permute(0, 2, 1, 3).reshape(B * n_ctx, D)
+    err = (out.to_f32().double() - ref).abs().max().item()
+    assert err <= 2e-4, err
+
+
 @pytest.mark.parametrize("backend", BACKENDS[:1])
 def test_log_mel_matches_oracle(tiny, backend):
     from whisper_timestamped.synthetic_audio import synthetic_speech

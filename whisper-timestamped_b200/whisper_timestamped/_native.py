@@ -93,6 +93,8 @@ def _load():
                                           i32, vp, vp, vp]
     lib.wts_cross_kv_pack.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.wts_cross_attention_f16.argtypes = [vp, i64, vp, vp, vp, vp, i32, i32, vp, i32, i32, vp, i64, i64, vp, i32, vp, vp, vp]
+    lib.wts_enc_attention.argtypes = [vp, i64, i64, vp, i64, i64, i32, i32, i32, i32, vp, i64, i64, vp]
+    lib.wts_enc_attention.restype = ctypes.c_int
     lib.wts_kv_append.argtypes = [vp, vp, i64, vp, vp, i32, i32, i32, vp, vp, i64, vp]
     lib.wts_decode_select.argtypes = [vp, i64, ctypes.POINTER(DecodeCfg), vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, vp]
     lib.wts_step_inputs.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp]
@@ -112,7 +114,7 @@ EXPORTED_SYMBOLS = [
     "wts_attn_prep_batch", "wts_dtw_batch", "wts_gemm", "wts_to_sb16", "wts_layernorm", "wts_softmax_rows",
     "wts_frames", "wts_power", "wts_logmel_max", "wts_logmel_finish", "wts_window_gather", "wts_embed",
     "wts_gather_rows", "wts_decoder_attention", "wts_kv_append", "wts_decode_select", "wts_step_inputs",
-    "wts_softmax_pick", "wts_cross_kv_pack", "wts_cross_attention_f16",
+    "wts_softmax_pick", "wts_cross_kv_pack", "wts_cross_attention_f16", "wts_enc_attention",
 ]
 
 

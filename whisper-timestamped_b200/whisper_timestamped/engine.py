@@ -42,6 +42,7 @@ class CudaEngine:
         self.backend = int(os.environ.get("WTS_GEMM_BACKEND", "0")) if gemm_backend is None else gemm_backend
         # the conv GEMMs read overlapping rows (row stride < K); WTS_CONV_BACKEND picks their kernel separately
         self.conv_backend = int(os.environ.get("WTS_CONV_BACKEND", str(self.backend)))
+        self.fused_attention = os.environ.get("WTS_FUSED_ATTN", "1") != "0"
         self.keep_full_logprobs = keep_full_logprobs
         self.qk_buffers = []            # one [B, N, rows, 1500] float32 tensor per decode_windows call
         self.window_index = []          # global window id -> (buffer idx, b)
@@ -206,8 +207,10 @@ class CudaEngine:
         hs = SB16(R, D, dev)
         qk = SB16(R, 2 * D, dev)
         vt = SB16(B * D, KPAD, dev)
-        S = torch.empty((B * H * 1500, KPAD), dtype=torch.float32, device=dev)
-        P = SB16(B * H * 1500, KPAD, dev)
+        fused = self.backend == 0 and self.fused_attention
+        if not fused:
+            S = torch.empty((B * H * 1500, KPAD), dtype=torch.float32, device=dev)
+            P = SB16(B * H * 1500, KPAD, dev)
         att = SB16(R, D, dev)
         mid = SB16(R, 4 * D, dev)
         for blk in w.enc:
@@ -217,17 +220,23 @@ class CudaEngine:
             # V^T per window: [D, 1500] = Wv [D, D] x h^T  (swapped operands, bias along M)
             self.gemm(a.v, hs, D, 1500, D, batch=(B, 1), b_b=(1500 * D, 0), bias=a.v_b, bias_on_m=True,
                       out_sb=vt, ldo=KPAD, o_b=(D * KPAD, 0))
-            # scores[b, h] = q_h k_h^T  (scale folded into the weights)
-            self.gemm(qk, qk, 1500, 1500, 64, lda=2 * D, ldb=2 * D, b_off=D, batch=(B, H),
-                      a_b=(1500 * 2 * D, 64), b_b=(1500 * 2 * D, 64), out_f32=S, ldc=KPAD,
-                      c_b=(H * 1500 * KPAD, 1500 * KPAD))
-            nat.check(nat.lib.wts_softmax_rows(S.data_ptr(), KPAD, B * H * 1500, 1500, P.ptr, KPAD, P.plane, st),
-                      "wts_softmax_rows")
-            self.launches += 1
-            # out[b, :, h*64:(h+1)*64] = P[b, h] x V_h   (B operand = rows h*64.. of V^T)
-            self.gemm(P, vt, 1500, 64, 1500, lda=KPAD, ldb=KPAD, batch=(B, H),
-                      a_b=(H * 1500 * KPAD, 1500 * KPAD), b_b=(D * KPAD, 64 * KPAD), out_sb=att, ldo=D,
-                      o_b=(1500 * D, 64))
+            if fused:
+                # softmax(q k^T) v on the tensor cores, scores never leave the SM
+                nat.check(nat.lib.wts_enc_attention(qk.ptr, 2 * D, qk.plane, vt.ptr, KPAD, vt.plane, B, H, D, 1500,
+                                                    att.ptr, D, att.plane, st), "wts_enc_attention")
+                self.launches += 1
+            else:
+                # scores[b, h] = q_h k_h^T  (scale folded into the weights)
+                self.gemm(qk, qk, 1500, 1500, 64, lda=2 * D, ldb=2 * D, b_off=D, batch=(B, H),
+                          a_b=(1500 * 2 * D, 64), b_b=(1500 * 2 * D, 64), out_f32=S, ldc=KPAD,
+                          c_b=(H * 1500 * KPAD, 1500 * KPAD))
+                nat.check(nat.lib.wts_softmax_rows(S.data_ptr(), KPAD, B * H * 1500, 1500, P.ptr, KPAD, P.plane, st),
+                          "wts_softmax_rows")
+                self.launches += 1
+                # out[b, :, h*64:(h+1)*64] = P[b, h] x V_h   (B operand = rows h*64.. of V^T)
+                self.gemm(P, vt, 1500, 64, 1500, lda=KPAD, ldb=KPAD, batch=(B, H),
+                          a_b=(H * 1500 * KPAD, 1500 * KPAD), b_b=(D * KPAD, 64 * KPAD), out_sb=att, ldo=D,
+                          o_b=(1500 * D, 64))
             self.gemm(att, a.out, R, D, D, bias=a.out_b, residual=x, ldr=D, out_f32=x, ldc=D)
             self.layernorm(x, blk.mlp_ln_g, blk.mlp_ln_b, R, D, out_sb=hs)
             self.gemm(hs, blk.fc1, R, 4 * D, D, bias=blk.fc1_b, act=1, out_sb=mid)
