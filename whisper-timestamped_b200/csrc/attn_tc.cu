@@ -87,7 +87,13 @@ __device__ __forceinline__ void at_ld32(uint32_t taddr, uint32_t (&v)[32])
           "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
           "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void at_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float at_ex2(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 __device__ __forceinline__ uint64_t at_desc(uint32_t saddr)      // K-major, SWIZZLE_128B, 8-row groups 1024 B apart
 {
@@ -226,44 +232,63 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
         const int r = 32 * q + lane;                    // query row inside the tile == TMEM lane
         const uint32_t lane_off = (uint32_t)(32 * q) << 16;
         float m = -INFINITY;
-        for (int i = 0; i < NT; ++i) {                  // pass 1
+        for (int i = 0; i < NT; ++i) {                  // pass 1: exact row maxima
             const int st = i & 1, u = i >> 1;
             at_wait(bar + 8 * (B_SFULL + st), u & 1);
             at_fence_after();
+            const bool tail = (i + 1) * 128 > a.n_ctx;  // only the last key tile has out-of-range keys
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                at_ld32(tm_S0 + st * 128 + lane_off + 32 * c, v);
-                const int key0 = i * 128 + 32 * c;
+            for (int c = 0; c < 4; c += 2) {
+                uint32_t v0[32], v1[32];
+                at_ld32(tm_S0 + st * 128 + lane_off + 32 * c, v0);
+                at_ld32(tm_S0 + st * 128 + lane_off + 32 * c + 32, v1);
+                at_ld_wait();
+                if (!tail) {
 #pragma unroll
-                for (int e = 0; e < 32; ++e)
-                    if (key0 + e < a.n_ctx) m = fmaxf(m, __uint_as_float(v[e]));
+                    for (int e = 0; e < 32; ++e) m = fmaxf(m, fmaxf(__uint_as_float(v0[e]), __uint_as_float(v1[e])));
+                } else {
+                    const int key0 = i * 128 + 32 * c;
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        if (key0 + e < a.n_ctx) m = fmaxf(m, __uint_as_float(v0[e]));
+                        if (key0 + 32 + e < a.n_ctx) m = fmaxf(m, __uint_as_float(v1[e]));
+                    }
+                }
             }
             at_fence_before();
             at_arrive(bar + 8 * (B_SEMPTY + st));
         }
         float sum = 0.f;
         const float ml2 = m * 1.4426950408889634f;
-        for (int j = 0; j < NT; ++j) {                  // pass 2
+        for (int j = 0; j < NT; ++j) {                  // pass 2: probabilities -> shared memory, row sums
             const int i = NT + j, st = i & 1, u = i >> 1;
             at_wait(bar + 8 * (B_SFULL + st), u & 1);
             at_fence_after();
-            at_wait(bar + 8 * B_PEMPTY, (j & 1) ^ 1);
+            const bool tail = (j + 1) * 128 > a.n_ctx;
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 uint32_t v[32];
                 at_ld32(tm_S0 + st * 128 + lane_off + 32 * c, v);
+                at_ld_wait();
                 const int key0 = j * 128 + 32 * c;
-                __align__(16) __nv_bfloat16 hi[32];
-                __align__(16) __nv_bfloat16 lo[32];
+                uint32_t hw[16], lw[16];
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    float p = 0.f;
-                    if (key0 + e < a.n_ctx) p = exp2f(fmaf(__uint_as_float(v[e]), 1.4426950408889634f, -ml2));
-                    sum += p;
-                    hi[e] = __float2bfloat16_rn(p);
-                    lo[e] = __float2bfloat16_rn(p - __bfloat162float(hi[e]));
+                for (int e = 0; e < 16; ++e) {
+                    float p0 = at_ex2(fmaf(__uint_as_float(v[2 * e]), 1.4426950408889634f, -ml2));
+                    float p1 = at_ex2(fmaf(__uint_as_float(v[2 * e + 1]), 1.4426950408889634f, -ml2));
+                    if (tail) {
+                        if (key0 + 2 * e >= a.n_ctx) p0 = 0.f;
+                        if (key0 + 2 * e + 1 >= a.n_ctx) p1 = 0.f;
+                    }
+                    sum += p0 + p1;
+                    const __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
+                    const uint32_t hbits = *reinterpret_cast<const uint32_t*>(&hb);
+                    const float h0 = __uint_as_float(hbits << 16), h1 = __uint_as_float(hbits & 0xffff0000u);
+                    const __nv_bfloat162 lb = __floats2bfloat162_rn(p0 - h0, p1 - h1);
+                    hw[e] = hbits;
+                    lw[e] = *reinterpret_cast<const uint32_t*>(&lb);
                 }
+                if (c == 0) at_wait(bar + 8 * B_PEMPTY, (j & 1) ^ 1);   // previous P V has finished reading the P buffer
                 // A operand of P V: [128 rows x 128 keys] as two 64-key atoms, row pitch 128 B, 16-byte chunks
                 // XOR-swizzled with (row & 7)
                 const int at = c >> 1;
@@ -271,10 +296,8 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
 #pragma unroll
                 for (int ch = 0; ch < 4; ++ch) {
                     const uint32_t chunk = (uint32_t)((c & 1) * 4 + ch) ^ (uint32_t)(r & 7);
-                    const uint4 hv = reinterpret_cast<const uint4*>(hi)[ch];
-                    const uint4 lv = reinterpret_cast<const uint4*>(lo)[ch];
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + chunk * 16), "r"(hv.x), "r"(hv.y), "r"(hv.z), "r"(hv.w) : "memory");
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + 32768 + chunk * 16), "r"(lv.x), "r"(lv.y), "r"(lv.z), "r"(lv.w) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + chunk * 16), "r"(hw[4 * ch]), "r"(hw[4 * ch + 1]), "r"(hw[4 * ch + 2]), "r"(hw[4 * ch + 3]) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + 32768 + chunk * 16), "r"(lw[4 * ch]), "r"(lw[4 * ch + 1]), "r"(lw[4 * ch + 2]), "r"(lw[4 * ch + 3]) : "memory");
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
@@ -290,6 +313,7 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
         for (int c = 0; c < 2; ++c) {
             uint32_t v[32];
             at_ld32(tm_O + lane_off + 32 * c, v);
+            at_ld_wait();
             if (row < a.n_ctx) {
                 __align__(16) __nv_bfloat16 hi[32];
                 __align__(16) __nv_bfloat16 lo[32];
