@@ -323,6 +323,79 @@ class CudaEngine:
             out.extend(self._decode_batch(jobs[i:i + self.max_batch], setup))
         return out
 
+    def _decoder_session(self, setup, need):
+        """Persistent decode state for up to `max_batch` windows: KV caches, token buffers, the alignment buffer
+        and ONE captured CUDA graph of a decode step.  Every batch reuses it (unused slots are marked done and
+        skipped by the attention / select kernels), so the graph is captured once per engine, not per batch."""
+        d, dev = self.dims, self.dev
+        tok = setup.tokenizer
+        V, D, n_ctx = d.n_vocab, d.n_text_state, d.n_text_ctx
+        ses = getattr(self, "_session", None)
+        cap = 4
+        while cap < need:
+            cap *= 2
+        cap = min(cap, max(self.max_batch, need))
+        if ses is not None and ses["cap"] >= need:
+            cap = ses["cap"]                      # a smaller batch reuses the larger session (and its graph)
+        key = (cap, setup.sample_len, tok.eot, tok.timestamp_begin, tok.no_timestamps, setup.max_initial_timestamp_index,
+               self.keep_full_logprobs)
+        if ses is not None and ses["key"] == key:
+            return ses
+        self._session = ses = None
+        qk_rows = setup.sample_len + 1
+        n_slots = len(self.m.heads)
+        i32 = dict(dtype=torch.int32, device=dev)
+        ses = dict(key=key, cap=cap, qk_rows=qk_rows, graph=None, per_step=0)
+        ses["st8"] = self._alloc_decoder_state(cap, cap)
+        ses["st8"]["hs_fin"] = SB16(cap, D, dev)
+        ses["tokens"] = torch.zeros((cap, n_ctx + 1), **i32)
+        ses["n_tokens"] = torch.ones(cap, **i32)
+        ses["n_prompt"] = torch.ones(cap, **i32)
+        ses["done"] = torch.ones(cap, **i32)
+        ses["logprobs"] = torch.zeros((cap, qk_rows), dtype=torch.float32, device=dev)
+        ses["full"] = torch.empty((cap, qk_rows, V), dtype=torch.float32, device=dev) if self.keep_full_logprobs else None
+        ses["qk_buf"] = torch.zeros((cap, max(1, n_slots), qk_rows, N_CTX_AUDIO), dtype=torch.float32, device=dev)
+        ses["s_tok"] = torch.zeros(cap, **i32)
+        ses["s_pos"] = torch.zeros(cap, **i32)
+        ses["s_qkr"] = torch.zeros(cap, **i32)
+        ses["s_act"] = torch.zeros(cap, **i32)
+        ses["seq_ids"] = _i32(list(range(cap)), dev)
+        ses["logits"] = torch.empty((cap, V), dtype=torch.float32, device=dev)
+        ses["xs"] = torch.empty((cap, D), dtype=torch.float32, device=dev)
+        ses["suppress"] = torch.zeros(V, dtype=torch.uint8, device=dev)
+        ses["blank"] = torch.zeros(V, dtype=torch.uint8, device=dev)
+        ses["cfg"] = nat.DecodeCfg(n_vocab=V, eot=tok.eot, timestamp_begin=tok.timestamp_begin,
+                                   no_timestamps=tok.no_timestamps,
+                                   max_initial_ts=-1 if setup.max_initial_timestamp_index is None else setup.max_initial_timestamp_index,
+                                   sample_len=setup.sample_len, n_ctx=n_ctx, tokens_ld=n_ctx + 1)
+        self._session = ses
+        return ses
+
+    def _select(self, ses, logits, rows):
+        d = self.dims
+        nat.check(nat.lib.wts_decode_select(logits.data_ptr(), d.n_vocab, ctypes.byref(ses["cfg"]), ses["suppress"].data_ptr(),
+                                            ses["blank"].data_ptr(), ses["tokens"].data_ptr(), ses["n_tokens"].data_ptr(),
+                                            ses["n_prompt"].data_ptr(), ses["done"].data_ptr(), ses["logprobs"].data_ptr(),
+                                            ses["qk_rows"], ses["full"].data_ptr() if ses["full"] is not None else None,
+                                            rows, self._st()), "wts_decode_select")
+        self.launches += 1
+
+    def _step(self, ses):
+        """One decode step for all `cap` slots (identical launch sequence every step: CUDA-graph friendly)."""
+        d, w, st = self.dims, self.w, self._st()
+        cap, D = ses["cap"], d.n_text_state
+        nat.check(nat.lib.wts_step_inputs(ses["tokens"].data_ptr(), d.n_text_ctx + 1, ses["n_tokens"].data_ptr(),
+                                          ses["n_prompt"].data_ptr(), ses["done"].data_ptr(), cap, ses["s_tok"].data_ptr(),
+                                          ses["s_pos"].data_ptr(), ses["s_qkr"].data_ptr(), ses["s_act"].data_ptr(), st),
+                  "wts_step_inputs")
+        nat.check(nat.lib.wts_embed(ses["s_tok"].data_ptr(), ses["s_pos"].data_ptr(), w.emb.data_ptr(), w.dec_pos.data_ptr(),
+                                    cap, D, ses["xs"].data_ptr(), st), "wts_embed")
+        self._decoder_rows(ses["st8"], ses["xs"], cap, ses["seq_ids"], ses["s_pos"], ses["s_qkr"], ses["qk_buf"],
+                           active=ses["s_act"])
+        self._final_logits_static(ses["xs"], cap, ses["logits"], ses["st8"])
+        self._select(ses, ses["logits"], cap)
+        self.launches += 2
+
     @torch.no_grad()
     def _decode_batch(self, jobs, setup):
         d, dev, st, w = self.dims, self.dev, self._st(), self.w
@@ -331,100 +404,76 @@ class CudaEngine:
         D, V = d.n_text_state, d.n_vocab
         n_ctx = d.n_text_ctx
         sample_len = setup.sample_len
-        qk_rows = sample_len + 1
-        n_slots = len(self.m.heads)
+        ses = self._decoder_session(setup, B)
+        cap, qk_rows = ses["cap"], ses["qk_rows"]
+        assert B <= cap
+        st8 = ses["st8"]
         with self.phase("encoder"):
             xa = self.encode(jobs)
-
         prompts = [list(j["prompt"]) for j in jobs]
         P = [len(p) for p in prompts]
         R0 = sum(P)
-        st8 = self._alloc_decoder_state(B, max(R0, B))
         with self.phase("cross_kv"):
             self._cross_kv(xa, st8, B)
         del xa
-        qk_buf = torch.zeros((B, n_slots, qk_rows, N_CTX_AUDIO), dtype=torch.float32, device=dev)
 
-        # ---- token state
-        tokens_h = np.zeros((B, n_ctx + 1), dtype=np.int32)
+        # ---- token state of this batch (slots >= B are parked as "done")
+        tokens_h = np.zeros((cap, n_ctx + 1), dtype=np.int32)
         for b, p in enumerate(prompts):
             tokens_h[b, :len(p)] = p
-        tokens = torch.from_numpy(tokens_h).to(dev)
-        n_tokens = _i32(P, dev)
-        n_prompt = _i32(P, dev)
-        done = torch.zeros(B, dtype=torch.int32, device=dev)
-        logprobs = torch.zeros((B, qk_rows), dtype=torch.float32, device=dev)
-        full = torch.empty((B, qk_rows, V), dtype=torch.float32, device=dev) if self.keep_full_logprobs else None
-        suppress = torch.zeros(V, dtype=torch.uint8, device=dev)
-        suppress[torch.as_tensor(list(setup.suppress_tokens), dtype=torch.long, device=dev)] = 1
-        blank = torch.zeros(V, dtype=torch.uint8, device=dev)
+        ses["tokens"].copy_(torch.from_numpy(tokens_h), non_blocking=False)
+        nt = np.ones(cap, dtype=np.int32)
+        nt[:B] = P
+        ses["n_tokens"].copy_(torch.from_numpy(nt))
+        ses["n_prompt"].copy_(torch.from_numpy(nt))
+        dn = np.ones(cap, dtype=np.int32)
+        dn[:B] = 0
+        ses["done"].copy_(torch.from_numpy(dn))
+        ses["logprobs"].zero_()
+        ses["suppress"].zero_()
+        ses["suppress"][torch.as_tensor(list(setup.suppress_tokens), dtype=torch.long, device=dev)] = 1
+        ses["blank"].zero_()
         if setup.blank_tokens:
-            blank[torch.as_tensor(list(setup.blank_tokens), dtype=torch.long, device=dev)] = 1
-        cfg = nat.DecodeCfg(n_vocab=V, eot=tok.eot, timestamp_begin=tok.timestamp_begin,
-                            no_timestamps=tok.no_timestamps,
-                            max_initial_ts=-1 if setup.max_initial_timestamp_index is None else setup.max_initial_timestamp_index,
-                            sample_len=sample_len, n_ctx=n_ctx, tokens_ld=n_ctx + 1)
+            ses["blank"][torch.as_tensor(list(setup.blank_tokens), dtype=torch.long, device=dev)] = 1
+        qk_buf = ses["qk_buf"]
 
-        # ---- prefill: every prompt token of every window in one ragged batch
+        # ---- prefill: every prompt token of every window in one ragged batch (own activation buffers)
         row_seq = _i32([b for b, p in enumerate(prompts) for _ in p], dev)
         row_pos = _i32([i for p in prompts for i in range(len(p))], dev)
         row_tok = _i32([t for p in prompts for t in p], dev)
         qk_row = _i32([0 if i == len(p) - 1 else -1 for p in prompts for i in range(len(p))], dev)
-        x = torch.empty((max(R0, B), D), dtype=torch.float32, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        pre = dict(st8)
+        pre.update(hs=SB16(R0, D, dev), att=SB16(R0, D, dev), mid=SB16(R0, 4 * D, dev),
+                   qkv=torch.empty((R0, 3 * D), **f32), q=torch.empty((R0, D), **f32))
+        x = torch.empty((R0, D), **f32)
         ph = self.phase("prefill")
         ph.__enter__()
         nat.check(nat.lib.wts_embed(row_tok.data_ptr(), row_pos.data_ptr(), w.emb.data_ptr(), w.dec_pos.data_ptr(), R0, D,
                                     x.data_ptr(), st), "wts_embed")
-        self._decoder_rows(st8, x, R0, row_seq, row_pos, qk_row, qk_buf)
+        self._decoder_rows(pre, x, R0, row_seq, row_pos, qk_row, qk_buf)
         ends = np.cumsum(P) - 1
         sot_rows = [int(ends[b] - P[b] + 1 + prompts[b].index(tok.sot)) for b in range(B)]
         sel = _i32(list(ends) + sot_rows, dev)
-        xr = torch.empty((2 * B, D), dtype=torch.float32, device=dev)
+        xr = torch.empty((2 * B, D), **f32)
         nat.check(nat.lib.wts_gather_rows(x.data_ptr(), D, sel.data_ptr(), 2 * B, D, xr.data_ptr(), st), "wts_gather_rows")
-        logits2 = torch.empty((2 * B, V), dtype=torch.float32, device=dev)
+        logits2 = torch.empty((2 * B, V), **f32)
         self._final_logits(xr, 2 * B, logits2)
-        no_speech = torch.zeros(B, dtype=torch.float32, device=dev)
+        no_speech = torch.zeros(B, **f32)
         if tok.no_speech is not None:
             nat.check(nat.lib.wts_softmax_pick(logits2.data_ptr() + 4 * B * V, V, V, tok.no_speech, no_speech.data_ptr(), B, st),
                       "wts_softmax_pick")
-
-        def select(lg):
-            nat.check(nat.lib.wts_decode_select(lg.data_ptr(), V, ctypes.byref(cfg), suppress.data_ptr(), blank.data_ptr(),
-                                                tokens.data_ptr(), n_tokens.data_ptr(), n_prompt.data_ptr(),
-                                                done.data_ptr(), logprobs.data_ptr(), qk_rows,
-                                                full.data_ptr() if full is not None else None, B, st), "wts_decode_select")
-            self.launches += 1
-
-        select(logits2)
+        self._select(ses, logits2, B)
         ph.__exit__()
+        del pre, x, xr
 
-        # ---- decode steps: one row per window, identical launch sequence every step (CUDA-graph friendly)
-        s_tok = torch.zeros(B, dtype=torch.int32, device=dev)
-        s_pos = torch.zeros(B, dtype=torch.int32, device=dev)
-        s_qkr = torch.zeros(B, dtype=torch.int32, device=dev)
-        s_act = torch.ones(B, dtype=torch.int32, device=dev)
-        seq_ids = _i32(list(range(B)), dev)
-        logits = torch.empty((B, V), dtype=torch.float32, device=dev)
-        xs = torch.empty((B, D), dtype=torch.float32, device=dev)
-
-        def step():
-            nat.check(nat.lib.wts_step_inputs(tokens.data_ptr(), n_ctx + 1, n_tokens.data_ptr(), n_prompt.data_ptr(),
-                                              done.data_ptr(), B, s_tok.data_ptr(), s_pos.data_ptr(), s_qkr.data_ptr(),
-                                              s_act.data_ptr(), st), "wts_step_inputs")
-            nat.check(nat.lib.wts_embed(s_tok.data_ptr(), s_pos.data_ptr(), w.emb.data_ptr(), w.dec_pos.data_ptr(), B, D,
-                                        xs.data_ptr(), st), "wts_embed")
-            self._decoder_rows(st8, xs, B, seq_ids, s_pos, s_qkr, qk_buf, active=s_act)
-            self._final_logits_static(xs, B, logits, st8)
-            select(logits)
-
-        st8["hs_fin"] = SB16(B, D, dev)
+        # ---- decode steps
         max_steps = sample_len - 1
         steps_done = 0
-        graph = None
         ph = self.phase("decode_steps")
         ph.__enter__()
-        if self.use_graph and max_steps > 4:
-            step()                       # warm-up outside capture
+        if self.use_graph and ses["graph"] is None and max_steps > 4:
+            self._step(ses)              # warm-up outside capture
             steps_done = 1
             torch.cuda.synchronize(dev)
             graph = torch.cuda.CUDAGraph()
@@ -432,25 +481,25 @@ class CudaEngine:
             cap_stream.wait_stream(torch.cuda.current_stream(dev))
             l0 = self.launches
             with torch.cuda.stream(cap_stream):
-                st = self._st()
                 with torch.cuda.graph(graph, stream=cap_stream):
-                    step()               # recorded, not executed
-            per_step = self.launches - l0
+                    self._step(ses)      # recorded, not executed
+            ses["per_step"] = self.launches - l0
             self.launches = l0
-            st = self._st()
             torch.cuda.current_stream(dev).wait_stream(cap_stream)
+            ses["graph"] = graph
+        graph = ses["graph"] if self.use_graph else None
+        done = ses["done"]
         while steps_done < max_steps:
             chunk = min(8, max_steps - steps_done)
             for _ in range(chunk):
                 if graph is not None:
                     graph.replay()
-                    self.launches += per_step
+                    self.launches += ses["per_step"]
                 else:
-                    step()
+                    self._step(ses)
             steps_done += chunk
             if bool((done != 0).all().item()):
                 break
-
         ph.__exit__()
         self.decode_steps_run = getattr(self, "decode_steps_run", 0) + steps_done
         if self.profile:
@@ -458,15 +507,18 @@ class CudaEngine:
             self.batch_log.append((B, steps_done, len(self._events) - 1))
         # ---- collect
         torch.cuda.synchronize(dev)
-        tokens_h = tokens.cpu().numpy()
-        n_tok_h = n_tokens.cpu().numpy()
-        done_h = done.cpu().numpy()
-        lp_h = logprobs.cpu().numpy()
+        tokens_h = ses["tokens"][:B].cpu().numpy()
+        n_tok_h = ses["n_tokens"][:B].cpu().numpy()
+        done_h = ses["done"][:B].cpu().numpy()
+        lp_h = ses["logprobs"][:B].cpu().numpy()
         ns_h = no_speech.cpu().numpy()
+        max_rows = int(max(1, (n_tok_h - np.asarray(P)).max() + 1))
         buf_idx = len(self.qk_buffers)
-        self.qk_buffers.append(qk_buf)
+        self.qk_buffers.append(qk_buf[:B, :, :max_rows].clone())     # the session buffer is reused by the next batch
+        full = ses["full"]
         if full is not None:
-            self.full_logprobs.append(full)
+            self.full_logprobs.append(full[:B, :max_rows].clone())
+            full = self.full_logprobs[-1]
         records = []
         for b, job in enumerate(jobs):
             n = int(n_tok_h[b] - P[b])
