@@ -284,11 +284,8 @@ def run_e2e(args, rank, world, local):
     model = wt.load_model(f"synthetic:{args.model}", device=dev, synthetic_kwargs=SYNTH_KW)
     eng = CudaEngine(model, max_batch=args.max_batch)
     audio = make_audio(args.audio_seconds)
-    step_samples = int(args.chunk_seconds * 16000)
-    n_chunks = (len(audio) + step_samples - 1) // step_samples
-    lo, hi = rank * n_chunks // world, (rank + 1) * n_chunks // world
-    mine = audio[lo * step_samples: min(hi * step_samples, len(audio))]
-    offset = lo * args.chunk_seconds
+    from whisper_timestamped import sharding
+    mine, offset, _ = sharding.shard_audio(audio, args.chunk_seconds, rank, world)
     host_audio = torch.from_numpy(mine).pin_memory()
     dev_audio = host_audio.to(dev)
     opts = dict(language="en", chunks=args.chunk_seconds, engine=eng)
@@ -296,20 +293,8 @@ def run_e2e(args, rank, world, local):
     def one(audio_in):
         eng.release()
         res = wt.transcribe(model, audio_in, **opts)
-        for s in res["segments"]:
-            s["start"] += offset
-            s["end"] += offset
-            for w in s.get("words", []):
-                w["start"] = round(w["start"] + offset, 2)
-                w["end"] = round(w["end"] + offset, 2)
-        if world > 1:
-            import torch.distributed as dist
-            gathered = [None] * world
-            dist.all_gather_object(gathered, json.dumps(res["segments"]))
-            if rank == 0:
-                segs = [s for g in gathered for s in json.loads(g)]
-                res = dict(res, segments=segs)
-        return res
+        sharding.shift_segments(res["segments"], offset)
+        return sharding.gather_results(res, rank, world)       # rank 0: the stitched whole-recording result
 
     def barrier():
         if world > 1:

@@ -383,6 +383,8 @@ def transcribe_timestamped(
                 if not include_punctuation_in_confidence:
                     cat = np.concatenate(nopunc) if nopunc else np.zeros(0, np.float32)
                     segment["confidence"] = W.round_confidence(float(np.exp(cat.mean(dtype=np.float32))))
+            for w in ws:
+                w["_stream"] = st.index
             all_words.extend(ws)
         # stream time shift (independent cuts) is applied after the per-window offsets
         if st.time_shift:
@@ -392,6 +394,7 @@ def transcribe_timestamped(
             for s in st.segments:
                 s["start"] += st.time_shift
                 s["end"] += st.time_shift
+                s["seek"] += int(round(st.time_shift * SAMPLE_RATE / HOP_LENGTH))
         all_segments.extend(st.segments)              # empty-text segments stay in the output, like the reference
         text_parts.append(tokenizer.decode(st.all_tokens[st.n_initial_prompt:]))
 
@@ -403,12 +406,16 @@ def transcribe_timestamped(
     # ---- post-processing, as T.py:313-357
     if remove_empty_words:
         transcription, words = W.remove_last_null_duration_words(transcription, words, recompute_text=True)
-    W.ensure_increasing_positions(words, min_duration=min_word_duration if trust_whisper_timestamps else 0)
+    # independent cuts are post-processed independently (each is "the reference run on that cut alone")
+    for idx in sorted({w["_stream"] for w in words}):
+        W.ensure_increasing_positions([w for w in words if w["_stream"] == idx],
+                                      min_duration=min_word_duration if trust_whisper_timestamps else 0)
     segs = transcription["segments"]
     for word in words:
         word.pop("tokens", None)
         word.pop("tokens_indices", None)
         word.pop("avg_logprob_reliable", None)
+        word.pop("_stream", None)
         idx = word.pop("idx_segment")
         assert idx < len(segs), f"Fatal error: Got unexpected segment index {idx} >= {len(segs)}"
         seg = segs[idx]
@@ -420,6 +427,9 @@ def transcribe_timestamped(
                 seg["start"] = word["start"]
         if refine_whisper_precision:
             seg["end"] = word["end"]
+    if chunks is not None:
+        for i, seg in enumerate(segs):        # independent cuts: ids / seeks are those of the whole recording
+            seg["id"] = i
     return transcription
 
 
