@@ -90,6 +90,83 @@ def test_gemm_skinny_inplace_residual(backend):
         assert err <= 2e-4 * max(1.0, ref.abs().max().item()), (M, N, K, err)
 
 
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_gemm_skinny_split_general_epilogue(backend):
+    """Decode-time GEMMs whose epilogue is NOT the in-place residual (bias, GELU, SB16 / float32 outputs): on the
+    tensor-core path K is split across CTAs, partial sums meet in a float32 workspace and the last CTA of a tile
+    finishes it and cleans up — so every shape runs three times and must stay exact."""
+    from whisper_timestamped.model import SB16
+    from whisper_timestamped.engine import CudaEngine
+    dev = torch.device("cuda:0")
+    eng = CudaEngine.__new__(CudaEngine)
+    eng.dev, eng.backend, eng.launches = dev, backend, 0
+    g = torch.Generator(device="cpu").manual_seed(11)
+    for (M, N, K) in [(128, 5120, 1280), (120, 3840, 1280), (7, 1280, 5120), (64, 1000, 1288), (128, 1284, 136), (1, 384, 384)]:
+        a = torch.randn(M, K, generator=g).to(dev)
+        b = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev)
+        bias = torch.randn(N, generator=g).to(dev)
+        res = torch.randn(M, N, generator=g).to(dev)
+        A, Bm = SB16.from_f32(a), SB16.from_f32(b)
+        lin = A.to_f32().double() @ Bm.to_f32().double().T + bias.double()
+        for rep in range(3):
+            out = torch.full((M, N), 7.0, device=dev)
+            osb = SB16(M, N, dev)
+            eng.gemm(A, Bm, M, N, K, bias=bias, act=1, out_sb=osb)                       # fc1-like
+            eng.gemm(A, Bm, M, N, K, bias=bias, out_f32=out, ldc=N)                      # qkv-like
+            out2 = torch.zeros(M, N, device=dev)
+            eng.gemm(A, Bm, M, N, K, bias=bias, residual=res, ldr=N, out_f32=out2, ldc=N)  # residual, not in place
+            torch.cuda.synchronize()
+            scale = max(1.0, lin.abs().max().item())
+            assert (osb.to_f32().double() - torch.nn.functional.gelu(lin)).abs().max().item() <= 3e-4 * scale, (M, N, K, rep)
+            assert (out.double() - lin).abs().max().item() <= 2e-4 * scale, (M, N, K, rep)
+            assert (out2.double() - (lin + res.double())).abs().max().item() <= 2e-4 * scale, (M, N, K, rep)
+
+
+def test_cross_attention_f16_vs_torch():
+    """wts_cross_attention_f16 (one pass, online softmax over fp16 K/V; float32 K for the alignment heads) against
+    float64 torch on the same cache contents; inactive rows must be left untouched."""
+    from whisper_timestamped import _native as nat
+    from whisper_timestamped.model import SB16
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(21)
+    B, H, ctx, n_slots, qk_rows = 3, 6, 1500, 2, 5
+    D = H * 64
+    head_slot = torch.tensor([-1, 0, -1, -1, 1, -1], dtype=torch.int32, device=dev)
+    k32 = (torch.randn(B, H, ctx, 64, generator=g) * 0.7).to(dev)
+    v32 = torch.randn(B, H, ctx, 64, generator=g).to(dev)
+    k16, v16 = k32.half().contiguous(), v32.half().contiguous()
+    kal = torch.stack([k32[:, 1], k32[:, 4]], dim=1).contiguous()
+    R = 5
+    q = (torch.randn(R, D, generator=g) * 0.8).to(dev)
+    row_seq = torch.tensor([0, 2, 1, 1, 0], dtype=torch.int32, device=dev)
+    qk_row = torch.tensor([0, 3, -1, 4, 2], dtype=torch.int32, device=dev)
+    active = torch.tensor([1, 1, 1, 0, 1], dtype=torch.int32, device=dev)
+    out = SB16(R, D, dev)
+    out.t.fill_(3.0)
+    qk_out = torch.full((B, n_slots, qk_rows, ctx), -77.0, device=dev)
+    rc = nat.lib.wts_cross_attention_f16(q.data_ptr(), D, k16.data_ptr(), v16.data_ptr(), kal.data_ptr(), head_slot.data_ptr(),
+                                         n_slots, ctx, row_seq.data_ptr(), R, H, out.ptr, out.ld, out.plane, qk_out.data_ptr(),
+                                         qk_rows, qk_row.data_ptr(), active.data_ptr(), nat.stream_ptr(dev))
+    nat.check(rc, "wts_cross_attention_f16")
+    torch.cuda.synchronize()
+    got = out.to_f32().double()
+    expect_qk = torch.full_like(qk_out, -77.0).double()
+    for r in range(R):
+        if not active[r]:
+            assert torch.all(got[r] == 3.0 + 3.0)       # untouched planes (hi = lo = 3)
+            continue
+        sq = int(row_seq[r])
+        for h in range(H):
+            slot = int(head_slot[h])
+            K = (k32 if slot >= 0 else k16.float())[sq, h].double()
+            s = K @ q[r, h * 64:(h + 1) * 64].double()
+            y = torch.softmax(s, dim=0) @ v16[sq, h].double()
+            assert (got[r, h * 64:(h + 1) * 64] - y).abs().max().item() <= 2e-5, (r, h)
+            if slot >= 0 and int(qk_row[r]) >= 0:
+                expect_qk[sq, slot, int(qk_row[r])] = s
+    assert (qk_out.double() - expect_qk).abs().max().item() <= 2e-5
+
+
 def test_enc_attention_fused_vs_torch():
     """wts_enc_attention (tcgen05, scores on-chip) against float64 softmax(q k^T) v of the same SB16 values."""
     from whisper_timestamped import _native as nat

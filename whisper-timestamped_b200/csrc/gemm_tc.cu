@@ -114,10 +114,69 @@ __device__ __forceinline__ float gelu_erf_tc(float v) { return 0.5f * v * (1.0f 
 struct TcArgs {
     WtsGemm g;
     int a_has_bo, a_has_bi, b_has_bo, b_has_bi;   // 0 => that batch stride is 0 (operand shared): coordinate 0
-    int split_k;                                  // > 1: blockIdx.z is a K split (batch must be 1); partial sums
-                                                  // are reduced with float32 atomics into out_f32 (which already
-                                                  // holds the residual)
+    int split_k;                                  // > 1: blockIdx.z is a K split (batch must be 1)
+    int inplace;                                  // split-K flavour 1: out_f32 already holds the residual and the
+                                                  // epilogue is linear, partial sums go straight into it (RED)
+    float* ws;                                    // split-K flavour 2: partial sums are RED-accumulated into this
+    int64_t ldws;                                 // zeroed float32 workspace; the LAST split CTA of a tile (ticket
+    int* tickets;                                 // counter) applies the epilogue, then re-zeroes its tile + ticket
 };
+
+__device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// alpha/bias/GELU/residual + float32 and/or SB16 stores of 32 consecutive columns of one output row
+__device__ __forceinline__ void epilogue_chunk(const WtsGemm& g, float (&y)[32], int m, int nb, float bias_m, const float* res,
+                                               float* of, __nv_bfloat16* ob)
+{
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const int n = nb + j;
+        float t = y[j];
+        if (g.bias) t += g.bias_on_m ? bias_m : (n < g.N ? g.bias[n] : 0.f);
+        if (g.act == 1) t = gelu_erf_tc(t);
+        if (res && n < g.N) t += res[n];
+        y[j] = t;
+    }
+    const bool full = nb + 32 <= g.N;
+    if (of) {
+        const int64_t off = g.head_dim > 0 ? (int64_t)(nb / g.head_dim) * g.head_stride + (int64_t)m * g.ldc + (nb % g.head_dim)
+                                           : (int64_t)m * g.ldc + nb;
+        float* dst = of + off;
+        if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (nb + j < g.N) dst[j] = y[j];
+        }
+    }
+    if (ob) {
+        const int64_t off = g.head_dim > 0 ? (int64_t)(nb / g.head_dim) * g.head_stride + (int64_t)m * g.ldo + (nb % g.head_dim)
+                                           : (int64_t)m * g.ldo + nb;
+        __nv_bfloat16* dh = ob + off;
+        __nv_bfloat16* dl = dh + g.o_plane;
+        __align__(16) __nv_bfloat16 hi[32];
+        __align__(16) __nv_bfloat16 lo[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            hi[j] = __float2bfloat16_rn(y[j]);
+            lo[j] = __float2bfloat16_rn(y[j] - __bfloat162float(hi[j]));
+        }
+        if (full && ((reinterpret_cast<uintptr_t>(dh) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dl) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                reinterpret_cast<uint4*>(dh)[j] = reinterpret_cast<const uint4*>(hi)[j];
+                reinterpret_cast<uint4*>(dl)[j] = reinterpret_cast<const uint4*>(lo)[j];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (nb + j < g.N) { dh[j] = hi[j]; dl[j] = lo[j]; }
+        }
+    }
+}
 
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -209,68 +268,76 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float* of = g.out_f32 ? g.out_f32 + (int64_t)zo * g.c_bo + (int64_t)zi * g.c_bi : nullptr;
         __nv_bfloat16* ob = g.out_sb16 ? reinterpret_cast<__nv_bfloat16*>(g.out_sb16) + (int64_t)zo * g.o_bo + (int64_t)zi * g.o_bi : nullptr;
         const float bias_m = (g.bias && g.bias_on_m && row_ok) ? g.bias[m] : 0.f;
+        if (!split) {
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), v);
-            const int nb = n0 + 32 * c;
-            if (!row_ok || nb >= g.N) continue;
-            float y[32];
-            if (split) {
-                // split-K partial: out_f32 already holds the residual; the first split also adds the bias
-                float* dst = of + (int64_t)m * g.ldc + nb;
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), v);
+                const int nb = n0 + 32 * c;
+                if (!row_ok || nb >= g.N) continue;
+                float y[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) y[j] = g.alpha * __uint_as_float(v[j]);
+                epilogue_chunk(g, y, m, nb, bias_m, res, of, ob);
+            }
+        } else {
+            // ---- split-K: RED the partial tile into out_f32 (in-place flavour) or into the workspace
+            float* acc = args.inplace ? of : args.ws;
+            const int64_t ldacc = args.inplace ? g.ldc : args.ldws;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), v);
+                const int nb = n0 + 32 * c;
+                if (!row_ok || nb >= g.N) continue;
+                float* dst = acc + (int64_t)m * ldacc + nb;
+                float t[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const int n = nb + j;
-                    float t = g.alpha * __uint_as_float(v[j]);
-                    if (g.bias && blockIdx.z == 0) t += g.bias_on_m ? bias_m : (n < g.N ? g.bias[n] : 0.f);
-                    if (n < g.N) atomicAdd(dst + j, t);
+                    t[j] = g.alpha * __uint_as_float(v[j]);
+                    if (args.inplace && g.bias && blockIdx.z == 0) t[j] += g.bias_on_m ? bias_m : (nb + j < g.N ? g.bias[nb + j] : 0.f);
                 }
-                continue;
-            }
+                if (nb + 32 <= g.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int n = nb + j;
-                float t = g.alpha * __uint_as_float(v[j]);
-                if (g.bias) t += g.bias_on_m ? bias_m : (n < g.N ? g.bias[n] : 0.f);
-                if (g.act == 1) t = gelu_erf_tc(t);
-                if (res && n < g.N) t += res[n];
-                y[j] = t;
-            }
-            const bool full = nb + 32 <= g.N;
-            if (of) {
-                const int64_t off = g.head_dim > 0 ? (int64_t)(nb / g.head_dim) * g.head_stride + (int64_t)m * g.ldc + (nb % g.head_dim)
-                                                   : (int64_t)m * g.ldc + nb;
-                float* dst = of + off;
-                if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+                    for (int j = 0; j < 32; j += 4) red_add_v4(dst + j, t[j], t[j + 1], t[j + 2], t[j + 3]);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) if (nb + j < g.N) dst[j] = y[j];
+                    for (int j = 0; j < 32; ++j) if (nb + j < g.N) atomicAdd(dst + j, t[j]);
                 }
             }
-            if (ob) {
-                const int64_t off = g.head_dim > 0 ? (int64_t)(nb / g.head_dim) * g.head_stride + (int64_t)m * g.ldo + (nb % g.head_dim)
-                                                   : (int64_t)m * g.ldo + nb;
-                __nv_bfloat16* dh = ob + off;
-                __nv_bfloat16* dl = dh + g.o_plane;
-                __align__(16) __nv_bfloat16 hi[32];
-                __align__(16) __nv_bfloat16 lo[32];
+            if (!args.inplace) {
+                // ---- ticket: the last split CTA of this tile owns the complete sums and runs the real epilogue
+                volatile int* flag = reinterpret_cast<volatile int*>(smem_raw + (bar_base - smem_addr(smem_raw)) + 144);
+                __threadfence();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+                if (threadIdx.x == 64) *flag = (atomicAdd(args.tickets + tile, 1) == args.split_k - 1) ? 1 : 0;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (*flag) {
+                    __threadfence();
+#pragma unroll 1
+                    for (int c = 0; c < BN / 32; ++c) {
+                        const int nb = n0 + 32 * c;
+                        if (!row_ok || nb >= g.N) continue;
+                        float* src = args.ws + (int64_t)m * args.ldws + nb;
+                        float y[32];
+                        if (nb + 32 <= g.N && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    hi[j] = __float2bfloat16_rn(y[j]);
-                    lo[j] = __float2bfloat16_rn(y[j] - __bfloat162float(hi[j]));
-                }
-                if (full && ((reinterpret_cast<uintptr_t>(dh) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dl) & 15) == 0)) {
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 f = __ldcg(reinterpret_cast<const float4*>(src + j));
+                                y[j] = f.x; y[j + 1] = f.y; y[j + 2] = f.z; y[j + 3] = f.w;
+                                __stcg(reinterpret_cast<float4*>(src + j), make_float4(0.f, 0.f, 0.f, 0.f));
+                            }
+                        } else {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        reinterpret_cast<uint4*>(dh)[j] = reinterpret_cast<const uint4*>(hi)[j];
-                        reinterpret_cast<uint4*>(dl)[j] = reinterpret_cast<const uint4*>(lo)[j];
+                            for (int j = 0; j < 32; ++j) {
+                                y[j] = 0.f;
+                                if (nb + j < g.N) { y[j] = __ldcg(src + j); __stcg(src + j, 0.f); }
+                            }
+                        }
+                        epilogue_chunk(g, y, m, nb, bias_m, res, of, ob);
                     }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) if (nb + j < g.N) { dh[j] = hi[j]; dl[j] = lo[j]; }
+                    if (threadIdx.x == 64) args.tickets[tile] = 0;
                 }
             }
         }
@@ -327,8 +394,37 @@ static int make_map(CUtensorMap* tm, const void* ptr, int64_t K, int64_t rows, i
     return 0;
 }
 
+// Split-K workspace of the current device: float32 [128, WS_LD] sums + one ticket per output tile, zero between
+// GEMMs (every finalising CTA cleans up after itself).  One GEMM at a time per device may use it: launches that
+// share it must be stream-ordered (the engine issues all its work on one stream).
+constexpr int64_t WS_LD = 148 * 128;
+struct SplitWs { float* ws = nullptr; int* tickets = nullptr; };
+static int get_split_ws(SplitWs* out)
+{
+    static std::mutex mu;
+    static SplitWs per_dev[64];
+    int dev = 0;
+    WTS_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) { set_error("wts_gemm: device ordinal %d out of range", dev); return -7; }
+    std::lock_guard<std::mutex> lock(mu);
+    if (!per_dev[dev].ws) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        (void)cs;
+        float* w = nullptr;
+        int* t = nullptr;
+        WTS_CUDA_CHECK(cudaMalloc(&w, (size_t)BM * WS_LD * sizeof(float)));
+        WTS_CUDA_CHECK(cudaMalloc(&t, 256 * sizeof(int)));
+        WTS_CUDA_CHECK(cudaMemset(w, 0, (size_t)BM * WS_LD * sizeof(float)));
+        WTS_CUDA_CHECK(cudaMemset(t, 0, 256 * sizeof(int)));
+        per_dev[dev].ws = w;
+        per_dev[dev].tickets = t;
+    }
+    *out = per_dev[dev];
+    return 0;
+}
+
 template <int BN>
-static int launch_bn(const WtsGemm& g, cudaStream_t st, int split_k)
+static int launch_bn(const WtsGemm& g, cudaStream_t st, int split_k, bool inplace)
 {
     static bool attr_set = false;
     if (!attr_set) {
@@ -345,6 +441,14 @@ static int launch_bn(const WtsGemm& g, cudaStream_t st, int split_k)
     args.a_has_bo = g.a_bo != 0; args.a_has_bi = g.a_bi != 0;
     args.b_has_bo = g.b_bo != 0; args.b_has_bi = g.b_bi != 0;
     args.split_k = split_k;
+    args.inplace = inplace ? 1 : 0;
+    args.ws = nullptr; args.tickets = nullptr; args.ldws = WS_LD;
+    if (split_k > 1 && !inplace) {
+        SplitWs w;
+        rc = get_split_ws(&w);
+        if (rc) return rc;
+        args.ws = w.ws; args.tickets = w.tickets;
+    }
     dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, split_k > 1 ? split_k : g.batch_outer * g.batch_inner);
     gemm_tc_kernel<BN><<<grid, TC_THREADS, TcCfg<BN>::SMEM, st>>>(tmA, tmB, args);
     WTS_LAUNCH_CHECK();
@@ -353,23 +457,28 @@ static int launch_bn(const WtsGemm& g, cudaStream_t st, int split_k)
 
 int gemm_tc_launch(const WtsGemm& g, cudaStream_t st)
 {
+    // WTS_SKINNY_GEMM: 1 (default) = 128-wide tiles split along K over ~all SMs; 32 = the older 32-wide tiles; 0 = off
     static const int skinny = []{ const char* e = getenv("WTS_SKINNY_GEMM"); return e ? atoi(e) : 1; }();
     static const int splitk = []{ const char* e = getenv("WTS_SPLITK"); return e ? atoi(e) : 1; }();
     const bool one_batch = g.batch_outer * g.batch_inner == 1;
     if (skinny && g.M <= BM && one_batch) {
-        // decode-time GEMM: one M tile.  Narrow N tiles for CTA count; split K when the epilogue is the linear
-        // in-place residual update (x += A W^T + b), reduced with float32 atomics.
+        // decode-time GEMM: one M tile, weight-bandwidth bound.  Split K so that tiles x splits fills the SMs in one
+        // wave; partial sums meet in float32 (RED) either directly in out_f32 when the epilogue is the linear
+        // in-place residual update (x += A W^T + b), or in the workspace with a last-arriver epilogue.
+        const int bn = skinny == 32 ? 32 : 128;
+        const int tiles = (g.N + bn - 1) / bn, nkb = (g.K + BK - 1) / BK;
+        const bool inplace = g.out_f32 && g.residual == g.out_f32 && g.act == 0 && !g.out_sb16 && g.head_dim == 0;
         int split = 1;
-        const int tiles = (g.N + 31) / 32, nkb = (g.K + BK - 1) / BK;
-        if (splitk && g.out_f32 && g.residual == g.out_f32 && g.act == 0 && !g.out_sb16 && g.head_dim == 0 && tiles < 148) {
-            split = (148 + tiles - 1) / tiles;
-            if (split > nkb / 4) split = nkb / 4;
-            if (split > 8) split = 8;
+        if (splitk && tiles <= 74 && g.N <= WS_LD) {
+            split = 148 / tiles;
+            if (split > nkb) split = nkb;
+            if (bn == 32 && split > 8) split = 8;
             if (split < 1) split = 1;
         }
-        return launch_bn<32>(g, st, split);
+        if (bn == 32) return launch_bn<32>(g, st, inplace ? split : 1, inplace);
+        return launch_bn<128>(g, st, split, inplace);
     }
-    return launch_bn<128>(g, st, 1);
+    return launch_bn<128>(g, st, 1, false);
 }
 
 }  // namespace wts

@@ -329,7 +329,73 @@ __global__ void cross_kv_pack_kernel(const float* __restrict__ src, __half* __re
     }
 }
 
-constexpr int CA_THREADS = 128;
+// One CTA per (query row, head); 256 threads = 32 key groups x 8 lanes, a lane owns 8 of the 64 channels.
+// A group streams keys g, g+32, ...: K row (16 B/lane fp16, or 32 B/lane from the float32 alignment copy) and
+// V row (16 B/lane) are both loaded CA_UNROLL keys ahead (coalesced 128-byte rows, >= 128 B in flight per lane),
+// the score is an 8-lane shuffle reduction and softmax x V is accumulated ONLINE (running max / sum), so K and V
+// are streamed exactly once, in one pass, with no score buffer.  The 32 partial (max, sum, acc) triples are
+// merged in shared memory.  Raw scores of the alignment heads go to qk_out on the way.
+constexpr int CA_THREADS = 256;
+constexpr int CA_GROUPS = CA_THREADS / 8;
+constexpr int CA_UNROLL = 4;
+
+template <bool KF32>
+__device__ __forceinline__ void ca_stream(const void* __restrict__ Kbase, const __half* __restrict__ Vbase, int ctx, int g,
+                                          int c8, const float (&qf)[8], float* __restrict__ qk_dst, float& m, float& l,
+                                          float (&acc)[8])
+{
+    for (int j0 = g; j0 < ctx; j0 += CA_GROUPS * CA_UNROLL) {
+        uint4 kr[CA_UNROLL][KF32 ? 2 : 1];
+        uint4 vr[CA_UNROLL];
+#pragma unroll
+        for (int u = 0; u < CA_UNROLL; ++u) {
+            const int j = min(j0 + CA_GROUPS * u, ctx - 1);
+            if (KF32) {
+                const uint4* p = reinterpret_cast<const uint4*>(static_cast<const float*>(Kbase) + (int64_t)j * 64 + c8 * 8);
+                kr[u][0] = __ldcs(p);
+                kr[u][KF32 ? 1 : 0] = __ldcs(p + 1);
+            } else {
+                kr[u][0] = __ldcs(reinterpret_cast<const uint4*>(static_cast<const __half*>(Kbase) + (int64_t)j * 64 + c8 * 8));
+            }
+            vr[u] = __ldcs(reinterpret_cast<const uint4*>(Vbase + (int64_t)j * 64 + c8 * 8));
+        }
+#pragma unroll
+        for (int u = 0; u < CA_UNROLL; ++u) {
+            const int j = j0 + CA_GROUPS * u;
+            const bool valid = j < ctx;
+            float s = 0.f;
+            if (KF32) {
+                const float* kf = reinterpret_cast<const float*>(&kr[u][0]);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) s += qf[e] * kf[e];
+            } else {
+                const __half2* h2 = reinterpret_cast<const __half2*>(&kr[u][0]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 f = __half22float2(h2[e]);
+                    s += qf[2 * e] * f.x + qf[2 * e + 1] * f.y;
+                }
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            if (valid && qk_dst != nullptr && c8 == 0) qk_dst[j] = s;
+            const float mn = fmaxf(m, valid ? s : -1e30f);
+            const float sc = __expf(m - mn);
+            const float p = valid ? __expf(s - mn) : 0.f;
+            l = l * sc + p;
+            const __half2* v2 = reinterpret_cast<const __half2*>(&vr[u]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(v2[e]);
+                acc[2 * e] = acc[2 * e] * sc + p * f.x;
+                acc[2 * e + 1] = acc[2 * e + 1] * sc + p * f.y;
+            }
+            m = mn;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(CA_THREADS)
 cross_attention_f16_kernel(const float* __restrict__ q, int64_t ldq, const __half* __restrict__ k16,
                            const __half* __restrict__ v16, const float* __restrict__ k_align,
@@ -338,92 +404,51 @@ cross_attention_f16_kernel(const float* __restrict__ q, int64_t ldq, const __hal
                            int64_t o_plane, float* __restrict__ qk_out, int qk_rows, const int32_t* __restrict__ qk_row,
                            const int32_t* __restrict__ row_active)
 {
-    extern __shared__ float sm[];
-    float* sc = sm;                 // [ctx]
-    float* qs = sm + ctx;           // [64]
-    float* red = qs + 64;           // [32]
-    float* part = red + 32;         // [16][64]
+    __shared__ float sm_acc[CA_GROUPS][64];
+    __shared__ float sm_m[CA_GROUPS], sm_l[CA_GROUPS], sm_w[CA_GROUPS];
+    __shared__ float sm_L;
     const int r = blockIdx.x, h = blockIdx.y;
     if (row_active != nullptr && !row_active[r]) return;   // finished sequence: skip its K/V stream
     const int seq = row_seq[r];
     const int slot = head_slot[h];
-    if (threadIdx.x < 64) qs[threadIdx.x] = q[(int64_t)r * ldq + h * 64 + threadIdx.x];
-    __syncthreads();
-    float mx = -CUDART_INF_F;
-    if (slot >= 0) {
-        const float* K = k_align + ((int64_t)seq * n_slots + slot) * ctx * 64;
-        for (int j = threadIdx.x; j < ctx; j += CA_THREADS) {
-            const float4* kr = reinterpret_cast<const float4*>(K + (int64_t)j * 64);
-            float acc = 0.f;
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                const float4 kv = kr[c];
-                acc += qs[4 * c] * kv.x + qs[4 * c + 1] * kv.y + qs[4 * c + 2] * kv.z + qs[4 * c + 3] * kv.w;
-            }
-            sc[j] = acc;
-            mx = fmaxf(mx, acc);
-        }
-    } else {
-        const __half* K = k16 + ((int64_t)seq * H + h) * ctx * 64;
-        for (int j = threadIdx.x; j < ctx; j += CA_THREADS) {
-            const uint4* kr = reinterpret_cast<const uint4*>(K + (int64_t)j * 64);
-            uint4 raw[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) raw[c] = kr[c];
-            float acc = 0.f;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const __half2* h2 = reinterpret_cast<const __half2*>(&raw[c]);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float2 f = __half22float2(h2[e]);
-                    acc += qs[8 * c + 2 * e] * f.x + qs[8 * c + 2 * e + 1] * f.y;
-                }
-            }
-            sc[j] = acc;
-            mx = fmaxf(mx, acc);
-        }
-    }
-    __syncthreads();
-    if (qk_out != nullptr && slot >= 0) {
-        const int qr = qk_row[r];
-        if (qr >= 0) {
-            float* dst = qk_out + (((int64_t)seq * n_slots + slot) * qk_rows + qr) * (int64_t)ctx;
-            for (int j = threadIdx.x; j < ctx; j += CA_THREADS) dst[j] = sc[j];
-        }
-    }
-    mx = block_reduce_max(mx, red);
-    float sum = 0.f;
-    for (int j = threadIdx.x; j < ctx; j += CA_THREADS) {
-        const float e = expf(sc[j] - mx);
-        sc[j] = e;
-        sum += e;
-    }
-    sum = block_reduce_sum(sum, red);
-    const float inv = 1.0f / sum;
-    // weighted sum of V: thread = (group g of keys, 8-channel slice c8); one 16-byte load per key
     const int c8 = threadIdx.x & 7, g = threadIdx.x >> 3;
-    const __half* V = v16 + ((int64_t)seq * H + h) * ctx * 64 + c8 * 8;
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int j = g; j < ctx; j += 16) {
-        const uint4 raw = *reinterpret_cast<const uint4*>(V + (int64_t)j * 64);
-        const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
-        const float p = sc[j];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float2 f = __half22float2(h2[e]);
-            acc[2 * e] += p * f.x;
-            acc[2 * e + 1] += p * f.y;
-        }
+    float qf[8];
+    {
+        const float4* qp = reinterpret_cast<const float4*>(q + (int64_t)r * ldq + h * 64 + c8 * 8);
+        const float4 a = qp[0], b = qp[1];
+        qf[0] = a.x; qf[1] = a.y; qf[2] = a.z; qf[3] = a.w; qf[4] = b.x; qf[5] = b.y; qf[6] = b.z; qf[7] = b.w;
     }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) part[g * 64 + c8 * 8 + e] = acc[e];
+    float m = -1e30f, l = 0.f;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const __half* V = v16 + ((int64_t)seq * H + h) * ctx * 64;
+    if (slot >= 0) {
+        float* qk_dst = nullptr;
+        if (qk_out != nullptr) {
+            const int qr = qk_row[r];
+            if (qr >= 0) qk_dst = qk_out + (((int64_t)seq * n_slots + slot) * qk_rows + qr) * (int64_t)ctx;
+        }
+        ca_stream<true>(k_align + ((int64_t)seq * n_slots + slot) * ctx * 64, V, ctx, g, c8, qf, qk_dst, m, l, acc);
+    } else {
+        ca_stream<false>(k16 + ((int64_t)seq * H + h) * ctx * 64, V, ctx, g, c8, qf, nullptr, m, l, acc);
+    }
+    if (c8 == 0) { sm_m[g] = m; sm_l[g] = l; }
+    *reinterpret_cast<float4*>(&sm_acc[g][c8 * 8]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(&sm_acc[g][c8 * 8 + 4]) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const float mg = sm_m[threadIdx.x];
+        const float M = warp_max(mg);
+        const float w = __expf(mg - M);
+        sm_w[threadIdx.x] = w;
+        const float L = warp_sum(sm_l[threadIdx.x] * w);
+        if (threadIdx.x == 0) sm_L = L;
+    }
     __syncthreads();
     if (threadIdx.x < 64) {
         float y = 0.f;
 #pragma unroll
-        for (int gg = 0; gg < 16; ++gg) y += part[gg * 64 + threadIdx.x];
-        y *= inv;
+        for (int gg = 0; gg < CA_GROUPS; ++gg) y += sm_acc[gg][threadIdx.x] * sm_w[gg];
+        y /= sm_L;
         __nv_bfloat16 hi, lo;
         split_bf16(y, hi, lo);
         o[(int64_t)r * ldo + h * 64 + threadIdx.x] = hi;
@@ -732,9 +757,9 @@ extern "C" int wts_cross_attention_f16(const float* d_q, int64_t ldq, const void
                                        void* stream)
 {
     if (rows <= 0) return 0;
-    const size_t smem = ((size_t)ctx + 64 + 32 + 16 * 64) * sizeof(float);
+    if ((ldq & 3) || (reinterpret_cast<uintptr_t>(d_q) & 15)) { set_error("wts_cross_attention_f16: q must be 16-byte aligned"); return -2; }
     dim3 grid(rows, H);
-    cross_attention_f16_kernel<<<grid, CA_THREADS, smem, (cudaStream_t)stream>>>(
+    cross_attention_f16_kernel<<<grid, CA_THREADS, 0, (cudaStream_t)stream>>>(
         d_q, ldq, (const __half*)d_k16, (const __half*)d_v16, d_k_align, d_head_slot, n_slots, ctx, d_row_seq, H,
         (__nv_bfloat16*)d_out_sb16, ldo, o_plane, d_qk_out, qk_rows, d_qk_row, d_row_active);
     WTS_LAUNCH_CHECK();
