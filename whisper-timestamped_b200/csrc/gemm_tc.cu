@@ -120,6 +120,7 @@ struct TcArgs {
     float* ws;                                    // split-K flavour 2: partial sums are RED-accumulated into this
     int64_t ldws;                                 // zeroed float32 workspace; the LAST split CTA of a tile (ticket
     int* tickets;                                 // counter) applies the epilogue, then re-zeroes its tile + ticket
+    int debug;                                    // probes (WTS_GEMM_DEBUG): 1 = TMA only, 2 = MMA only, 3 = hi*hi only
 };
 
 __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d)
@@ -222,7 +223,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             const int azo = args.a_has_bo ? zo : 0, azi = args.a_has_bi ? zi : 0;
             const int bzo = args.b_has_bo ? zo : 0, bzi = args.b_has_bi ? zi : 0;
-            for (int kb = 0; kb < nkb; ++kb) {
+            for (int kb = 0; kb < (args.debug == 2 ? 0 : nkb); ++kb) {
                 const int s = kb % STAGES, u = kb / STAGES;
                 mbar_wait(bar_base + 64 + 8 * s, (u & 1) ^ 1);
                 const uint32_t full = bar_base + 8 * s;
@@ -241,8 +242,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES, u = kb / STAGES;
-                mbar_wait(bar_base + 8 * s, u & 1);
+                if (args.debug != 2) mbar_wait(bar_base + 8 * s, u & 1);
                 tc_fence_after();
+                if (args.debug == 1) {
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_base + 64 + 8 * s) : "memory");
+                    continue;
+                }
                 const uint32_t st = base + s * STAGE_BYTES;
                 const uint64_t a_hi = umma_desc(st), a_lo = umma_desc(st + TILE_BYTES);
                 const uint64_t b_hi = umma_desc(st + 2 * TILE_BYTES), b_lo = umma_desc(st + 2 * TILE_BYTES + B_TILE);
@@ -250,6 +255,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int k = 0; k < BK / 16; ++k) {
                     const uint64_t adv = (uint64_t)(k * 2);       // 32 bytes per K=16 step, in 16-byte units
                     umma_bf16(tmem_base, a_hi + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
+                    if (args.debug == 3) continue;
                     umma_bf16(tmem_base, a_lo + adv, b_hi + adv, idesc, 1u);
                     umma_bf16(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
                 }
@@ -350,6 +356,190 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+// ------------------------------------------------------------------------------------ skinny (decode) GEMM
+// M <= 128 rows (one row per decoded window): weight-bandwidth / latency bound.  The operands trade places: the
+// 128 x 64 WEIGHT box is the UMMA "A" operand (M = 128 output features), the activations are the "B" operand
+// (UMMA N = rows rounded up to 16), so the accumulator holds C^T: TMEM lane = output feature n, column = row m.
+// An epilogue thread then owns ONE feature and walks the rows: every global access of a warp (stores, float32
+// REDs of the split-K partial sums, workspace reads) covers 32 consecutive features of one row — 128-byte
+// coalesced, 8x fewer L2 requests than the row-per-thread layout, which is what bounded these kernels before.
+// grid = (ceil(N/128), split_k): K is split so that one wave covers the SMs; partial sums meet in float32
+// either directly in out_f32 (linear in-place residual update) or in the workspace with a last-arriver epilogue.
+struct SkArgs {
+    WtsGemm g;
+    int split_k, inplace;
+    float* ws;
+    int64_t ldws;
+    int* tickets;
+    int bn;                 // UMMA N: rows rounded up to a multiple of 16
+    int stages, stage_bytes;
+};
+
+constexpr int SK_SMEM = 3 * 65536 + 256 + 1024;
+
+__device__ __forceinline__ void sk_finish(const WtsGemm& g, float t, int m, int n, float bias_n, float* of, __nv_bfloat16* ob)
+{
+    if (g.bias) t += g.bias_on_m ? g.bias[m] : bias_n;
+    if (g.act == 1) t = gelu_erf_tc(t);
+    if (g.residual) t += g.residual[(int64_t)m * g.ldr + n];
+    if (of) of[(int64_t)m * g.ldc + n] = t;
+    if (ob) {
+        const __nv_bfloat16 hi = __float2bfloat16_rn(t);
+        ob[(int64_t)m * g.ldo + n] = hi;
+        ob[(int64_t)m * g.ldo + n + g.o_plane] = __float2bfloat16_rn(t - __bfloat162float(hi));
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const SkArgs args)
+{
+    extern __shared__ unsigned char smem_raw[];
+    const WtsGemm& g = args.g;
+    const uint32_t base = (smem_addr(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = base + 3 * 65536;
+    // barriers: full[s] at +8s (s < 8), empty[s] at +64+8s, tmem_full at +128, tmem pointer at +136, flag at +144
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BM;
+    const int nkb_all = (g.K + BK - 1) / BK;
+    const int kb0 = (int)((int64_t)blockIdx.y * nkb_all / args.split_k);
+    const int kb1 = (int)((int64_t)(blockIdx.y + 1) * nkb_all / args.split_k);
+    const int nkb = kb1 - kb0;
+    const int STAGES = args.stages, STAGE_BYTES = args.stage_bytes;
+    const int X_TILE = args.bn * BK * 2;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) { mbar_init(bar_base + 8 * s, 1); mbar_init(bar_base + 64 + 8 * s, 1); }
+            mbar_init(bar_base + 128, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bar_base + 136), "r"(128) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(bar_base + 136));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES, u = kb / STAGES;
+                mbar_wait(bar_base + 64 + 8 * s, (u & 1) ^ 1);
+                const uint32_t full = bar_base + 8 * s;
+                mbar_expect_tx(full, STAGE_BYTES);
+                const uint32_t st = base + s * STAGE_BYTES;
+                const int kc = (kb0 + kb) * BK;
+                tma_load_5d(st, &tmW, full, kc, n0, 0, 0, 0);
+                tma_load_5d(st + TILE_BYTES, &tmW, full, kc, n0, 0, 0, 1);
+                tma_load_5d(st + 2 * TILE_BYTES, &tmX, full, kc, 0, 0, 0, 0);
+                tma_load_5d(st + 2 * TILE_BYTES + X_TILE, &tmX, full, kc, 0, 0, 0, 1);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(args.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES, u = kb / STAGES;
+                mbar_wait(bar_base + 8 * s, u & 1);
+                tc_fence_after();
+                const uint32_t st = base + s * STAGE_BYTES;
+                const uint64_t w_hi = umma_desc(st), w_lo = umma_desc(st + TILE_BYTES);
+                const uint64_t x_hi = umma_desc(st + 2 * TILE_BYTES), x_lo = umma_desc(st + 2 * TILE_BYTES + X_TILE);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    const uint64_t adv = (uint64_t)(k * 2);
+                    umma_bf16(tmem_base, w_hi + adv, x_hi + adv, idesc, (kb | k) ? 1u : 0u);
+                    umma_bf16(tmem_base, w_lo + adv, x_hi + adv, idesc, 1u);
+                    umma_bf16(tmem_base, w_hi + adv, x_lo + adv, idesc, 1u);
+                }
+                umma_commit(bar_base + 64 + 8 * s);
+            }
+            umma_commit(bar_base + 128);
+        }
+    } else {
+        // ---------------- epilogue: this thread owns output feature n and walks the rows m
+        const int q = warp & 3;
+        const int n = n0 + 32 * q + lane;
+        const bool n_ok = n < g.N;
+        const int nchunk = (g.M + 31) / 32;
+        float* of = g.out_f32;
+        __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(g.out_sb16);
+        const float bias_n = (g.bias && !g.bias_on_m && n_ok) ? g.bias[n] : 0.f;
+        mbar_wait(bar_base + 128, 0);
+        tc_fence_after();
+        const bool split = args.split_k > 1;
+        float* acc = args.inplace ? of : args.ws;
+        const int64_t ldacc = args.inplace ? g.ldc : args.ldws;
+#pragma unroll 1
+        for (int c = 0; c < nchunk; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), v);
+            if (!n_ok) continue;
+            if (!split) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int m = 32 * c + j;
+                    if (m < g.M) sk_finish(g, g.alpha * __uint_as_float(v[j]), m, n, bias_n, of, ob);
+                }
+            } else {
+                const bool add_bias = args.inplace && g.bias && blockIdx.y == 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int m = 32 * c + j;
+                    if (m < g.M) {
+                        float t = g.alpha * __uint_as_float(v[j]);
+                        if (add_bias) t += g.bias_on_m ? g.bias[m] : bias_n;
+                        atomicAdd(acc + (int64_t)m * ldacc + n, t);      // result unused: compiles to RED
+                    }
+                }
+            }
+        }
+        if (split && !args.inplace) {
+            volatile int* flag = reinterpret_cast<volatile int*>(smem_raw + (bar_base - smem_addr(smem_raw)) + 144);
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (threadIdx.x == 64) *flag = (atomicAdd(args.tickets + blockIdx.x, 1) == args.split_k - 1) ? 1 : 0;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (*flag) {
+                __threadfence();
+                if (n_ok) {
+#pragma unroll 1
+                    for (int c = 0; c < nchunk; ++c) {
+                        float y[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int m = 32 * c + j;
+                            y[j] = (m < g.M) ? __ldcg(args.ws + (int64_t)m * args.ldws + n) : 0.f;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int m = 32 * c + j;
+                            if (m < g.M) {
+                                __stcg(args.ws + (int64_t)m * args.ldws + n, 0.f);
+                                sk_finish(g, y[j], m, n, bias_n, of, ob);
+                            }
+                        }
+                    }
+                }
+                if (threadIdx.x == 64) args.tickets[blockIdx.x] = 0;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------------------------------- host side
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode()
 {
@@ -442,6 +632,7 @@ static int launch_bn(const WtsGemm& g, cudaStream_t st, int split_k, bool inplac
     args.b_has_bo = g.b_bo != 0; args.b_has_bi = g.b_bi != 0;
     args.split_k = split_k;
     args.inplace = inplace ? 1 : 0;
+    { const char* e = getenv("WTS_GEMM_DEBUG"); args.debug = e ? atoi(e) : 0; }
     args.ws = nullptr; args.tickets = nullptr; args.ldws = WS_LD;
     if (split_k > 1 && !inplace) {
         SplitWs w;
@@ -455,9 +646,43 @@ static int launch_bn(const WtsGemm& g, cudaStream_t st, int split_k, bool inplac
     return 0;
 }
 
+static int launch_skinny(const WtsGemm& g, cudaStream_t st, int split_k, bool inplace)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        WTS_CUDA_CHECK(cudaFuncSetAttribute(gemm_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM));
+        attr_set = true;
+    }
+    SkArgs args;
+    args.g = g;
+    args.bn = ((g.M + 15) / 16) * 16;
+    args.stage_bytes = 2 * TILE_BYTES + 2 * args.bn * BK * 2;
+    args.stages = (3 * 65536) / args.stage_bytes;
+    if (args.stages > 8) args.stages = 8;
+    alignas(64) CUtensorMap tmW, tmX;
+    int rc = make_map(&tmW, g.b, g.K, g.N, g.ldb, g.b_plane, 1, 0, 1, 0, BM, "B(weights)");
+    if (rc) return rc;
+    rc = make_map(&tmX, g.a, g.K, g.M, g.lda, g.a_plane, 1, 0, 1, 0, args.bn, "A(rows)");
+    if (rc) return rc;
+    args.split_k = split_k;
+    args.inplace = inplace ? 1 : 0;
+    args.ws = nullptr; args.tickets = nullptr; args.ldws = WS_LD;
+    if (split_k > 1 && !inplace) {
+        SplitWs w;
+        rc = get_split_ws(&w);
+        if (rc) return rc;
+        args.ws = w.ws; args.tickets = w.tickets;
+    }
+    dim3 grid((g.N + BM - 1) / BM, split_k);
+    gemm_skinny_kernel<<<grid, TC_THREADS, SK_SMEM, st>>>(tmW, tmX, args);
+    WTS_LAUNCH_CHECK();
+    return 0;
+}
+
 int gemm_tc_launch(const WtsGemm& g, cudaStream_t st)
 {
-    // WTS_SKINNY_GEMM: 1 (default) = 128-wide tiles split along K over ~all SMs; 32 = the older 32-wide tiles; 0 = off
+    // WTS_SKINNY_GEMM: 1 (default) = gemm_skinny_kernel (operands swapped, split K over ~all SMs); 128 / 32 = the
+    // row-per-thread kernels with 128- / 32-wide tiles (kept for A/B timing); 0 = off
     static const int skinny = []{ const char* e = getenv("WTS_SKINNY_GEMM"); return e ? atoi(e) : 1; }();
     static const int splitk = []{ const char* e = getenv("WTS_SPLITK"); return e ? atoi(e) : 1; }();
     const bool one_batch = g.batch_outer * g.batch_inner == 1;
@@ -476,7 +701,8 @@ int gemm_tc_launch(const WtsGemm& g, cudaStream_t st)
             if (split < 1) split = 1;
         }
         if (bn == 32) return launch_bn<32>(g, st, inplace ? split : 1, inplace);
-        return launch_bn<128>(g, st, split, inplace);
+        if (skinny == 128 || g.head_dim != 0) return launch_bn<128>(g, st, g.head_dim != 0 ? 1 : split, inplace);
+        return launch_skinny(g, st, split, inplace);
     }
     return launch_bn<128>(g, st, 1, false);
 }
