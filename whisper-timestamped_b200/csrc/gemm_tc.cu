@@ -5,7 +5,7 @@
 // (the dropped lo*lo term is ~2^-16 relative).  That keeps logits and cross-attention scores within
 // the 1e-3 bar of the reference's float32 CPU path while running on the 5th-generation tensor cores.
 //
-// One CTA per 128x128 output tile, 192 threads, warp-specialised:
+// gemm_tc_kernel: one CTA per 128x128 output tile, 192 threads, warp-specialised:
 //   warp 0 (one lane)  TMA producer: 4 boxes (A_hi, A_lo, B_hi, B_lo; 64 x 128 bf16, SWIZZLE_128B) per
 //                      k-block into a 3-stage shared-memory ring, completion on an mbarrier (expect_tx)
 //   warp 1 (one lane)  MMA issuer: tcgen05.mma.cta_group::1.kind::f16 M128 N128 K16, accumulator in TMEM
@@ -13,6 +13,8 @@
 //   warps 2..5         epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> alpha/bias/GELU/residual ->
 //                      float32 and/or SB16 stores (optionally head-major for the K/V caches)
 // Batched problems (two batch levels) are extra tensor-map dimensions; M/N/K tails rely on TMA zero fill.
+//
+// gemm_skinny_kernel: the decode-time GEMM (M <= 128 rows, one per decoded window), see its own header below.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cudaTypedefs.h>
@@ -27,10 +29,8 @@ namespace wts {
 constexpr int BM = 128, BK = 64;
 constexpr int TILE_BYTES = BM * BK * 2;                 // 16 KB: one 128 x 64 bf16 box (A planes)
 constexpr int TC_THREADS = 192;
-// Two instantiations: BN = 128 (3-stage ring) for the big encoder GEMMs, BN = 32 (5-stage ring, optional
-// split-K) for the skinny decode GEMMs (M <= 128) where the CTA count, not the tensor pipe, limits throughput.
 template <int BN> struct TcCfg {
-    static constexpr int STAGES = BN >= 128 ? 3 : 5;
+    static constexpr int STAGES = 3;
     static constexpr int B_TILE = BN * BK * 2;
     static constexpr int STAGE_BYTES = 2 * TILE_BYTES + 2 * B_TILE;
     static constexpr int SMEM = STAGES * STAGE_BYTES + 256 + 1024;
@@ -114,19 +114,8 @@ __device__ __forceinline__ float gelu_erf_tc(float v) { return 0.5f * v * (1.0f 
 struct TcArgs {
     WtsGemm g;
     int a_has_bo, a_has_bi, b_has_bo, b_has_bi;   // 0 => that batch stride is 0 (operand shared): coordinate 0
-    int split_k;                                  // > 1: blockIdx.z is a K split (batch must be 1)
-    int inplace;                                  // split-K flavour 1: out_f32 already holds the residual and the
-                                                  // epilogue is linear, partial sums go straight into it (RED)
-    float* ws;                                    // split-K flavour 2: partial sums are RED-accumulated into this
-    int64_t ldws;                                 // zeroed float32 workspace; the LAST split CTA of a tile (ticket
-    int* tickets;                                 // counter) applies the epilogue, then re-zeroes its tile + ticket
     int debug;                                    // probes (WTS_GEMM_DEBUG): 1 = TMA only, 2 = MMA only, 3 = hi*hi only
 };
-
-__device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d)
-{
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
 
 // alpha/bias/GELU/residual + float32 and/or SB16 stores of 32 consecutive columns of one output row
 __device__ __forceinline__ void epilogue_chunk(const WtsGemm& g, float (&y)[32], int m, int nb, float bias_m, const float* res,
@@ -192,12 +181,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // barriers: full[s] at +8s, empty[s] at +64+8s, tmem_full at +128, tmem pointer at +136
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const bool split = args.split_k > 1;
-    const int z = split ? 0 : blockIdx.z, zo = z / g.batch_inner, zi = z - zo * g.batch_inner;
-    const int nkb_all = (g.K + BK - 1) / BK;
-    const int kb0 = split ? (int)((int64_t)blockIdx.z * nkb_all / args.split_k) : 0;
-    const int kb1 = split ? (int)((int64_t)(blockIdx.z + 1) * nkb_all / args.split_k) : nkb_all;
-    const int nkb = kb1 - kb0;
+    const int z = blockIdx.z, zo = z / g.batch_inner, zi = z - zo * g.batch_inner;
+    const int nkb = (g.K + BK - 1) / BK;
+    constexpr int kb0 = 0;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -274,78 +260,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float* of = g.out_f32 ? g.out_f32 + (int64_t)zo * g.c_bo + (int64_t)zi * g.c_bi : nullptr;
         __nv_bfloat16* ob = g.out_sb16 ? reinterpret_cast<__nv_bfloat16*>(g.out_sb16) + (int64_t)zo * g.o_bo + (int64_t)zi * g.o_bi : nullptr;
         const float bias_m = (g.bias && g.bias_on_m && row_ok) ? g.bias[m] : 0.f;
-        if (!split) {
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), v);
-                const int nb = n0 + 32 * c;
-                if (!row_ok || nb >= g.N) continue;
-                float y[32];
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), v);
+            const int nb = n0 + 32 * c;
+            if (!row_ok || nb >= g.N) continue;
+            float y[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) y[j] = g.alpha * __uint_as_float(v[j]);
-                epilogue_chunk(g, y, m, nb, bias_m, res, of, ob);
-            }
-        } else {
-            // ---- split-K: RED the partial tile into out_f32 (in-place flavour) or into the workspace
-            float* acc = args.inplace ? of : args.ws;
-            const int64_t ldacc = args.inplace ? g.ldc : args.ldws;
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), v);
-                const int nb = n0 + 32 * c;
-                if (!row_ok || nb >= g.N) continue;
-                float* dst = acc + (int64_t)m * ldacc + nb;
-                float t[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    t[j] = g.alpha * __uint_as_float(v[j]);
-                    if (args.inplace && g.bias && blockIdx.z == 0) t[j] += g.bias_on_m ? bias_m : (nb + j < g.N ? g.bias[nb + j] : 0.f);
-                }
-                if (nb + 32 <= g.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) red_add_v4(dst + j, t[j], t[j + 1], t[j + 2], t[j + 3]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) if (nb + j < g.N) atomicAdd(dst + j, t[j]);
-                }
-            }
-            if (!args.inplace) {
-                // ---- ticket: the last split CTA of this tile owns the complete sums and runs the real epilogue
-                volatile int* flag = reinterpret_cast<volatile int*>(smem_raw + (bar_base - smem_addr(smem_raw)) + 144);
-                __threadfence();
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-                if (threadIdx.x == 64) *flag = (atomicAdd(args.tickets + tile, 1) == args.split_k - 1) ? 1 : 0;
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (*flag) {
-                    __threadfence();
-#pragma unroll 1
-                    for (int c = 0; c < BN / 32; ++c) {
-                        const int nb = n0 + 32 * c;
-                        if (!row_ok || nb >= g.N) continue;
-                        float* src = args.ws + (int64_t)m * args.ldws + nb;
-                        float y[32];
-                        if (nb + 32 <= g.N && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const float4 f = __ldcg(reinterpret_cast<const float4*>(src + j));
-                                y[j] = f.x; y[j + 1] = f.y; y[j + 2] = f.z; y[j + 3] = f.w;
-                                __stcg(reinterpret_cast<float4*>(src + j), make_float4(0.f, 0.f, 0.f, 0.f));
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                y[j] = 0.f;
-                                if (nb + j < g.N) { y[j] = __ldcg(src + j); __stcg(src + j, 0.f); }
-                            }
-                        }
-                        epilogue_chunk(g, y, m, nb, bias_m, res, of, ob);
-                    }
-                    if (threadIdx.x == 64) args.tickets[tile] = 0;
-                }
-            }
+            for (int j = 0; j < 32; ++j) y[j] = g.alpha * __uint_as_float(v[j]);
+            epilogue_chunk(g, y, m, nb, bias_m, res, of, ob);
         }
     }
     tc_fence_before();
@@ -357,20 +281,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------ skinny (decode) GEMM
-// M <= 128 rows (one row per decoded window): weight-bandwidth / latency bound.  The operands trade places: the
-// 128 x 64 WEIGHT box is the UMMA "A" operand (M = 128 output features), the activations are the "B" operand
-// (UMMA N = rows rounded up to 16), so the accumulator holds C^T: TMEM lane = output feature n, column = row m.
-// An epilogue thread then owns ONE feature and walks the rows: every global access of a warp (stores, float32
-// REDs of the split-K partial sums, workspace reads) covers 32 consecutive features of one row — 128-byte
-// coalesced, 8x fewer L2 requests than the row-per-thread layout, which is what bounded these kernels before.
-// grid = (ceil(N/128), split_k): K is split so that one wave covers the SMs; partial sums meet in float32
-// either directly in out_f32 (linear in-place residual update) or in the workspace with a last-arriver epilogue.
+// M <= 128 rows (one row per decoded window): weight-bandwidth / latency bound, never tensor bound.
+//  * The operands trade places: the 128 x 64 WEIGHT box is the UMMA "A" operand (M = 128 output features), the
+//    activation rows are the "B" operand (UMMA N = rows rounded up to 16; a single window costs a 16-row box, not
+//    128), so the accumulator holds C^T: TMEM lane = output feature n, column = row m.  An epilogue thread owns
+//    one feature and walks the rows: every global access of a warp covers 32 consecutive features of one row.
+//  * K is split over the CTAs of a thread-block CLUSTER (grid = (N tiles, S), cluster = (1, S, 1), S <= 8) so
+//    that one wave of tiles x S CTAs streams the weights.  Each CTA parks its float32 partial tile in its own
+//    shared memory (the idle operand ring), the cluster synchronises, and CTA r reduces rows r*M/S.. of all S
+//    partials over distributed shared memory (ld.shared::cluster) and applies the epilogue to them: no atomics,
+//    no global workspace, a fixed summation order (bit-reproducible), and the epilogue itself is spread over S SMs.
 struct SkArgs {
     WtsGemm g;
-    int split_k, inplace;
-    float* ws;
-    int64_t ldws;
-    int* tickets;
+    int split_k;
     int bn;                 // UMMA N: rows rounded up to a multiple of 16
     int stages, stage_bytes;
 };
@@ -390,6 +313,12 @@ __device__ __forceinline__ void sk_finish(const WtsGemm& g, float t, int m, int 
     }
 }
 
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const SkArgs args)
 {
@@ -397,12 +326,13 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     const WtsGemm& g = args.g;
     const uint32_t base = (smem_addr(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = base + 3 * 65536;
-    // barriers: full[s] at +8s (s < 8), empty[s] at +64+8s, tmem_full at +128, tmem pointer at +136, flag at +144
+    // barriers: full[s] at +8s (s < 8), empty[s] at +64+8s, tmem_full at +128, tmem pointer at +136
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * BM;
+    const int S = args.split_k;
     const int nkb_all = (g.K + BK - 1) / BK;
-    const int kb0 = (int)((int64_t)blockIdx.y * nkb_all / args.split_k);
-    const int kb1 = (int)((int64_t)(blockIdx.y + 1) * nkb_all / args.split_k);
+    const int kb0 = (int)((int64_t)blockIdx.y * nkb_all / S);
+    const int kb1 = (int)((int64_t)(blockIdx.y + 1) * nkb_all / S);
     const int nkb = kb1 - kb0;
     const int STAGES = args.stages, STAGE_BYTES = args.stage_bytes;
     const int X_TILE = args.bn * BK * 2;
@@ -426,6 +356,13 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(bar_base + 136));
+
+    const int q = warp & 3;
+    const int nl = 32 * q + lane;                  // feature of this epilogue thread inside the tile
+    const int n = n0 + nl;
+    const bool n_ok = n < g.N;
+    float* of = g.out_f32;
+    __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(g.out_sb16);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -464,73 +401,65 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
             umma_commit(bar_base + 128);
         }
     } else {
-        // ---------------- epilogue: this thread owns output feature n and walks the rows m
-        const int q = warp & 3;
-        const int n = n0 + 32 * q + lane;
-        const bool n_ok = n < g.N;
+        // ---------------- epilogue, part 1: accumulator (lane = feature, column = row) out of TMEM
         const int nchunk = (g.M + 31) / 32;
-        float* of = g.out_f32;
-        __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(g.out_sb16);
         const float bias_n = (g.bias && !g.bias_on_m && n_ok) ? g.bias[n] : 0.f;
         mbar_wait(bar_base + 128, 0);
         tc_fence_after();
-        const bool split = args.split_k > 1;
-        float* acc = args.inplace ? of : args.ws;
-        const int64_t ldacc = args.inplace ? g.ldc : args.ldws;
+        float* part = reinterpret_cast<float*>(smem_raw + (base - smem_addr(smem_raw)));   // [rows][128] partial sums
 #pragma unroll 1
         for (int c = 0; c < nchunk; ++c) {
             uint32_t v[32];
             tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), v);
-            if (!n_ok) continue;
-            if (!split) {
+            if (S == 1) {
+                if (!n_ok) continue;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int m = 32 * c + j;
                     if (m < g.M) sk_finish(g, g.alpha * __uint_as_float(v[j]), m, n, bias_n, of, ob);
                 }
             } else {
-                const bool add_bias = args.inplace && g.bias && blockIdx.y == 0;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int m = 32 * c + j;
-                    if (m < g.M) {
-                        float t = g.alpha * __uint_as_float(v[j]);
-                        if (add_bias) t += g.bias_on_m ? g.bias[m] : bias_n;
-                        atomicAdd(acc + (int64_t)m * ldacc + n, t);      // result unused: compiles to RED
-                    }
+                    if (m < g.M) part[m * BM + nl] = g.alpha * __uint_as_float(v[j]);
                 }
             }
         }
-        if (split && !args.inplace) {
-            volatile int* flag = reinterpret_cast<volatile int*>(smem_raw + (bar_base - smem_addr(smem_raw)) + 144);
-            __threadfence();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (threadIdx.x == 64) *flag = (atomicAdd(args.tickets + blockIdx.x, 1) == args.split_k - 1) ? 1 : 0;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (*flag) {
-                __threadfence();
-                if (n_ok) {
-#pragma unroll 1
-                    for (int c = 0; c < nchunk; ++c) {
-                        float y[32];
+    }
+    if (S > 1) {
+        // ---------------- part 2: cluster-wide reduction over distributed shared memory
+        __syncwarp();
+        cluster_sync_all();                          // every partial tile is parked and visible cluster-wide
+        if (warp >= 2 && n_ok) {
+            uint32_t rank;
+            asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+            const int rows_per = (g.M + S - 1) / S;
+            const int m_begin = (int)rank * rows_per;
+            const int m_end = min(g.M, m_begin + rows_per);
+            const float bias_n = (g.bias && !g.bias_on_m) ? g.bias[n] : 0.f;
+            uint32_t peer[8];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int m = 32 * c + j;
-                            y[j] = (m < g.M) ? __ldcg(args.ws + (int64_t)m * args.ldws + n) : 0.f;
-                        }
+            for (int s = 0; s < 8; ++s) {
+                peer[s] = 0;
+                if (s < S) asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer[s]) : "r"(base + 4u * nl), "r"(s));
+            }
+#pragma unroll 2
+            for (int m = m_begin; m < m_end; ++m) {
+                float t = 0.f;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int m = 32 * c + j;
-                            if (m < g.M) {
-                                __stcg(args.ws + (int64_t)m * args.ldws + n, 0.f);
-                                sk_finish(g, y[j], m, n, bias_n, of, ob);
-                            }
-                        }
+                for (int s = 0; s < 8; ++s) {
+                    if (s < S) {
+                        float x;
+                        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(x) : "r"(peer[s] + (uint32_t)(m * BM * 4)) : "memory");
+                        t += x;
                     }
                 }
-                if (threadIdx.x == 64) args.tickets[blockIdx.x] = 0;
+                sk_finish(g, t, m, n, bias_n, of, ob);
             }
         }
+        __syncwarp();
+        cluster_sync_all();                          // nobody leaves while a peer may still read its partial tile
     }
     tc_fence_before();
     __syncthreads();
@@ -584,38 +513,9 @@ static int make_map(CUtensorMap* tm, const void* ptr, int64_t K, int64_t rows, i
     return 0;
 }
 
-// Split-K workspace of the current device: float32 [128, WS_LD] sums + one ticket per output tile, zero between
-// GEMMs (every finalising CTA cleans up after itself).  One GEMM at a time per device may use it: launches that
-// share it must be stream-ordered (the engine issues all its work on one stream).
-constexpr int64_t WS_LD = 148 * 128;
-struct SplitWs { float* ws = nullptr; int* tickets = nullptr; };
-static int get_split_ws(SplitWs* out)
+static int launch_big(const WtsGemm& g, cudaStream_t st)
 {
-    static std::mutex mu;
-    static SplitWs per_dev[64];
-    int dev = 0;
-    WTS_CUDA_CHECK(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64) { set_error("wts_gemm: device ordinal %d out of range", dev); return -7; }
-    std::lock_guard<std::mutex> lock(mu);
-    if (!per_dev[dev].ws) {
-        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-        (void)cs;
-        float* w = nullptr;
-        int* t = nullptr;
-        WTS_CUDA_CHECK(cudaMalloc(&w, (size_t)BM * WS_LD * sizeof(float)));
-        WTS_CUDA_CHECK(cudaMalloc(&t, 256 * sizeof(int)));
-        WTS_CUDA_CHECK(cudaMemset(w, 0, (size_t)BM * WS_LD * sizeof(float)));
-        WTS_CUDA_CHECK(cudaMemset(t, 0, 256 * sizeof(int)));
-        per_dev[dev].ws = w;
-        per_dev[dev].tickets = t;
-    }
-    *out = per_dev[dev];
-    return 0;
-}
-
-template <int BN>
-static int launch_bn(const WtsGemm& g, cudaStream_t st, int split_k, bool inplace)
-{
+    constexpr int BN = 128;
     static bool attr_set = false;
     if (!attr_set) {
         WTS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM));
@@ -630,23 +530,14 @@ static int launch_bn(const WtsGemm& g, cudaStream_t st, int split_k, bool inplac
     args.g = g;
     args.a_has_bo = g.a_bo != 0; args.a_has_bi = g.a_bi != 0;
     args.b_has_bo = g.b_bo != 0; args.b_has_bi = g.b_bi != 0;
-    args.split_k = split_k;
-    args.inplace = inplace ? 1 : 0;
     { const char* e = getenv("WTS_GEMM_DEBUG"); args.debug = e ? atoi(e) : 0; }
-    args.ws = nullptr; args.tickets = nullptr; args.ldws = WS_LD;
-    if (split_k > 1 && !inplace) {
-        SplitWs w;
-        rc = get_split_ws(&w);
-        if (rc) return rc;
-        args.ws = w.ws; args.tickets = w.tickets;
-    }
-    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, split_k > 1 ? split_k : g.batch_outer * g.batch_inner);
+    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.batch_outer * g.batch_inner);
     gemm_tc_kernel<BN><<<grid, TC_THREADS, TcCfg<BN>::SMEM, st>>>(tmA, tmB, args);
     WTS_LAUNCH_CHECK();
     return 0;
 }
 
-static int launch_skinny(const WtsGemm& g, cudaStream_t st, int split_k, bool inplace)
+static int launch_skinny(const WtsGemm& g, cudaStream_t st, int split_k)
 {
     static bool attr_set = false;
     if (!attr_set) {
@@ -659,52 +550,45 @@ static int launch_skinny(const WtsGemm& g, cudaStream_t st, int split_k, bool in
     args.stage_bytes = 2 * TILE_BYTES + 2 * args.bn * BK * 2;
     args.stages = (3 * 65536) / args.stage_bytes;
     if (args.stages > 8) args.stages = 8;
+    args.split_k = split_k;
     alignas(64) CUtensorMap tmW, tmX;
     int rc = make_map(&tmW, g.b, g.K, g.N, g.ldb, g.b_plane, 1, 0, 1, 0, BM, "B(weights)");
     if (rc) return rc;
     rc = make_map(&tmX, g.a, g.K, g.M, g.lda, g.a_plane, 1, 0, 1, 0, args.bn, "A(rows)");
     if (rc) return rc;
-    args.split_k = split_k;
-    args.inplace = inplace ? 1 : 0;
-    args.ws = nullptr; args.tickets = nullptr; args.ldws = WS_LD;
-    if (split_k > 1 && !inplace) {
-        SplitWs w;
-        rc = get_split_ws(&w);
-        if (rc) return rc;
-        args.ws = w.ws; args.tickets = w.tickets;
-    }
-    dim3 grid((g.N + BM - 1) / BM, split_k);
-    gemm_skinny_kernel<<<grid, TC_THREADS, SK_SMEM, st>>>(tmW, tmX, args);
-    WTS_LAUNCH_CHECK();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((g.N + BM - 1) / BM, split_k, 1);
+    cfg.blockDim = dim3(TC_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = SK_SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = split_k;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    WTS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_skinny_kernel, tmW, tmX, args));
     return 0;
 }
 
 int gemm_tc_launch(const WtsGemm& g, cudaStream_t st)
 {
-    // WTS_SKINNY_GEMM: 1 (default) = gemm_skinny_kernel (operands swapped, split K over ~all SMs); 128 / 32 = the
-    // row-per-thread kernels with 128- / 32-wide tiles (kept for A/B timing); 0 = off
+    // WTS_SKINNY_GEMM=0 sends decode-time GEMMs through the generic kernel; WTS_SPLITK=0 disables the K split
     static const int skinny = []{ const char* e = getenv("WTS_SKINNY_GEMM"); return e ? atoi(e) : 1; }();
     static const int splitk = []{ const char* e = getenv("WTS_SPLITK"); return e ? atoi(e) : 1; }();
-    const bool one_batch = g.batch_outer * g.batch_inner == 1;
-    if (skinny && g.M <= BM && one_batch) {
-        // decode-time GEMM: one M tile, weight-bandwidth bound.  Split K so that tiles x splits fills the SMs in one
-        // wave; partial sums meet in float32 (RED) either directly in out_f32 when the epilogue is the linear
-        // in-place residual update (x += A W^T + b), or in the workspace with a last-arriver epilogue.
-        const int bn = skinny == 32 ? 32 : 128;
-        const int tiles = (g.N + bn - 1) / bn, nkb = (g.K + BK - 1) / BK;
-        const bool inplace = g.out_f32 && g.residual == g.out_f32 && g.act == 0 && !g.out_sb16 && g.head_dim == 0;
+    if (skinny && g.M <= BM && g.batch_outer * g.batch_inner == 1 && g.head_dim == 0) {
+        const int tiles = (g.N + BM - 1) / BM, nkb = (g.K + BK - 1) / BK;
         int split = 1;
-        if (splitk && tiles <= 74 && g.N <= WS_LD) {
+        if (splitk && tiles <= 74) {
             split = 148 / tiles;
+            if (split > 8) split = 8;                 // portable cluster size
             if (split > nkb) split = nkb;
-            if (bn == 32 && split > 8) split = 8;
             if (split < 1) split = 1;
         }
-        if (bn == 32) return launch_bn<32>(g, st, inplace ? split : 1, inplace);
-        if (skinny == 128 || g.head_dim != 0) return launch_bn<128>(g, st, g.head_dim != 0 ? 1 : split, inplace);
-        return launch_skinny(g, st, split, inplace);
+        return launch_skinny(g, st, split);
     }
-    return launch_bn<128>(g, st, 1, false);
+    return launch_big(g, st);
 }
 
 }  // namespace wts
