@@ -296,15 +296,17 @@ struct SkArgs {
     int split_k;
     int bn;                 // UMMA N: rows rounded up to a multiple of 16
     int stages, stage_bytes;
+    int debug;              // probes (WTS_GEMM_DEBUG): 1 = TMA only, 2 = MMA only, 4 = no main loop, 5 = launch + exit
 };
 
 constexpr int SK_SMEM = 3 * 65536 + 256 + 1024;
 
-__device__ __forceinline__ void sk_finish(const WtsGemm& g, float t, int m, int n, float bias_n, float* of, __nv_bfloat16* ob)
+__device__ __forceinline__ void sk_finish(const WtsGemm& g, float t, float resid, int m, int n, float bias_n, float* of,
+                                          __nv_bfloat16* ob)
 {
     if (g.bias) t += g.bias_on_m ? g.bias[m] : bias_n;
     if (g.act == 1) t = gelu_erf_tc(t);
-    if (g.residual) t += g.residual[(int64_t)m * g.ldr + n];
+    t += resid;
     if (of) of[(int64_t)m * g.ldc + n] = t;
     if (ob) {
         const __nv_bfloat16 hi = __float2bfloat16_rn(t);
@@ -333,9 +335,10 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     const int nkb_all = (g.K + BK - 1) / BK;
     const int kb0 = (int)((int64_t)blockIdx.y * nkb_all / S);
     const int kb1 = (int)((int64_t)(blockIdx.y + 1) * nkb_all / S);
-    const int nkb = kb1 - kb0;
+    const int nkb = args.debug == 4 ? 0 : kb1 - kb0;
     const int STAGES = args.stages, STAGE_BYTES = args.stage_bytes;
     const int X_TILE = args.bn * BK * 2;
+    if (args.debug == 5) return;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
@@ -366,7 +369,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < nkb; ++kb) {
+            for (int kb = 0; kb < (args.debug == 2 ? 0 : nkb); ++kb) {
                 const int s = kb % STAGES, u = kb / STAGES;
                 mbar_wait(bar_base + 64 + 8 * s, (u & 1) ^ 1);
                 const uint32_t full = bar_base + 8 * s;
@@ -384,8 +387,12 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(args.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES, u = kb / STAGES;
-                mbar_wait(bar_base + 8 * s, u & 1);
+                if (args.debug != 2) mbar_wait(bar_base + 8 * s, u & 1);
                 tc_fence_after();
+                if (args.debug == 1) {
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_base + 64 + 8 * s) : "memory");
+                    continue;
+                }
                 const uint32_t st = base + s * STAGE_BYTES;
                 const uint64_t w_hi = umma_desc(st), w_lo = umma_desc(st + TILE_BYTES);
                 const uint64_t x_hi = umma_desc(st + 2 * TILE_BYTES), x_lo = umma_desc(st + 2 * TILE_BYTES + X_TILE);
@@ -413,10 +420,16 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
             tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), v);
             if (S == 1) {
                 if (!n_ok) continue;
+                float r[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int m = 32 * c + j;
-                    if (m < g.M) sk_finish(g, g.alpha * __uint_as_float(v[j]), m, n, bias_n, of, ob);
+                    r[j] = (g.residual && m < g.M) ? g.residual[(int64_t)m * g.ldr + n] : 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int m = 32 * c + j;
+                    if (m < g.M) sk_finish(g, g.alpha * __uint_as_float(v[j]), r[j], m, n, bias_n, of, ob);
                 }
             } else {
 #pragma unroll
@@ -444,18 +457,34 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
                 peer[s] = 0;
                 if (s < S) asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer[s]) : "r"(base + 4u * nl), "r"(s));
             }
-#pragma unroll 2
-            for (int m = m_begin; m < m_end; ++m) {
-                float t = 0.f;
+            // batches of SK_RB rows: all distributed-shared-memory loads (and the residuals) of a batch are in flight
+            // together; the sum over the S partials keeps a fixed order
+            constexpr int SK_RB = 4;
+#pragma unroll 1
+            for (int mb = m_begin; mb < m_end; mb += SK_RB) {
+                float x[SK_RB][8], r[SK_RB];
 #pragma unroll
-                for (int s = 0; s < 8; ++s) {
-                    if (s < S) {
-                        float x;
-                        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(x) : "r"(peer[s] + (uint32_t)(m * BM * 4)) : "memory");
-                        t += x;
+                for (int i = 0; i < SK_RB; ++i) {
+                    const int m = mb + i;
+                    const bool ok = m < m_end;
+                    r[i] = (ok && g.residual) ? g.residual[(int64_t)m * g.ldr + n] : 0.f;
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) {
+                        x[i][s] = 0.f;
+                        if (s < S && ok)
+                            asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(x[i][s]) : "r"(peer[s] + (uint32_t)(m * BM * 4)));
                     }
                 }
-                sk_finish(g, t, m, n, bias_n, of, ob);
+#pragma unroll
+                for (int i = 0; i < SK_RB; ++i) {
+                    const int m = mb + i;
+                    if (m < m_end) {
+                        float t = 0.f;
+#pragma unroll
+                        for (int s = 0; s < 8; ++s) t += x[i][s];
+                        sk_finish(g, t, r[i], m, n, bias_n, of, ob);
+                    }
+                }
             }
         }
         __syncwarp();
@@ -551,6 +580,7 @@ static int launch_skinny(const WtsGemm& g, cudaStream_t st, int split_k)
     args.stages = (3 * 65536) / args.stage_bytes;
     if (args.stages > 8) args.stages = 8;
     args.split_k = split_k;
+    { const char* e = getenv("WTS_GEMM_DEBUG"); args.debug = e ? atoi(e) : 0; }
     alignas(64) CUtensorMap tmW, tmX;
     int rc = make_map(&tmW, g.b, g.K, g.N, g.ldb, g.b_plane, 1, 0, 1, 0, BM, "B(weights)");
     if (rc) return rc;
