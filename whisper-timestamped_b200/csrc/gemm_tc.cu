@@ -321,6 +321,40 @@ __device__ __forceinline__ void cluster_sync_all()
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// Cluster reduction of rows [m_begin, m_end) of feature n: batches of RB rows, all RB x S distributed-shared-memory
+// loads (and the residuals) of a batch in flight together; the sum over the S partials keeps a fixed order.
+template <int SMAX, int RB>
+__device__ __forceinline__ void sk_reduce_rows(const WtsGemm& g, const uint32_t (&peer)[8], int S, int m_begin, int m_end, int n,
+                                               float bias_n, float* of, __nv_bfloat16* ob)
+{
+#pragma unroll 1
+    for (int mb = m_begin; mb < m_end; mb += RB) {
+        float x[RB][SMAX], r[RB];
+#pragma unroll
+        for (int i = 0; i < RB; ++i) {
+            const int m = mb + i;
+            const bool ok = m < m_end;
+            r[i] = (ok && g.residual) ? g.residual[(int64_t)m * g.ldr + n] : 0.f;
+#pragma unroll
+            for (int s = 0; s < SMAX; ++s) {
+                x[i][s] = 0.f;
+                if (s < S && ok)
+                    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(x[i][s]) : "r"(peer[s] + (uint32_t)(m * BM * 4)));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < RB; ++i) {
+            const int m = mb + i;
+            if (m < m_end) {
+                float t = 0.f;
+#pragma unroll
+                for (int s = 0; s < SMAX; ++s) t += x[i][s];
+                sk_finish(g, t, r[i], m, n, bias_n, of, ob);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const SkArgs args)
 {
@@ -338,7 +372,8 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     const int nkb = args.debug == 4 ? 0 : kb1 - kb0;
     const int STAGES = args.stages, STAGE_BYTES = args.stage_bytes;
     const int X_TILE = args.bn * BK * 2;
-    if (args.debug == 5) return;
+    pdl_launch();
+    if (args.debug == 5) { pdl_wait(); return; }
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
@@ -359,6 +394,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(bar_base + 136));
+    pdl_wait();                                     // everything above overlapped the previous kernel's tail
 
     const int q = warp & 3;
     const int nl = 32 * q + lane;                  // feature of this epilogue thread inside the tile
@@ -457,35 +493,8 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
                 peer[s] = 0;
                 if (s < S) asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer[s]) : "r"(base + 4u * nl), "r"(s));
             }
-            // batches of SK_RB rows: all distributed-shared-memory loads (and the residuals) of a batch are in flight
-            // together; the sum over the S partials keeps a fixed order
-            constexpr int SK_RB = 4;
-#pragma unroll 1
-            for (int mb = m_begin; mb < m_end; mb += SK_RB) {
-                float x[SK_RB][8], r[SK_RB];
-#pragma unroll
-                for (int i = 0; i < SK_RB; ++i) {
-                    const int m = mb + i;
-                    const bool ok = m < m_end;
-                    r[i] = (ok && g.residual) ? g.residual[(int64_t)m * g.ldr + n] : 0.f;
-#pragma unroll
-                    for (int s = 0; s < 8; ++s) {
-                        x[i][s] = 0.f;
-                        if (s < S && ok)
-                            asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(x[i][s]) : "r"(peer[s] + (uint32_t)(m * BM * 4)));
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < SK_RB; ++i) {
-                    const int m = mb + i;
-                    if (m < m_end) {
-                        float t = 0.f;
-#pragma unroll
-                        for (int s = 0; s < 8; ++s) t += x[i][s];
-                        sk_finish(g, t, r[i], m, n, bias_n, of, ob);
-                    }
-                }
-            }
+            if (S <= 4) sk_reduce_rows<4, 12>(g, peer, S, m_begin, m_end, n, bias_n, of, ob);
+            else        sk_reduce_rows<8, 6>(g, peer, S, m_begin, m_end, n, bias_n, of, ob);
         }
         __syncwarp();
         cluster_sync_all();                          // nobody leaves while a peer may still read its partial tile
@@ -591,13 +600,15 @@ static int launch_skinny(const WtsGemm& g, cudaStream_t st, int split_k)
     cfg.blockDim = dim3(TC_THREADS, 1, 1);
     cfg.dynamicSmemBytes = SK_SMEM;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 1;
     attr[0].val.clusterDim.y = split_k;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     WTS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_skinny_kernel, tmW, tmX, args));
     return 0;
 }

@@ -63,6 +63,8 @@ layernorm_kernel(const float* __restrict__ x, int64_t ldx, const float* __restri
                  const float* __restrict__ beta, int M, int D, __nv_bfloat16* __restrict__ o, int64_t ldo,
                  int64_t o_plane, float* __restrict__ of, int64_t ldf)
 {
+    pdl_launch();
+    pdl_wait();
     __shared__ float red[32];
     const int row = blockIdx.x;
     const float* xr = x + (int64_t)row * ldx;
@@ -222,6 +224,8 @@ __global__ void embed_kernel(const int32_t* __restrict__ tokens, const int32_t* 
                              const float* __restrict__ emb, const float* __restrict__ pos, int rows, int D,
                              float* __restrict__ out)
 {
+    pdl_launch();
+    pdl_wait();
     const int r = blockIdx.x;
     if (r >= rows) return;
     const float* e = emb + (int64_t)tokens[r] * D;
@@ -249,6 +253,8 @@ decoder_attention_kernel(const int kind, const float* __restrict__ q, int64_t ld
                          const int32_t* __restrict__ head_slot, int n_slots, int qk_rows,
                          const int32_t* __restrict__ qk_row, const int32_t* __restrict__ row_active)
 {
+    pdl_launch();
+    pdl_wait();
     extern __shared__ float sm[];
     float* sc = sm;                 // [ctx] scores
     float* qs = sm + ctx;           // [64]
@@ -404,6 +410,8 @@ cross_attention_f16_kernel(const float* __restrict__ q, int64_t ldq, const __hal
                            int64_t o_plane, float* __restrict__ qk_out, int qk_rows, const int32_t* __restrict__ qk_row,
                            const int32_t* __restrict__ row_active)
 {
+    pdl_launch();
+    pdl_wait();
     __shared__ float sm_acc[CA_GROUPS][64];
     __shared__ float sm_m[CA_GROUPS], sm_l[CA_GROUPS], sm_w[CA_GROUPS];
     __shared__ float sm_L;
@@ -460,6 +468,8 @@ __global__ void kv_append_kernel(const float* __restrict__ k, const float* __res
                                  const int32_t* __restrict__ row_seq, const int32_t* __restrict__ row_pos, int H,
                                  int ctx, float* __restrict__ kc, float* __restrict__ vc, int64_t seq_stride)
 {
+    pdl_launch();
+    pdl_wait();
     const int r = blockIdx.x;
     const int seq = row_seq[r], pos = row_pos[r];
     for (int c = threadIdx.x; c < H * 64; c += blockDim.x) {
@@ -479,6 +489,8 @@ decode_select_kernel(float* __restrict__ logits, int64_t ldl, const WtsDecodeCfg
                      const int32_t* __restrict__ n_prompt, int32_t* __restrict__ done,
                      float* __restrict__ logprobs, int lp_ld, float* __restrict__ full)
 {
+    pdl_launch();
+    pdl_wait();
     __shared__ float red[32];
     __shared__ int s_flags[8];
     __shared__ float s_best[DS_THREADS / 32];
@@ -592,6 +604,8 @@ __global__ void step_inputs_kernel(const int32_t* __restrict__ tokens, int ld, c
                                    int32_t* __restrict__ tok, int32_t* __restrict__ pos, int32_t* __restrict__ qk_row,
                                    int32_t* __restrict__ active)
 {
+    pdl_launch();
+    pdl_wait();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const int nt = n_tokens[b];
@@ -639,8 +653,8 @@ extern "C" int wts_layernorm(const float* d_x, int64_t ldx, const float* d_gamma
 {
     if (M <= 0) return 0;
     if (D > LN_THREADS * LN_MAXV) { set_error("wts_layernorm: D=%d > %d", D, LN_THREADS * LN_MAXV); return -2; }
-    layernorm_kernel<<<M, LN_THREADS, 0, (cudaStream_t)stream>>>(d_x, ldx, d_gamma, d_beta, M, D,
-                                                                   (__nv_bfloat16*)d_out_sb16, ldo, o_plane, d_out_f32, ldf);
+    WTS_CUDA_CHECK(launch_pdl(layernorm_kernel, dim3(M), dim3(LN_THREADS), 0, (cudaStream_t)stream, d_x, ldx, d_gamma, d_beta, M, D,
+                                                                   (__nv_bfloat16*)d_out_sb16, ldo, o_plane, d_out_f32, ldf));
     WTS_LAUNCH_CHECK();
     return 0;
 }
@@ -708,7 +722,7 @@ extern "C" int wts_embed(const int32_t* d_tokens, const int32_t* d_positions, co
                          int32_t rows, int32_t D, float* d_out, void* stream)
 {
     if (rows <= 0) return 0;
-    embed_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(d_tokens, d_positions, d_emb, d_pos, rows, D, d_out);
+    WTS_CUDA_CHECK(launch_pdl(embed_kernel, dim3(rows), dim3(256), 0, (cudaStream_t)stream, d_tokens, d_positions, d_emb, d_pos, rows, D, d_out));
     WTS_LAUNCH_CHECK();
     return 0;
 }
@@ -731,9 +745,9 @@ extern "C" int wts_decoder_attention(int32_t kind, const float* d_q, int64_t ldq
     if (rows <= 0) return 0;
     const size_t smem = ((size_t)ctx + 64 + 32 + 128) * sizeof(float);
     dim3 grid(rows, H);
-    decoder_attention_kernel<<<grid, DA_THREADS, smem, (cudaStream_t)stream>>>(
+    WTS_CUDA_CHECK(launch_pdl(decoder_attention_kernel, grid, dim3(DA_THREADS), smem, (cudaStream_t)stream, 
         kind, d_q, ldq, d_k, d_v, seq_stride, ctx, d_row_seq, d_row_pos, H, (__nv_bfloat16*)d_out_sb16, ldo, o_plane,
-        d_qk_out, d_head_slot, n_slots, qk_rows, d_qk_row, d_row_active);
+        d_qk_out, d_head_slot, n_slots, qk_rows, d_qk_row, d_row_active));
     WTS_LAUNCH_CHECK();
     return 0;
 }
@@ -759,9 +773,9 @@ extern "C" int wts_cross_attention_f16(const float* d_q, int64_t ldq, const void
     if (rows <= 0) return 0;
     if ((ldq & 3) || (reinterpret_cast<uintptr_t>(d_q) & 15)) { set_error("wts_cross_attention_f16: q must be 16-byte aligned"); return -2; }
     dim3 grid(rows, H);
-    cross_attention_f16_kernel<<<grid, CA_THREADS, 0, (cudaStream_t)stream>>>(
+    WTS_CUDA_CHECK(launch_pdl(cross_attention_f16_kernel, grid, dim3(CA_THREADS), 0, (cudaStream_t)stream, 
         d_q, ldq, (const __half*)d_k16, (const __half*)d_v16, d_k_align, d_head_slot, n_slots, ctx, d_row_seq, H,
-        (__nv_bfloat16*)d_out_sb16, ldo, o_plane, d_qk_out, qk_rows, d_qk_row, d_row_active);
+        (__nv_bfloat16*)d_out_sb16, ldo, o_plane, d_qk_out, qk_rows, d_qk_row, d_row_active));
     WTS_LAUNCH_CHECK();
     return 0;
 }
@@ -771,7 +785,7 @@ extern "C" int wts_kv_append(const float* d_k, const float* d_v, int64_t ld, con
                              int64_t seq_stride, void* stream)
 {
     if (rows <= 0) return 0;
-    kv_append_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(d_k, d_v, ld, d_row_seq, d_row_pos, H, ctx, d_kc, d_vc, seq_stride);
+    WTS_CUDA_CHECK(launch_pdl(kv_append_kernel, dim3(rows), dim3(256), 0, (cudaStream_t)stream, d_k, d_v, ld, d_row_seq, d_row_pos, H, ctx, d_kc, d_vc, seq_stride));
     WTS_LAUNCH_CHECK();
     return 0;
 }
@@ -782,9 +796,9 @@ extern "C" int wts_decode_select(float* d_logits, int64_t ldl, const WtsDecodeCf
                                  float* d_full_logprobs, int32_t B, void* stream)
 {
     if (B <= 0) return 0;
-    decode_select_kernel<<<B, DS_THREADS, 0, (cudaStream_t)stream>>>(d_logits, ldl, *cfg, d_suppress, d_blank, d_tokens,
+    WTS_CUDA_CHECK(launch_pdl(decode_select_kernel, dim3(B), dim3(DS_THREADS), 0, (cudaStream_t)stream, d_logits, ldl, *cfg, d_suppress, d_blank, d_tokens,
                                                                     d_n_tokens, d_n_prompt, d_done, d_logprobs, lp_ld,
-                                                                    d_full_logprobs);
+                                                                    d_full_logprobs));
     WTS_LAUNCH_CHECK();
     return 0;
 }
@@ -794,8 +808,8 @@ extern "C" int wts_step_inputs(const int32_t* d_tokens, int32_t tokens_ld, const
                                int32_t* d_pos, int32_t* d_qk_row, int32_t* d_active, void* stream)
 {
     if (B <= 0) return 0;
-    step_inputs_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_tokens, tokens_ld, d_n_tokens, d_n_prompt,
-                                                                         d_done, B, d_tok, d_pos, d_qk_row, d_active);
+    WTS_CUDA_CHECK(launch_pdl(step_inputs_kernel, dim3((B + 127) / 128), dim3(128), 0, (cudaStream_t)stream, d_tokens, tokens_ld, d_n_tokens, d_n_prompt,
+                                                                         d_done, B, d_tok, d_pos, d_qk_row, d_active));
     WTS_LAUNCH_CHECK();
     return 0;
 }
