@@ -280,6 +280,150 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+// ---------------------------------------------------------------------------------- persistent big GEMM
+// Same tile math as gemm_tc_kernel, but ONE CTA per SM walks a static list of output tiles (tile = blockIdx.x +
+// i * gridDim.x; N fastest so neighbouring CTAs share the A tile in L2) and the accumulator is double-buffered in
+// TMEM (2 x 128 columns): while the eight epilogue warps drain tile i (bias / GELU / residual / SB16 split / stores),
+// the producer and MMA warps are already streaming tile i+1.  The one-tile-per-CTA kernel spends more time in its
+// prologue + epilogue than in its 20-k-block main loop on the encoder shapes; here that time is hidden.
+//   warp 0      TMA producer (ring position continues across tiles)
+//   warp 1      MMA issuer; waits tmem_empty[buf] before reusing an accumulator, commits tmem_full[buf]
+//   warps 2..9  epilogue: warp w reads TMEM lanes 32*(w%4).. and columns 64*((w-2)/4) .. +63 of the tile
+constexpr int P_THREADS = 320;
+constexpr int P_STAGES = 3;
+constexpr int P_STAGE_BYTES = 4 * TILE_BYTES;
+constexpr int P_SMEM = P_STAGES * P_STAGE_BYTES + 256 + 1024;
+
+__global__ void __launch_bounds__(P_THREADS, 1)
+gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs args)
+{
+    extern __shared__ unsigned char smem_raw[];
+    const WtsGemm& g = args.g;
+    const uint32_t base = (smem_addr(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = base + P_STAGES * P_STAGE_BYTES;
+    // barriers: full[s] +8s, empty[s] +32+8s, tmem_full[b] +64+8b, tmem_empty[b] +80+8b, tmem pointer +96
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_n = (g.N + BM - 1) / BM, tiles_m = (g.M + BM - 1) / BM;
+    const int n_tiles = tiles_n * tiles_m * g.batch_outer * g.batch_inner;
+    const int nkb = (g.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < P_STAGES; ++s) { mbar_init(bar_base + 8 * s, 1); mbar_init(bar_base + 32 + 8 * s, 1); }
+            for (int b = 0; b < 2; ++b) { mbar_init(bar_base + 64 + 8 * b, 1); mbar_init(bar_base + 80 + 8 * b, 256); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bar_base + 96), "r"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(bar_base + 96));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int nt = t % tiles_n, mt = (t / tiles_n) % tiles_m, z = t / (tiles_n * tiles_m);
+                const int zo = z / g.batch_inner, zi = z - zo * g.batch_inner;
+                const int azo = args.a_has_bo ? zo : 0, azi = args.a_has_bi ? zi : 0;
+                const int bzo = args.b_has_bo ? zo : 0, bzi = args.b_has_bi ? zi : 0;
+                const int m0 = mt * BM, n0 = nt * BM;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % P_STAGES, u = it / P_STAGES;
+                    mbar_wait(bar_base + 32 + 8 * s, (u & 1) ^ 1);
+                    const uint32_t full = bar_base + 8 * s;
+                    mbar_expect_tx(full, P_STAGE_BYTES);
+                    const uint32_t st = base + s * P_STAGE_BYTES;
+                    const int kc = kb * BK;
+                    tma_load_5d(st, &tmA, full, kc, m0, azi, azo, 0);
+                    tma_load_5d(st + TILE_BYTES, &tmA, full, kc, m0, azi, azo, 1);
+                    tma_load_5d(st + 2 * TILE_BYTES, &tmB, full, kc, n0, bzi, bzo, 0);
+                    tma_load_5d(st + 3 * TILE_BYTES, &tmB, full, kc, n0, bzi, bzo, 1);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BM >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            int it = 0, lt = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++lt) {
+                const int buf = lt & 1, ut = lt >> 1;
+                mbar_wait(bar_base + 80 + 8 * buf, (ut & 1) ^ 1);       // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t acc = tmem_base + (uint32_t)(buf * BM);
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % P_STAGES, u = it / P_STAGES;
+                    mbar_wait(bar_base + 8 * s, u & 1);
+                    tc_fence_after();
+                    const uint32_t st = base + s * P_STAGE_BYTES;
+                    const uint64_t a_hi = umma_desc(st), a_lo = umma_desc(st + TILE_BYTES);
+                    const uint64_t b_hi = umma_desc(st + 2 * TILE_BYTES), b_lo = umma_desc(st + 3 * TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t adv = (uint64_t)(k * 2);
+                        umma_bf16(acc, a_hi + adv, b_hi + adv, idesc, (kb | k) ? 1u : 0u);
+                        umma_bf16(acc, a_lo + adv, b_hi + adv, idesc, 1u);
+                        umma_bf16(acc, a_hi + adv, b_lo + adv, idesc, 1u);
+                    }
+                    umma_commit(bar_base + 32 + 8 * s);
+                }
+                umma_commit(bar_base + 64 + 8 * buf);
+            }
+        }
+    } else {
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        int lt = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++lt) {
+            const int nt = t % tiles_n, mt = (t / tiles_n) % tiles_m, z = t / (tiles_n * tiles_m);
+            const int zo = z / g.batch_inner, zi = z - zo * g.batch_inner;
+            const int m0 = mt * BM, n0 = nt * BM;
+            const int buf = lt & 1, ut = lt >> 1;
+            const int m = m0 + 32 * q + lane;
+            const bool row_ok = m < g.M;
+            const float* res = g.residual ? g.residual + (int64_t)zo * g.r_bo + (int64_t)zi * g.r_bi + (int64_t)m * g.ldr : nullptr;
+            float* of = g.out_f32 ? g.out_f32 + (int64_t)zo * g.c_bo + (int64_t)zi * g.c_bi : nullptr;
+            __nv_bfloat16* ob = g.out_sb16 ? reinterpret_cast<__nv_bfloat16*>(g.out_sb16) + (int64_t)zo * g.o_bo + (int64_t)zi * g.o_bi : nullptr;
+            const float bias_m = (g.bias && g.bias_on_m && row_ok) ? g.bias[m] : 0.f;
+            mbar_wait(bar_base + 64 + 8 * buf, ut & 1);
+            tc_fence_after();
+            uint32_t v0[32], v1[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * BM + 64 * half);
+            tmem_ld32(taddr, v0);
+            tmem_ld32(taddr + 32, v1);
+            tc_fence_before();
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_base + 80 + 8 * buf) : "memory");   // accumulator free
+            if (!row_ok) continue;
+            float y[32];
+            int nb = n0 + 64 * half;
+            if (nb < g.N) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) y[j] = g.alpha * __uint_as_float(v0[j]);
+                epilogue_chunk(g, y, m, nb, bias_m, res, of, ob);
+            }
+            nb += 32;
+            if (nb < g.N) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) y[j] = g.alpha * __uint_as_float(v1[j]);
+                epilogue_chunk(g, y, m, nb, bias_m, res, of, ob);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------ skinny (decode) GEMM
 // M <= 128 rows (one row per decoded window): weight-bandwidth / latency bound, never tensor bound.
 //  * The operands trade places: the 128 x 64 WEIGHT box is the UMMA "A" operand (M = 128 output features), the
@@ -569,6 +713,25 @@ static int launch_big(const WtsGemm& g, cudaStream_t st)
     args.a_has_bo = g.a_bo != 0; args.a_has_bi = g.a_bi != 0;
     args.b_has_bo = g.b_bo != 0; args.b_has_bi = g.b_bi != 0;
     { const char* e = getenv("WTS_GEMM_DEBUG"); args.debug = e ? atoi(e) : 0; }
+    static const int persist = []{ const char* e = getenv("WTS_GEMM_PERSIST"); return e ? atoi(e) : 1; }();
+    const int64_t n_tiles = (int64_t)((g.N + BN - 1) / BN) * ((g.M + BM - 1) / BM) * g.batch_outer * g.batch_inner;
+    if (persist && args.debug == 0 && n_tiles > 1) {
+        static bool pattr = false;
+        static int n_sm = 148;
+        if (!pattr) {
+            WTS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
+            int dev = 0;
+            WTS_CUDA_CHECK(cudaGetDevice(&dev));
+            WTS_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+            pattr = true;
+        }
+        // equal-length tile lists: the smallest CTA count that still needs the same number of rounds
+        const int64_t rounds = (n_tiles + n_sm - 1) / n_sm;
+        const int ctas = (int)((n_tiles + rounds - 1) / rounds);
+        gemm_tc_persist_kernel<<<ctas, P_THREADS, P_SMEM, st>>>(tmA, tmB, args);
+        WTS_LAUNCH_CHECK();
+        return 0;
+    }
     dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.batch_outer * g.batch_inner);
     gemm_tc_kernel<BN><<<grid, TC_THREADS, TcCfg<BN>::SMEM, st>>>(tmA, tmB, args);
     WTS_LAUNCH_CHECK();
