@@ -2,13 +2,16 @@
 // without ever writing the score matrix to HBM.  Replaces the upstream MultiHeadAttention.qkv_attention of the
 // AudioEncoder blocks (reached by the reference through model.transcribe, T.py:904).
 //
-// One CTA per (128-query tile, head, window); 192 threads, warp-specialised:
+// One CTA per (128-query tile, head, window); 576 threads, warp-specialised:
 //   warp 0     TMA producer (Q tile once; K tiles double-buffered; V^T tile per key tile in pass 2)
 //   warp 1     MMA issuer   S = Q K^T (bf16x3, M128 N128 K64) into a double-buffered TMEM score tile,
 //                           O += P V (bf16x3, M128 N64 K128) into a TMEM accumulator
-//   warps 2-5  softmax      one thread per query row: tcgen05.ld the scores, exp, row sums, and the
-//                           probabilities written back to shared memory (hi/lo bf16, SWIZZLE_128B K-major) as
-//                           the A operand of the second MMA
+//   warps 2-17 softmax      FOUR threads per query row (warp w: TMEM lanes 32*(w%4).., the 32-key column part
+//                           (w-2)/4 of every 128-key tile): tcgen05.ld the scores, exp, partial row max / sums
+//                           (merged through shared memory), and the probabilities written back to shared memory
+//                           (hi/lo bf16, SWIZZLE_128B K-major) as the A operand of the second MMA.  The softmax
+//                           side, not the tensor pipe, bounds this kernel: with one warp per scheduler it ran
+//                           latency-bound, four warps per scheduler hide the ALU/MUFU/convert latencies
 // Two passes over the keys instead of an online-softmax rescale: pass 1 finds the exact row maxima (S only),
 // pass 2 recomputes S, accumulates exp(s - max) and P V, and the epilogue divides by the row sum.  The extra
 // Q K^T costs 1/3 more tensor work but no TMEM read-modify-write of O, and the score tile never leaves the SM.
@@ -23,9 +26,11 @@
 
 namespace wts {
 
-constexpr int AT_THREADS = 192;
+constexpr int AT_PARTS = 4;                         // column parts (softmax threads per query row)
+constexpr int AT_THREADS = 64 + 128 * AT_PARTS;
 constexpr int AT_Q = 0, AT_K = 32768, AT_V = 98304, AT_P = 131072, AT_BAR = 196608;
-constexpr int AT_SMEM = AT_BAR + 256 + 1024;
+constexpr int AT_XCH = AT_BAR + 256;                // float [AT_PARTS][128] row max / row sum exchange
+constexpr int AT_SMEM = AT_XCH + AT_PARTS * 512 + 1024;
 // barrier slots (8 bytes each) relative to AT_BAR
 enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 3, B_VFULL = 5, B_VEMPTY = 6, B_SFULL = 7, B_SEMPTY = 9, B_PFULL = 11,
        B_PEMPTY = 12, B_OFULL = 13, B_TMEM = 14 };
@@ -134,11 +139,11 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
                 at_mbar_init(bar + 8 * (B_KFULL + s), 1);
                 at_mbar_init(bar + 8 * (B_KEMPTY + s), 1);
                 at_mbar_init(bar + 8 * (B_SFULL + s), 1);
-                at_mbar_init(bar + 8 * (B_SEMPTY + s), 128);
+                at_mbar_init(bar + 8 * (B_SEMPTY + s), 128 * AT_PARTS);
             }
             at_mbar_init(bar + 8 * B_VFULL, 1);
             at_mbar_init(bar + 8 * B_VEMPTY, 1);
-            at_mbar_init(bar + 8 * B_PFULL, 128);
+            at_mbar_init(bar + 8 * B_PFULL, 128 * AT_PARTS);
             at_mbar_init(bar + 8 * B_PEMPTY, 1);
             at_mbar_init(bar + 8 * B_OFULL, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -228,89 +233,99 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
             at_commit(bar + 8 * B_OFULL);
         }
     } else {
-        const int q = warp & 3;
+        const int q = warp & 3, part = (warp - 2) >> 2;
         const int r = 32 * q + lane;                    // query row inside the tile == TMEM lane
         const uint32_t lane_off = (uint32_t)(32 * q) << 16;
+        float* xch = reinterpret_cast<float*>(smem_raw + (base - at_smem(smem_raw)) + AT_XCH);
         float m = -INFINITY;
-        for (int i = 0; i < NT; ++i) {                  // pass 1: exact row maxima
+        for (int i = 0; i < NT; ++i) {                  // pass 1: exact row maxima (this thread: 32 of the 128 keys)
             const int st = i & 1, u = i >> 1;
             at_wait(bar + 8 * (B_SFULL + st), u & 1);
             at_fence_after();
-            const bool tail = (i + 1) * 128 > a.n_ctx;  // only the last key tile has out-of-range keys
-#pragma unroll 1
-            for (int c = 0; c < 4; c += 2) {
-                uint32_t v0[32], v1[32];
-                at_ld32(tm_S0 + st * 128 + lane_off + 32 * c, v0);
-                at_ld32(tm_S0 + st * 128 + lane_off + 32 * c + 32, v1);
-                at_ld_wait();
-                if (!tail) {
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) m = fmaxf(m, fmaxf(__uint_as_float(v0[e]), __uint_as_float(v1[e])));
-                } else {
-                    const int key0 = i * 128 + 32 * c;
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        if (key0 + e < a.n_ctx) m = fmaxf(m, __uint_as_float(v0[e]));
-                        if (key0 + 32 + e < a.n_ctx) m = fmaxf(m, __uint_as_float(v1[e]));
-                    }
-                }
-            }
+            uint32_t v[32];
+            at_ld32(tm_S0 + st * 128 + lane_off + 32 * part, v);
+            at_ld_wait();
             at_fence_before();
             at_arrive(bar + 8 * (B_SEMPTY + st));
+            const int key0 = i * 128 + 32 * part;
+            if (key0 + 32 <= a.n_ctx) {
+                float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]), m3 = __uint_as_float(v[3]);
+#pragma unroll
+                for (int e = 4; e < 32; e += 4) {
+                    m0 = fmaxf(m0, __uint_as_float(v[e]));
+                    m1 = fmaxf(m1, __uint_as_float(v[e + 1]));
+                    m2 = fmaxf(m2, __uint_as_float(v[e + 2]));
+                    m3 = fmaxf(m3, __uint_as_float(v[e + 3]));
+                }
+                m = fmaxf(m, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+            } else {
+#pragma unroll
+                for (int e = 0; e < 32; ++e)
+                    if (key0 + e < a.n_ctx) m = fmaxf(m, __uint_as_float(v[e]));
+            }
         }
+        xch[part * 128 + r] = m;
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * AT_PARTS) : "memory");
+#pragma unroll
+        for (int pp = 0; pp < AT_PARTS; ++pp) m = fmaxf(m, xch[pp * 128 + r]);
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * AT_PARTS) : "memory");       // everyone has read before the sums reuse xch
         float sum = 0.f;
         const float ml2 = m * 1.4426950408889634f;
-        for (int j = 0; j < NT; ++j) {                  // pass 2: probabilities -> shared memory, row sums
+        for (int j = 0; j < NT; ++j) {                  // pass 2: probabilities -> shared memory, partial row sums
             const int i = NT + j, st = i & 1, u = i >> 1;
             at_wait(bar + 8 * (B_SFULL + st), u & 1);
             at_fence_after();
-            const bool tail = (j + 1) * 128 > a.n_ctx;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                at_ld32(tm_S0 + st * 128 + lane_off + 32 * c, v);
-                at_ld_wait();
-                const int key0 = j * 128 + 32 * c;
-                uint32_t hw[16], lw[16];
+            uint32_t v[32];
+            at_ld32(tm_S0 + st * 128 + lane_off + 32 * part, v);
+            at_ld_wait();
+            at_fence_before();
+            at_arrive(bar + 8 * (B_SEMPTY + st));       // scores are in registers: the tile can be overwritten
+            const int key0 = j * 128 + 32 * part;
+            const bool tail = key0 + 32 > a.n_ctx;
+            uint32_t hw[16], lw[16];
+            float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    float p0 = at_ex2(fmaf(__uint_as_float(v[2 * e]), 1.4426950408889634f, -ml2));
-                    float p1 = at_ex2(fmaf(__uint_as_float(v[2 * e + 1]), 1.4426950408889634f, -ml2));
-                    if (tail) {
-                        if (key0 + 2 * e >= a.n_ctx) p0 = 0.f;
-                        if (key0 + 2 * e + 1 >= a.n_ctx) p1 = 0.f;
-                    }
-                    sum += p0 + p1;
-                    const __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
-                    const uint32_t hbits = *reinterpret_cast<const uint32_t*>(&hb);
-                    const float h0 = __uint_as_float(hbits << 16), h1 = __uint_as_float(hbits & 0xffff0000u);
-                    const __nv_bfloat162 lb = __floats2bfloat162_rn(p0 - h0, p1 - h1);
-                    hw[e] = hbits;
-                    lw[e] = *reinterpret_cast<const uint32_t*>(&lb);
+            for (int e = 0; e < 16; ++e) {
+                float p0 = at_ex2(fmaf(__uint_as_float(v[2 * e]), 1.4426950408889634f, -ml2));
+                float p1 = at_ex2(fmaf(__uint_as_float(v[2 * e + 1]), 1.4426950408889634f, -ml2));
+                if (tail) {
+                    if (key0 + 2 * e >= a.n_ctx) p0 = 0.f;
+                    if (key0 + 2 * e + 1 >= a.n_ctx) p1 = 0.f;
                 }
-                if (c == 0) at_wait(bar + 8 * B_PEMPTY, (j & 1) ^ 1);   // previous P V has finished reading the P buffer
-                // A operand of P V: [128 rows x 128 keys] as two 64-key atoms, row pitch 128 B, 16-byte chunks
-                // XOR-swizzled with (row & 7)
-                const int at = c >> 1;
-                const uint32_t rowb = base + AT_P + at * 16384 + r * 128;
+                s0 += p0;
+                s1 += p1;
+                const __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
+                const uint32_t hbits = *reinterpret_cast<const uint32_t*>(&hb);
+                const float h0 = __uint_as_float(hbits << 16), h1 = __uint_as_float(hbits & 0xffff0000u);
+                const __nv_bfloat162 lb = __floats2bfloat162_rn(p0 - h0, p1 - h1);
+                hw[e] = hbits;
+                lw[e] = *reinterpret_cast<const uint32_t*>(&lb);
+            }
+            sum += s0 + s1;
+            at_wait(bar + 8 * B_PEMPTY, (j & 1) ^ 1);   // previous P V has finished reading the P buffer
+            // A operand of P V: [128 rows x 128 keys] as two 64-key atoms, row pitch 128 B, 16-byte chunks
+            // XOR-swizzled with (row & 7)
+            const uint32_t rowb = base + AT_P + (part >> 1) * 16384 + r * 128;
 #pragma unroll
-                for (int ch = 0; ch < 4; ++ch) {
-                    const uint32_t chunk = (uint32_t)((c & 1) * 4 + ch) ^ (uint32_t)(r & 7);
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + chunk * 16), "r"(hw[4 * ch]), "r"(hw[4 * ch + 1]), "r"(hw[4 * ch + 2]), "r"(hw[4 * ch + 3]) : "memory");
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + 32768 + chunk * 16), "r"(lw[4 * ch]), "r"(lw[4 * ch + 1]), "r"(lw[4 * ch + 2]), "r"(lw[4 * ch + 3]) : "memory");
-                }
+            for (int ch = 0; ch < 4; ++ch) {
+                const uint32_t chunk = (uint32_t)((part & 1) * 4 + ch) ^ (uint32_t)(r & 7);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + chunk * 16), "r"(hw[4 * ch]), "r"(hw[4 * ch + 1]), "r"(hw[4 * ch + 2]), "r"(hw[4 * ch + 3]) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + 32768 + chunk * 16), "r"(lw[4 * ch]), "r"(lw[4 * ch + 1]), "r"(lw[4 * ch + 2]), "r"(lw[4 * ch + 3]) : "memory");
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
-            at_fence_before();
             at_arrive(bar + 8 * B_PFULL);
-            at_arrive(bar + 8 * (B_SEMPTY + st));
         }
+        xch[part * 128 + r] = sum;
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * AT_PARTS) : "memory");
+        sum = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < AT_PARTS; ++pp) sum += xch[pp * 128 + r];
         at_wait(bar + 8 * B_OFULL, 0);
         at_fence_after();
         const float inv = 1.0f / sum;
         const int row = q0 + r;
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
+        if (part < 2) {                                 // the 64 output channels are two 32-column chunks
+            const int c = part;
             uint32_t v[32];
             at_ld32(tm_O + lane_off + 32 * c, v);
             at_ld_wait();
