@@ -271,7 +271,7 @@ def gemm_roofline(engine, peaks, reps=20):
     tf = 2.0 * M * N * K / (ms * 1e-3) / 1e12
     return {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
             "frac": tf / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
-            "kernel": "gemm_tc_kernel (bf16x3: 3 UMMAs per float32-accurate product; tensor-pipe work = 3x achieved)",
+            "kernel": "gemm_tc_persist_kernel (bf16x3: 3 UMMAs per float32-accurate product; tensor-pipe work = 3x achieved)",
             "shape": [M, N, K], "ms": ms}
 
 
@@ -404,6 +404,10 @@ def cpu_baseline_e2e(args, seconds=None):
     seconds = seconds or args.cpu_seconds
     cores = usable_cores()
     torch.set_num_threads(cores)
+    try:
+        torch.set_num_interop_threads(1)
+    except RuntimeError:
+        pass
     dims = zoo.DIMS[args.model]
     sd = zoo.synthetic_state_dict(dims, seed=1234, **SYNTH_KW)
     heads = zoo.ALIGNMENT_HEADS[args.model]
@@ -429,7 +433,7 @@ def cpu_baseline_e2e(args, seconds=None):
     dt = time.perf_counter() - t0
     how = ("unmodified reference (baseline/_ref) over the oracle stand-ins for openai-whisper/dtw-python" if kind == "reference"
            else "oracle engine (stand-in for openai-whisper + scipy/torch/oracle-DTW alignment)")
-    return {"value": seconds / dt, "unit": "audio-sec/s", "cores": cores, "kind": kind,
+    return {"value": seconds / dt, "unit": "audio-sec/s", "cores": cores, "kind": kind, "wall_s": dt,
             "sample": f"first {seconds:.0f} s of the same synthetic audio in {args.chunk_seconds:.0f}-s chunks, {args.model} "
                       f"float32 on CPU, {how}; {dt:.1f} s wall, {ntok} tokens"}
 
@@ -468,6 +472,7 @@ def main():
             metric, cfg = "audio-sec/s (RTF) large-v3 1h synthetic @1/2/4/8 B200; DTW GB/s vs HBM peak", {"workload": workload_name}
         print(json.dumps({"impl": "reference", "metric": metric, "value": cb["value"], "unit": cb["unit"],
                           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+                          "ms_per_step": cb.get("wall_s", 0.0) * 1e3, "scaling": "strong", "vs_baseline": None,
                           "cpu_baseline": cb, "config": cfg, "data": "synthetic", "dtype": "f32",
                           "e2e": {"value": cb["value"], "unit": cb["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return

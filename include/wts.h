@@ -115,6 +115,8 @@ typedef struct WtsGemm {
                                                 (n / head_dim) * head_stride + m * ld + (n % head_dim) */
     int32_t backend;          /* 0 = tcgen05 tensor cores, 1 = SIMT float32 validator */
     int32_t a_is_f32, b_is_f32;   /* SIMT backend only: operand is plain float32 (log-mel DFT / filterbank GEMMs) */
+    const int32_t* row_mask;  /* optional [M] (M <= 128, unbatched): rows with mask 0 are skipped, their outputs stay
+                                 untouched (finished windows of a decode batch); NULL = every row */
 } WtsGemm;
 
 /* Error-compensated GEMM.  Replaces every torch Linear / Conv1d / matmul of the encoder and decoder. */

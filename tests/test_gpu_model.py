@@ -122,6 +122,40 @@ def test_gemm_skinny_split_general_epilogue(backend):
             assert (out2.double() - (lin + res.double())).abs().max().item() <= 2e-4 * scale, (M, N, K, rep)
 
 
+def test_gemm_skinny_row_mask():
+    """row_mask: rows of finished windows are skipped (outputs untouched), the others are exact; the active rows are
+    spread over the cluster CTAs, so odd counts and all-inactive batches are covered."""
+    from whisper_timestamped.model import SB16
+    from whisper_timestamped.engine import CudaEngine
+    dev = torch.device("cuda:0")
+    eng = CudaEngine.__new__(CudaEngine)
+    eng.dev, eng.backend, eng.launches = dev, 0, 0
+    g = torch.Generator(device="cpu").manual_seed(13)
+    for (M, N, K, n_act) in [(128, 1280, 1280, 5), (128, 5120, 1280, 37), (64, 1000, 1288, 0), (128, 51866, 384, 3), (20, 1280, 5120, 20)]:
+        a = torch.randn(M, K, generator=g).to(dev)
+        b = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev)
+        bias = torch.randn(N, generator=g).to(dev)
+        x0 = torch.randn(M, N, generator=g).to(dev)
+        mask = torch.zeros(M, dtype=torch.int32)
+        mask[torch.randperm(M, generator=g)[:n_act]] = 1
+        mask = mask.to(dev)
+        A, Bm = SB16.from_f32(a), SB16.from_f32(b)
+        lin = A.to_f32().double() @ Bm.to_f32().double().T + bias.double()
+        x = x0.clone()
+        eng.gemm(A, Bm, M, N, K, bias=bias, residual=x, ldr=N, out_f32=x, ldc=N, row_mask=mask)
+        osb = SB16(M, N, dev)
+        osb.t.fill_(2.0)
+        eng.gemm(A, Bm, M, N, K, bias=bias, act=1, out_sb=osb, row_mask=mask)
+        torch.cuda.synchronize()
+        on = mask.bool()
+        scale = max(1.0, lin.abs().max().item())
+        assert torch.equal(x[~on], x0[~on]), (M, N, K)
+        assert torch.all(osb.to_f32()[~on] == 4.0)
+        if n_act:
+            assert (x[on].double() - (x0[on].double() + lin[on])).abs().max().item() <= 2e-4 * scale
+            assert (osb.to_f32()[on].double() - torch.nn.functional.gelu(lin[on])).abs().max().item() <= 3e-4 * scale
+
+
 def test_cross_attention_f16_vs_torch():
     """wts_cross_attention_f16 (one pass, online softmax over fp16 K/V; float32 K for the alignment heads) against
     float64 torch on the same cache contents; inactive rows must be left untouched."""

@@ -443,7 +443,7 @@ struct SkArgs {
     int debug;              // probes (WTS_GEMM_DEBUG): 1 = TMA only, 2 = MMA only, 4 = no main loop, 5 = launch + exit
 };
 
-constexpr int SK_SMEM = 3 * 65536 + 256 + 1024;
+constexpr int SK_SMEM = 3 * 65536 + 256 + 1024 + 1024;     // ring | barriers | active-row list | alignment slack
 
 __device__ __forceinline__ void sk_finish(const WtsGemm& g, float t, float resid, int m, int n, float bias_n, float* of,
                                           __nv_bfloat16* ob)
@@ -465,19 +465,23 @@ __device__ __forceinline__ void cluster_sync_all()
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-// Cluster reduction of rows [m_begin, m_end) of feature n: batches of RB rows, all RB x S distributed-shared-memory
-// loads (and the residuals) of a batch in flight together; the sum over the S partials keeps a fixed order.
+// Cluster reduction of feature n over the active rows list[rank], list[rank + S], ...: batches of RB rows, all
+// RB x S distributed-shared-memory loads (and the residuals) of a batch in flight together; the sum over the S
+// partials keeps a fixed order.
 template <int SMAX, int RB>
-__device__ __forceinline__ void sk_reduce_rows(const WtsGemm& g, const uint32_t (&peer)[8], int S, int m_begin, int m_end, int n,
-                                               float bias_n, float* of, __nv_bfloat16* ob)
+__device__ __forceinline__ void sk_reduce_rows(const WtsGemm& g, const uint32_t (&peer)[8], int S, const int* list, int rank,
+                                               int n_rows, int n, float bias_n, float* of, __nv_bfloat16* ob)
 {
 #pragma unroll 1
-    for (int mb = m_begin; mb < m_end; mb += RB) {
+    for (int kb = rank; kb < n_rows; kb += RB * S) {
         float x[RB][SMAX], r[RB];
+        int mm[RB];
 #pragma unroll
         for (int i = 0; i < RB; ++i) {
-            const int m = mb + i;
-            const bool ok = m < m_end;
+            const int k = kb + i * S;
+            const bool ok = k < n_rows;
+            const int m = ok ? list[k] : 0;
+            mm[i] = ok ? m : -1;
             r[i] = (ok && g.residual) ? g.residual[(int64_t)m * g.ldr + n] : 0.f;
 #pragma unroll
             for (int s = 0; s < SMAX; ++s) {
@@ -488,12 +492,11 @@ __device__ __forceinline__ void sk_reduce_rows(const WtsGemm& g, const uint32_t 
         }
 #pragma unroll
         for (int i = 0; i < RB; ++i) {
-            const int m = mb + i;
-            if (m < m_end) {
+            if (mm[i] >= 0) {
                 float t = 0.f;
 #pragma unroll
                 for (int s = 0; s < SMAX; ++s) t += x[i][s];
-                sk_finish(g, t, r[i], m, n, bias_n, of, ob);
+                sk_finish(g, t, r[i], mm[i], n, bias_n, of, ob);
             }
         }
     }
@@ -539,6 +542,22 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(bar_base + 136));
     pdl_wait();                                     // everything above overlapped the previous kernel's tail
+
+    // active rows (row_mask): compact list in shared memory; row k of the list is reduced by cluster CTA k % S
+    int* rows_list = reinterpret_cast<int*>(smem_raw + (bar_base - smem_addr(smem_raw)) + 256);   // [128] + count at [128]
+    if (warp >= 2) {
+        const int t = threadIdx.x - 64;
+        const bool act = t < g.M && (g.row_mask == nullptr || g.row_mask[t] != 0);
+        const unsigned bal = __ballot_sync(0xffffffffu, act);
+        int* wcount = rows_list + 132;              // per-warp counts [4]
+        if (lane == 0) wcount[warp - 2] = __popc(bal);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        int off = 0;
+        for (int w2 = 0; w2 < warp - 2; ++w2) off += wcount[w2];
+        if (act) rows_list[off + __popc(bal & ((1u << lane) - 1u))] = t;
+        if (t == 0) rows_list[128] = wcount[0] + wcount[1] + wcount[2] + wcount[3];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
 
     const int q = warp & 3;
     const int nl = 32 * q + lane;                  // feature of this epilogue thread inside the tile
@@ -609,7 +628,8 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int m = 32 * c + j;
-                    if (m < g.M) sk_finish(g, g.alpha * __uint_as_float(v[j]), r[j], m, n, bias_n, of, ob);
+                    if (m < g.M && (g.row_mask == nullptr || g.row_mask[m] != 0))
+                        sk_finish(g, g.alpha * __uint_as_float(v[j]), r[j], m, n, bias_n, of, ob);
                 }
             } else {
 #pragma unroll
@@ -627,9 +647,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         if (warp >= 2 && n_ok) {
             uint32_t rank;
             asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-            const int rows_per = (g.M + S - 1) / S;
-            const int m_begin = (int)rank * rows_per;
-            const int m_end = min(g.M, m_begin + rows_per);
+            const int n_rows = rows_list[128];
             const float bias_n = (g.bias && !g.bias_on_m) ? g.bias[n] : 0.f;
             uint32_t peer[8];
 #pragma unroll
@@ -637,8 +655,8 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
                 peer[s] = 0;
                 if (s < S) asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer[s]) : "r"(base + 4u * nl), "r"(s));
             }
-            if (S <= 4) sk_reduce_rows<4, 12>(g, peer, S, m_begin, m_end, n, bias_n, of, ob);
-            else        sk_reduce_rows<8, 6>(g, peer, S, m_begin, m_end, n, bias_n, of, ob);
+            if (S <= 4) sk_reduce_rows<4, 12>(g, peer, S, rows_list, (int)rank, n_rows, n, bias_n, of, ob);
+            else        sk_reduce_rows<8, 6>(g, peer, S, rows_list, (int)rank, n_rows, n, bias_n, of, ob);
         }
         __syncwarp();
         cluster_sync_all();                          // nobody leaves while a peer may still read its partial tile

@@ -92,7 +92,7 @@ class CudaEngine:
              batch=(1, 1), a_b=(0, 0), b_b=(0, 0), alpha=1.0, bias=None, bias_on_m=False, act=0,
              residual=None, ldr=0, r_b=(0, 0), out_f32=None, ldc=0, c_b=(0, 0), c_off=0,
              out_sb=None, ldo=0, o_plane=0, o_b=(0, 0), o_off=0, head_dim=0, head_stride=0,
-             a_f32=False, b_f32=False, backend=None):
+             a_f32=False, b_f32=False, backend=None, row_mask=None):
         """a/b: SB16 objects (or float32 tensors with a_f32/b_f32).  Offsets/strides in elements."""
         g = nat.Gemm()
         if a_f32:
@@ -123,6 +123,7 @@ class CudaEngine:
         g.head_dim, g.head_stride = head_dim, head_stride
         g.backend = self.backend if backend is None else backend
         g.a_is_f32, g.b_is_f32 = int(a_f32), int(b_f32)
+        g.row_mask = row_mask.data_ptr() if row_mask is not None else None
         if a_f32 or b_f32:
             g.backend = 1
         nat.check(nat.lib.wts_gemm(ctypes.byref(g), self._st()), "wts_gemm")
@@ -255,7 +256,7 @@ class CudaEngine:
         for li, blk in enumerate(w.dec):
             a, c = blk.attn, blk.cross
             self.layernorm(x, a.ln_g, a.ln_b, R, D, out_sb=hs)
-            self.gemm(hs, a.qkv, R, 3 * D, D, bias=a.qkv_b, out_f32=qkv, ldc=3 * D)
+            self.gemm(hs, a.qkv, R, 3 * D, D, bias=a.qkv_b, out_f32=qkv, ldc=3 * D, row_mask=active)
             nat.check(nat.lib.wts_kv_append(qkv.data_ptr() + 4 * D, qkv.data_ptr() + 8 * D, 3 * D, row_seq.data_ptr(),
                                             row_pos.data_ptr(), R, H, d.n_text_ctx, st8["sk"][li].data_ptr(),
                                             st8["sv"][li].data_ptr(), H * d.n_text_ctx * 64, st), "wts_kv_append")
@@ -265,19 +266,19 @@ class CudaEngine:
                                                     att.plane, None, None, 0, 0, None,
                                                     active.data_ptr() if active is not None else None, st),
                       "wts_decoder_attention")
-            self.gemm(att, a.out, R, D, D, bias=a.out_b, residual=x, ldr=D, out_f32=x, ldc=D)
+            self.gemm(att, a.out, R, D, D, bias=a.out_b, residual=x, ldr=D, out_f32=x, ldc=D, row_mask=active)
             self.layernorm(x, c.ln_g, c.ln_b, R, D, out_sb=hs)
-            self.gemm(hs, c.q, R, D, D, bias=c.q_b, out_f32=q, ldc=D)
+            self.gemm(hs, c.q, R, D, D, bias=c.q_b, out_f32=q, ldc=D, row_mask=active)
             nat.check(nat.lib.wts_cross_attention_f16(q.data_ptr(), D, st8["ck"][li].data_ptr(), st8["cv"][li].data_ptr(),
                                                       st8["ckal"][li].data_ptr(), w.head_slot[li].data_ptr(), n_slots,
                                                       N_CTX_AUDIO, row_seq.data_ptr(), R, H, att.ptr, att.ld, att.plane,
                                                       qk_buf.data_ptr(), qk_buf.shape[2], qk_row.data_ptr(),
                                                       active.data_ptr() if active is not None else None, st),
                       "wts_cross_attention_f16")
-            self.gemm(att, c.out, R, D, D, bias=c.out_b, residual=x, ldr=D, out_f32=x, ldc=D)
+            self.gemm(att, c.out, R, D, D, bias=c.out_b, residual=x, ldr=D, out_f32=x, ldc=D, row_mask=active)
             self.layernorm(x, blk.mlp_ln_g, blk.mlp_ln_b, R, D, out_sb=hs)
-            self.gemm(hs, blk.fc1, R, 4 * D, D, bias=blk.fc1_b, act=1, out_sb=mid)
-            self.gemm(mid, blk.fc2, R, D, 4 * D, bias=blk.fc2_b, residual=x, ldr=D, out_f32=x, ldc=D)
+            self.gemm(hs, blk.fc1, R, 4 * D, D, bias=blk.fc1_b, act=1, out_sb=mid, row_mask=active)
+            self.gemm(mid, blk.fc2, R, D, 4 * D, bias=blk.fc2_b, residual=x, ldr=D, out_f32=x, ldc=D, row_mask=active)
             self.launches += 3
 
     def _alloc_decoder_state(self, B, R):
@@ -392,7 +393,7 @@ class CudaEngine:
                                     cap, D, ses["xs"].data_ptr(), st), "wts_embed")
         self._decoder_rows(ses["st8"], ses["xs"], cap, ses["seq_ids"], ses["s_pos"], ses["s_qkr"], ses["qk_buf"],
                            active=ses["s_act"])
-        self._final_logits_static(ses["xs"], cap, ses["logits"], ses["st8"])
+        self._final_logits_static(ses["xs"], cap, ses["logits"], ses["st8"], active=ses["s_act"])
         self._select(ses, ses["logits"], cap)
         self.launches += 2
 
@@ -536,11 +537,11 @@ class CudaEngine:
                                         language=tok.language, last_row_logprobs=last_lp))
         return records
 
-    def _final_logits_static(self, x_rows, n_rows, logits, st8):
+    def _final_logits_static(self, x_rows, n_rows, logits, st8, active=None):
         d, w = self.dims, self.w
         hs = st8["hs_fin"]
         self.layernorm(x_rows, w.ln_g, w.ln_b, n_rows, d.n_text_state, out_sb=hs)
-        self.gemm(hs, w.emb_sb, n_rows, d.n_vocab, d.n_text_state, out_f32=logits, ldc=d.n_vocab)
+        self.gemm(hs, w.emb_sb, n_rows, d.n_vocab, d.n_text_state, out_f32=logits, ldc=d.n_vocab, row_mask=active)
 
     # ------------------------------------------------------------------ language detection
     @torch.no_grad()
