@@ -269,8 +269,16 @@ def gemm_roofline(engine, peaks, reps=20):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     tf = 2.0 * M * N * K / (ms * 1e-3) / 1e12
+    traffic = None
+    try:        # DRAM bytes of one launch of this shape from the committed ncu --set full capture
+        t = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))["gemm_tc_persist_kernel"]
+        if t["shape"] == [M, N, K]:
+            traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+    except (OSError, KeyError, ValueError):
+        pass
     return {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-            "frac": tf / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
+            "frac": tf / peaks["bf16_tflops"], "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write, ncu)",
+            "peak_source": peaks["source"],
             "kernel": "gemm_tc_persist_kernel (bf16x3: 3 UMMAs per float32-accurate product; tensor-pipe work = 3x achieved)",
             "shape": [M, N, K], "ms": ms}
 
