@@ -59,9 +59,9 @@ __global__ void to_sb16_kernel(const float* __restrict__ x, int64_t n, __nv_bflo
 // into registers (D <= 2048), two block reductions, one write: a single memory round trip per LayerNorm.
 constexpr int LN_THREADS = 128, LN_MAXV = 16;
 __global__ void __launch_bounds__(LN_THREADS)
-layernorm_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, int M, int D, __nv_bfloat16* __restrict__ o, int64_t ldo,
-                 int64_t o_plane, float* __restrict__ of, int64_t ldf)
+layernorm_kernel(const float* x, int64_t ldx, const float* gamma,
+                 const float* beta, int M, int D, __nv_bfloat16* o, int64_t ldo,
+                 int64_t o_plane, float* of, int64_t ldf)
 {
     pdl_launch();
     pdl_wait();
@@ -220,9 +220,9 @@ __global__ void window_gather_kernel(const int64_t* __restrict__ mel_ptr, int n_
 }
 
 // ------------------------------------------------------------------------------------------- embed
-__global__ void embed_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ positions,
-                             const float* __restrict__ emb, const float* __restrict__ pos, int rows, int D,
-                             float* __restrict__ out)
+__global__ void embed_kernel(const int32_t* tokens, const int32_t* positions,
+                             const float* emb, const float* pos, int rows, int D,
+                             float* out)
 {
     pdl_launch();
     pdl_wait();
@@ -246,12 +246,12 @@ __global__ void gather_rows_kernel(const float* __restrict__ x, int64_t ldx, con
 // One CTA (128 threads) per (query row, head); head_dim 64.  Scores, softmax and weighted sum in fp32.
 constexpr int DA_THREADS = 128;
 __global__ void __launch_bounds__(DA_THREADS)
-decoder_attention_kernel(const int kind, const float* __restrict__ q, int64_t ldq, const float* __restrict__ kc,
-                         const float* __restrict__ vc, int64_t seq_stride, int ctx,
-                         const int32_t* __restrict__ row_seq, const int32_t* __restrict__ row_pos, int H,
-                         __nv_bfloat16* __restrict__ o, int64_t ldo, int64_t o_plane, float* __restrict__ qk_out,
-                         const int32_t* __restrict__ head_slot, int n_slots, int qk_rows,
-                         const int32_t* __restrict__ qk_row, const int32_t* __restrict__ row_active)
+decoder_attention_kernel(const int kind, const float* q, int64_t ldq, const float* kc,
+                         const float* vc, int64_t seq_stride, int ctx,
+                         const int32_t* row_seq, const int32_t* row_pos, int H,
+                         __nv_bfloat16* o, int64_t ldo, int64_t o_plane, float* qk_out,
+                         const int32_t* head_slot, int n_slots, int qk_rows,
+                         const int32_t* qk_row, const int32_t* row_active)
 {
     pdl_launch();
     pdl_wait();
@@ -335,6 +335,9 @@ __global__ void cross_kv_pack_kernel(const float* __restrict__ src, __half* __re
     }
 }
 
+// (The decode-step kernels take plain, not __restrict__, pointers: under programmatic dependent launch a consumer is
+// resident before its producer has finished, so producer-written buffers must not be read through the non-coherent
+// ld.global.nc path the compiler picks for const __restrict__ data.)
 // One CTA per (query row, head); 256 threads = 32 key groups x 8 lanes, a lane owns 8 of the 64 channels.
 // A group streams keys g, g+32, ...: K row (16 B/lane fp16, or 32 B/lane from the float32 alignment copy) and
 // V row (16 B/lane) are both loaded CA_UNROLL keys ahead (coalesced 128-byte rows, >= 128 B in flight per lane),
@@ -403,12 +406,12 @@ __device__ __forceinline__ void ca_stream(const void* __restrict__ Kbase, const 
 }
 
 __global__ void __launch_bounds__(CA_THREADS)
-cross_attention_f16_kernel(const float* __restrict__ q, int64_t ldq, const __half* __restrict__ k16,
-                           const __half* __restrict__ v16, const float* __restrict__ k_align,
-                           const int32_t* __restrict__ head_slot, int n_slots, int ctx,
-                           const int32_t* __restrict__ row_seq, int H, __nv_bfloat16* __restrict__ o, int64_t ldo,
-                           int64_t o_plane, float* __restrict__ qk_out, int qk_rows, const int32_t* __restrict__ qk_row,
-                           const int32_t* __restrict__ row_active)
+cross_attention_f16_kernel(const float* q, int64_t ldq, const __half* k16,
+                           const __half* v16, const float* k_align,
+                           const int32_t* head_slot, int n_slots, int ctx,
+                           const int32_t* row_seq, int H, __nv_bfloat16* o, int64_t ldo,
+                           int64_t o_plane, float* qk_out, int qk_rows, const int32_t* qk_row,
+                           const int32_t* row_active)
 {
     pdl_launch();
     pdl_wait();
@@ -464,9 +467,9 @@ cross_attention_f16_kernel(const float* __restrict__ q, int64_t ldq, const __hal
     }
 }
 
-__global__ void kv_append_kernel(const float* __restrict__ k, const float* __restrict__ v, int64_t ld,
-                                 const int32_t* __restrict__ row_seq, const int32_t* __restrict__ row_pos, int H,
-                                 int ctx, float* __restrict__ kc, float* __restrict__ vc, int64_t seq_stride)
+__global__ void kv_append_kernel(const float* k, const float* v, int64_t ld,
+                                 const int32_t* row_seq, const int32_t* row_pos, int H,
+                                 int ctx, float* kc, float* vc, int64_t seq_stride)
 {
     pdl_launch();
     pdl_wait();
@@ -483,11 +486,11 @@ __global__ void kv_append_kernel(const float* __restrict__ k, const float* __res
 // ------------------------------------------------------------------------------------ decode select
 constexpr int DS_THREADS = 512;
 __global__ void __launch_bounds__(DS_THREADS)
-decode_select_kernel(float* __restrict__ logits, int64_t ldl, const WtsDecodeCfg cfg,
-                     const uint8_t* __restrict__ suppress, const uint8_t* __restrict__ blank,
-                     int32_t* __restrict__ tokens, int32_t* __restrict__ n_tokens,
-                     const int32_t* __restrict__ n_prompt, int32_t* __restrict__ done,
-                     float* __restrict__ logprobs, int lp_ld, float* __restrict__ full)
+decode_select_kernel(float* logits, int64_t ldl, const WtsDecodeCfg cfg,
+                     const uint8_t* suppress, const uint8_t* blank,
+                     int32_t* tokens, int32_t* n_tokens,
+                     const int32_t* n_prompt, int32_t* done,
+                     float* logprobs, int lp_ld, float* full)
 {
     pdl_launch();
     pdl_wait();
@@ -599,10 +602,10 @@ decode_select_kernel(float* __restrict__ logits, int64_t ldl, const WtsDecodeCfg
     }
 }
 
-__global__ void step_inputs_kernel(const int32_t* __restrict__ tokens, int ld, const int32_t* __restrict__ n_tokens,
-                                   const int32_t* __restrict__ n_prompt, const int32_t* __restrict__ done, int B,
-                                   int32_t* __restrict__ tok, int32_t* __restrict__ pos, int32_t* __restrict__ qk_row,
-                                   int32_t* __restrict__ active)
+__global__ void step_inputs_kernel(const int32_t* tokens, int ld, const int32_t* n_tokens,
+                                   const int32_t* n_prompt, const int32_t* done, int B,
+                                   int32_t* tok, int32_t* pos, int32_t* qk_row,
+                                   int32_t* active)
 {
     pdl_launch();
     pdl_wait();
