@@ -65,7 +65,7 @@ __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.laun
 
 inline bool pdl_enabled()
 {
-    static const bool on = [] { const char* e = getenv("WTS_PDL"); return e ? atoi(e) != 0 : false; }();
+    static const bool on = [] { const char* e = getenv("WTS_PDL"); return e ? atoi(e) != 0 : true; }();
     return on;
 }
 
