@@ -4,7 +4,7 @@ Lane-level numpy model of the CUDA wavefront DTW kernel
 
 It mirrors the kernel's data flow step by step — 31-row strips, lane 0 as the row above the
 strip, shfl_up for `up`, last step's `up` as `diag`, the skewed 64-slot shared-memory staging
-with its 16-step software pipeline, 2-bit direction fields packed by step index, boundary row
+ring (row k of tile t+1 is issued at step k of tile t, so a slot is rewritten only after its last read), 2-bit direction fields packed by step index, boundary row
 hand-over between strips, and the clz-based one-step-per-token backtrack — so that the index
 arithmetic of the kernel can be checked on the CPU (no GPU in the build container) against the
 oracle.  It is a test helper, not product code.
@@ -12,7 +12,7 @@ oracle.  It is a test helper, not product code.
 import numpy as np
 
 RS = 31
-RING = 128
+RING = 64
 PITCH = RING + 1
 
 
@@ -55,7 +55,6 @@ def model_dtw(cost):
                 tile[k, (lanes + 32 * u + k - 1) & (RING - 1)] = flat[base + (k - 1) * F + col]
 
         issue_tile(0, range(1, Ts + 1))
-        issue_tile(1, range(1, Ts + 1))
         bndnext = np.full(32, INF)
         if not first:
             idx = 1 + lanes
@@ -69,7 +68,7 @@ def model_dtw(cost):
             cb = (32 * t) & (RING - 1)
             for k in range(32):
                 if 1 <= k <= Ts:
-                    issue_tile(t + 2, [k])
+                    issue_tile(t + 1, [k])      # row k of the NEXT tile is issued at step k (cp.async, one row per step)
                 s = 32 * t + k
                 l = tile[lanes, cb + k].astype(np.float64)
                 # staging check: every active cell must see its own cost value
