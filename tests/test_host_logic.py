@@ -82,6 +82,35 @@ def test_abi_exports_every_declared_symbol():
     assert nat.lib.wts_version() >= 100
 
 
+def test_struct_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors (whisper_timestamped/_native.py) must have the size and field offsets gcc gives the structs
+    of include/wts.h — this is the C-ABI boundary the reference-side binding relies on."""
+    import ctypes
+    import subprocess
+    from whisper_timestamped import _native as nat
+    mirrors = {"WtsSegDesc": nat.SegDesc, "WtsGemm": nat.Gemm, "WtsDecodeCfg": nat.DecodeCfg}
+    src = ["#include <stdio.h>", "#include <stddef.h>", '#include "wts.h"', "int main(void) {"]
+    for cname, cls in mirrors.items():
+        src.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            src.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    src += ["  return 0;", "}"]
+    c = tmp_path / "layout.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)])
+    seen = 0
+    for line in subprocess.check_output([str(exe)], text=True).splitlines():
+        cname, fname, val = line.split()
+        cls = mirrors[cname]
+        if fname == "size":
+            assert ctypes.sizeof(cls) == int(val), (cname, ctypes.sizeof(cls), val)
+        else:
+            assert getattr(cls, fname).offset == int(val), (cname, fname, getattr(cls, fname).offset, val)
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in mirrors.values())
+
+
 def test_plan_segments_layout():
     from whisper_timestamped import _native as nat
     from whisper_timestamped.alignment import plan_segments
