@@ -69,8 +69,8 @@ def test_gemm_backends_vs_torch(backend):
 
 @pytest.mark.parametrize("backend", BACKENDS)
 def test_gemm_skinny_inplace_residual(backend):
-    """Decode-time shape: one M tile, x += A W^T + b in place (the tensor-core path narrows the N tile and
-    splits K with float32 atomics)."""
+    """Decode-time shape: one M tile, x += A W^T + b in place (tensor-core path: gemm_skinny_kernel, K split over a
+    thread-block cluster and reduced through distributed shared memory)."""
     from whisper_timestamped.model import SB16
     from whisper_timestamped.engine import CudaEngine
     dev = torch.device("cuda:0")
@@ -92,9 +92,8 @@ def test_gemm_skinny_inplace_residual(backend):
 
 @pytest.mark.parametrize("backend", BACKENDS)
 def test_gemm_skinny_split_general_epilogue(backend):
-    """Decode-time GEMMs whose epilogue is NOT the in-place residual (bias, GELU, SB16 / float32 outputs): on the
-    tensor-core path K is split across CTAs, partial sums meet in a float32 workspace and the last CTA of a tile
-    finishes it and cleans up — so every shape runs three times and must stay exact."""
+    """Decode-time GEMMs whose epilogue is NOT the in-place residual (bias, GELU, SB16 / float32 outputs), ragged N and
+    K, 1..128 rows: the cluster reduction must be exact and leave no state behind (every shape runs three times)."""
     from whisper_timestamped.model import SB16
     from whisper_timestamped.engine import CudaEngine
     dev = torch.device("cuda:0")
