@@ -52,6 +52,8 @@ CASES = {
     "tiny_norefine": ("tiny", {}, (40.0, 16), {"language": "en", "refine_whisper_precision": 0.0}),
     "tiny_short": ("tiny", {}, (3.3, 17), {"language": "en"}),
     "tiny_ja_unspaced": ("tiny", {}, (40.0, 18), {"language": "ja"}),
+    # explicit-list VAD: speech spans glued, times mapped back, `speech_activity` reported
+    "tiny_vad_list": ("tiny", {}, (70.0, 19), {"language": "en", "vad": [(2.0, 21.5), (30.25, 52.0), (58.0, 66.4)]}),
 }
 
 

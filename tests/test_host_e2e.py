@@ -53,6 +53,9 @@ def compare(res, ref, conf_tol=0.0015, time_tol=0.0, prob_tol=1e-5):
             assert abs(x["start"] - y["start"]) <= time_tol + 1e-9 and abs(x["end"] - y["end"]) <= time_tol + 1e-9, \
                 (a["id"], x, y)
             assert abs(x["confidence"] - y["confidence"]) <= conf_tol, (a["id"], x, y)
+    assert ("speech_activity" in res) == ("speech_activity" in ref)
+    if "speech_activity" in ref:
+        assert res["speech_activity"] == ref["speech_activity"]
     if "language_probs" in ref:
         for k, v in ref["language_probs"].items():
             assert abs(res["language_probs"][k] - v) < prob_tol
@@ -62,3 +65,26 @@ def compare(res, ref, conf_tol=0.0015, time_tol=0.0, prob_tol=1e-5):
 def test_host_logic_matches_reference_golden(path):
     g, res = run_case(path)
     compare(res, g["result"])
+
+
+def test_vad_convert_timestamps_hand_cases():
+    """Explicit-list VAD remap (restating T.py:2158-2200): glued-axis times back to the original axis."""
+    from whisper_timestamped.vad import check_vad_method, convert_timestamps
+    spans = [(2.0, 21.5), (30.25, 52.0), (58.0, 66.4)]           # glued lengths 19.5, 21.75, 8.4
+    assert convert_timestamps(spans, 0.0) == 2.0
+    assert convert_timestamps(spans, 19.5) == 21.5                # last instant of the first span
+    assert convert_timestamps(spans, 19.6) == 30.35               # 0.1 s into the second span
+    assert convert_timestamps(spans, 41.25 + 1.0) == 59.0
+    assert convert_timestamps(spans, 100.0) == 116.75             # beyond the end: shifted by the removed 16.75 s, not clamped
+    # a pair straddling the first cut: candidates are [21.0, 21.5] (first span, end clamped) and [30.25, 30.75] (second
+    # span, start clamped); both keep 0.5 s of the 1.0 s, the stable sort keeps the first
+    assert convert_timestamps(spans, 19.0, 20.0) == [21.0, 21.5]
+    assert convert_timestamps(spans, 19.4, 21.0) == [30.25, 31.75]   # here the second span preserves more of the duration
+    assert check_vad_method(False) is None and check_vad_method(None) is None
+    assert check_vad_method([[0, 1.5], (2, 3)]) == [(0, 1.5), (2, 3)]
+    with pytest.raises(NotImplementedError):
+        check_vad_method("silero")
+    with pytest.raises(NotImplementedError):
+        check_vad_method(True)
+    with pytest.raises(AssertionError):
+        check_vad_method([(0, 1, 2)])

@@ -18,6 +18,7 @@ from typing import List, Optional
 
 import numpy as np
 
+from . import vad as V
 from . import words as W
 from .tokenizer import LANGUAGES, TO_LANGUAGE_CODE, get_tokenizer
 from .windows import (HOP_LENGTH, N_FRAMES, SAMPLE_RATE, WindowRecord, make_decode_setup, plan_window_alignment,
@@ -165,8 +166,7 @@ def transcribe_timestamped(
         raise NotImplementedError("detect_disfluencies is a 'next' row (SURVEY.md §8f) and not built yet")
     if plot_word_alignment:
         raise NotImplementedError("plot_word_alignment is out of scope of the hot path")
-    if vad not in (False, None):
-        raise NotImplementedError("vad is a 'next' row (SURVEY.md §8f) and not built yet")
+    vad = V.check_vad_method(vad)          # explicit (start, end) lists only; detector names raise NotImplementedError
     if temperature != 0:
         raise NotImplementedError("temperature sampling is not built yet; greedy (temperature=0) only")
     if word_alignment_most_top_layers is not None:
@@ -179,6 +179,9 @@ def transcribe_timestamped(
 
     # ---- audio -> log-mel on the device, per stream (upstream pads 30 s and floors at the stream max)
     audio = eng.load_audio(audio)
+    vad_spans = convert_timestamps = None
+    if vad is not None:                    # T.py:294-296: the model only sees the glued speech
+        audio, vad_spans, convert_timestamps = V.remove_non_speech(audio, vad)
     n_samples = int(audio.shape[-1])
     if chunks is None:
         cuts = [(0, n_samples)]
@@ -430,6 +433,17 @@ def transcribe_timestamped(
     if chunks is not None:
         for i, seg in enumerate(segs):        # independent cuts: ids / seeks are those of the whole recording
             seg["id"] = i
+    if vad is not None:
+        # back to the time axis of the original audio (T.py:341-355)
+        for seg in segs:
+            for word in seg.get("words", []):
+                word["start"], word["end"] = convert_timestamps(word["start"], word["end"])
+            if refine_whisper_precision and len(seg.get("words", [])):
+                seg["start"] = seg["words"][0]["start"]
+                seg["end"] = seg["words"][-1]["end"]
+            else:
+                seg["start"], seg["end"] = convert_timestamps(seg["start"], seg["end"])
+        transcription["speech_activity"] = [{"start": s, "end": e} for (s, e) in vad_spans]
     return transcription
 
 
