@@ -173,6 +173,8 @@ def transcribe_timestamped(
         raise NotImplementedError("word_alignment_most_top_layers: only the alignment-head tables are built")
 
     eng = engine if engine is not None else model.engine()
+    if hasattr(eng, "release"):
+        eng.release()                      # alignment buffers of a previous call (they are per call, 1.7 GB per 128 windows)
     dims = model.dims
     is_multilingual = model.is_multilingual
     num_languages = model.num_languages
@@ -444,6 +446,8 @@ def transcribe_timestamped(
             else:
                 seg["start"], seg["end"] = convert_timestamps(seg["start"], seg["end"])
         transcription["speech_activity"] = [{"start": s, "end": e} for (s, e) in vad_spans]
+    if hasattr(eng, "release"):
+        eng.release()
     return transcription
 
 
