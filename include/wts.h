@@ -173,6 +173,8 @@ int wts_gather_rows(const float* d_x, int64_t ldx, const int32_t* d_idx, int32_t
 
 /* Decoder attention for a ragged token batch (one query row per (sequence, position)).
  * kind 0: causal self-attention over the sequence's KV cache (keys 0..position);
+ * kind 2: the same for a decode step (ONE row per sequence): d_q points at packed [q | k | v] rows (ldq = 3*D) and
+ *         every (row, head) CTA first appends its K/V of the new position to the cache — wts_kv_append fused in;
  * kind 1: cross-attention over the 1500 encoder positions; when d_qk_out != NULL the PRE-softmax
  *         scores of head `h` are written to d_qk_out[(seq*N + slot)*qk_rows + qk_row[r]] for every head
  *         whose d_head_slot[h] >= 0 (= the alignment heads; replaces hook_attention_weights T.py:783-793).

@@ -263,9 +263,18 @@ decoder_attention_kernel(const int kind, const float* q, int64_t ldq, const floa
     const int r = blockIdx.x, h = blockIdx.y;
     if (row_active != nullptr && !row_active[r]) return;
     const int seq = row_seq[r];
-    const int nk = kind == 0 ? row_pos[r] + 1 : ctx;
+    const int nk = kind == 1 ? ctx : row_pos[r] + 1;
     const float* K = kc + (int64_t)seq * seq_stride + (int64_t)h * ctx * 64;
     const float* V = vc + (int64_t)seq * seq_stride + (int64_t)h * ctx * 64;
+    if (kind == 2) {
+        // decode step (one row per sequence): q points at packed [q | k | v] rows; this CTA appends its head's K/V
+        // of the new position to the cache itself (saves the separate kv_append launch).  The barrier below makes
+        // the two 64-float rows visible to the whole CTA before the score loop reads position row_pos[r].
+        const float* src = q + (int64_t)r * ldq + h * 64;
+        const int64_t at = (int64_t)(nk - 1) * 64 + (threadIdx.x & 63);
+        if (threadIdx.x < 64) const_cast<float*>(K)[at] = src[(int64_t)H * 64 + threadIdx.x];
+        else                  const_cast<float*>(V)[at] = src[(int64_t)2 * H * 64 + (threadIdx.x & 63)];
+    }
     if (threadIdx.x < 64) qs[threadIdx.x] = q[(int64_t)r * ldq + h * 64 + threadIdx.x];
     __syncthreads();
     float mx = -CUDART_INF_F;

@@ -257,10 +257,13 @@ class CudaEngine:
             a, c = blk.attn, blk.cross
             self.layernorm(x, a.ln_g, a.ln_b, R, D, out_sb=hs)
             self.gemm(hs, a.qkv, R, 3 * D, D, bias=a.qkv_b, out_f32=qkv, ldc=3 * D, row_mask=active)
-            nat.check(nat.lib.wts_kv_append(qkv.data_ptr() + 4 * D, qkv.data_ptr() + 8 * D, 3 * D, row_seq.data_ptr(),
-                                            row_pos.data_ptr(), R, H, d.n_text_ctx, st8["sk"][li].data_ptr(),
-                                            st8["sv"][li].data_ptr(), H * d.n_text_ctx * 64, st), "wts_kv_append")
-            nat.check(nat.lib.wts_decoder_attention(0, qkv.data_ptr(), 3 * D, st8["sk"][li].data_ptr(),
+            fused_append = active is not None          # decode step: one row per sequence, the attention CTA appends K/V
+            if not fused_append:
+                nat.check(nat.lib.wts_kv_append(qkv.data_ptr() + 4 * D, qkv.data_ptr() + 8 * D, 3 * D, row_seq.data_ptr(),
+                                                row_pos.data_ptr(), R, H, d.n_text_ctx, st8["sk"][li].data_ptr(),
+                                                st8["sv"][li].data_ptr(), H * d.n_text_ctx * 64, st), "wts_kv_append")
+                self.launches += 1
+            nat.check(nat.lib.wts_decoder_attention(2 if fused_append else 0, qkv.data_ptr(), 3 * D, st8["sk"][li].data_ptr(),
                                                     st8["sv"][li].data_ptr(), H * d.n_text_ctx * 64, d.n_text_ctx,
                                                     row_seq.data_ptr(), row_pos.data_ptr(), R, H, att.ptr, att.ld,
                                                     att.plane, None, None, 0, 0, None,
@@ -279,7 +282,7 @@ class CudaEngine:
             self.layernorm(x, blk.mlp_ln_g, blk.mlp_ln_b, R, D, out_sb=hs)
             self.gemm(hs, blk.fc1, R, 4 * D, D, bias=blk.fc1_b, act=1, out_sb=mid, row_mask=active)
             self.gemm(mid, blk.fc2, R, D, 4 * D, bias=blk.fc2_b, residual=x, ldr=D, out_f32=x, ldc=D, row_mask=active)
-            self.launches += 3
+            self.launches += 2
 
     def _alloc_decoder_state(self, B, R):
         d, dev = self.dims, self.dev
