@@ -510,6 +510,20 @@ def main():
             }
             if "roofline" in res:
                 line["roofline"] = res["roofline"]
+            if world == 1 and not args.no_roofline:
+                # second half of the metric ("DTW GB/s vs HBM peak"): the SURVEY §8(d) alignment micro-workload, measured
+                # in the same run (what `--workload align` reports); never allowed to take the headline down with it
+                try:
+                    import torch
+                    torch.cuda.empty_cache()
+                    al = run_align(args, rank, world)
+                    line["dtw_roofline"] = {
+                        "bound": "hbm", "achieved": al["dtw_gbs"], "peak": al["peaks"]["hbm_gbs"], "unit": "GB/s",
+                        "frac": al["dtw_gbs"] / al["peaks"]["hbm_gbs"], "traffic": None, "kernel": "dtw_warp_kernel<float>",
+                        "ms": al["ms_dtw"], "prep_gbs": al["prep_gbs"], "prep_ms": al["ms_prep"],
+                        "workload": f"{args.align_batch} segments, T={args.align_T}, F={args.align_F}, N=10 heads"}
+                except Exception as err:                                   # noqa: BLE001
+                    line["dtw_roofline"] = {"error": f"{type(err).__name__}: {err}"[:200]}
             if not args.no_cpu_baseline:
                 line["cpu_baseline"] = cpu_baseline_e2e(args)
             print(json.dumps(line))
