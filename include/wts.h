@@ -226,6 +226,11 @@ int wts_step_inputs(const int32_t* d_tokens, int32_t tokens_ld, const int32_t* d
 int wts_softmax_pick(const float* d_logits, int64_t ldl, int32_t n, int32_t index, float* d_out, int32_t rows,
                      void* stream);
 
+/* d_out[i] = log_softmax(d_logits[d_rows[i]])[d_tokens[i]]: teacher-forced token log-probabilities of the two-pass
+ * strategy (F.log_softmax + gather, T.py:1245-1246, 1285-1300). */
+int wts_logprob_gather(const float* d_logits, int64_t ldl, int32_t n, const int32_t* d_rows, const int32_t* d_tokens,
+                       float* d_out, int32_t count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

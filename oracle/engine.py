@@ -64,8 +64,9 @@ class OracleEngine:
             audio = torch.from_numpy(audio)
         return audio.float()
 
-    def log_mel(self, audio):
-        return whisper.log_mel_spectrogram(audio, self.model.dims.n_mels, padding=whisper.audio.N_SAMPLES)
+    def log_mel(self, audio, pad_30s=True):
+        # pad_30s=False: the two-pass strategy's per-segment mel (reference T.py:1213: no padding argument)
+        return whisper.log_mel_spectrogram(audio, self.model.dims.n_mels, padding=whisper.audio.N_SAMPLES if pad_30s else 0)
 
     def mel_frames(self, mel):
         return mel.shape[-1]
@@ -126,6 +127,30 @@ class OracleEngine:
                                     temperature=0.0, language=tok.language,
                                     last_row_logprobs=lambda t, last=last: float(last[t])))
         return out
+
+    # ---- teacher-forced pass of the two-pass strategy (reference T.py:1213-1249)
+    @torch.no_grad()
+    def teacher_forced(self, mel, tokens_in, i_start, pairs):
+        """mel: un-padded [n_mels, frames]; tokens_in: sot sequence + <|0.00|> + text tokens.  Registers the alignment
+        heads' cross-attention rows from position i_start-1 on as a new window and returns (window id, float32
+        log_softmax(logits[step])[token] for every (step, token) in `pairs`)."""
+        mfcc = whisper.pad_or_trim(mel, whisper.audio.N_FRAMES).unsqueeze(0)
+        captured = [None] * len(self.model.decoder.blocks)
+        hooks = []
+        for i, blk in enumerate(self.model.decoder.blocks):
+            hooks.append(blk.cross_attn.register_forward_hook(
+                lambda layer, ins, outs, index=i: captured.__setitem__(index, outs[-1])))
+        try:
+            with disable_sdpa():
+                logits = self.model(mfcc, torch.tensor(list(tokens_in), dtype=torch.int32).unsqueeze(0))
+        finally:
+            for h in hooks:
+                h.remove()
+        lp = torch.nn.functional.log_softmax(logits, dim=-1)
+        qk = torch.stack([captured[l][0, h, i_start - 1:, :] for (l, h) in self.heads]).float()   # [N, rows, 1500]
+        self.qk.append(qk)
+        vals = np.array([float(lp[0, s_, t_]) for (s_, t_) in pairs], dtype=np.float32)
+        return len(self.qk) - 1, vals
 
     # ---- alignment numerics (oracle)
     def align(self, items):

@@ -52,6 +52,13 @@ CASES = {
     "tiny_norefine": ("tiny", {}, (40.0, 16), {"language": "en", "refine_whisper_precision": 0.0}),
     "tiny_short": ("tiny", {}, (3.3, 17), {"language": "en"}),
     "tiny_ja_unspaced": ("tiny", {}, (40.0, 18), {"language": "ja"}),
+    # two-pass ("naive") strategy, greedy, with and without trust in Whisper's timestamps
+    "tiny_naive": ("tiny", {}, (75.0, 21), {"language": "en", "naive_approach": True, "temperature": 0.0}),
+    "tiny_naive_notrust": ("tiny", {}, (65.0, 22), {"language": "en", "naive_approach": True, "temperature": 0.0,
+                                                    "trust_whisper_timestamps": False}),
+    "tiny_naive_opts": ("tiny", {}, (45.0, 23), {"language": "fr", "naive_approach": True, "temperature": 0.0,
+                                                 "include_punctuation_in_confidence": True,
+                                                 "remove_punctuation_from_words": True, "refine_whisper_precision": 0.2}),
     # explicit-list VAD: speech spans glued, times mapped back, `speech_activity` reported
     "tiny_vad_list": ("tiny", {}, (70.0, 19), {"language": "en", "vad": [(2.0, 21.5), (30.25, 52.0), (58.0, 66.4)]}),
 }

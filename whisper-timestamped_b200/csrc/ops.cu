@@ -641,6 +641,22 @@ __global__ void softmax_pick_kernel(const float* __restrict__ logits, int64_t ld
     if (threadIdx.x == 0) out[blockIdx.x] = expf(x[index] - mx) / s;
 }
 
+// log_softmax(logits[row[i]])[token[i]] for a list of (row, token) pairs: the teacher-forced log-probabilities the
+// two-pass ("naive") strategy turns into word confidences (T.py:1245-1246, 1285-1300).  One CTA per pair.
+__global__ void logprob_gather_kernel(const float* logits, int64_t ldl, int n, const int32_t* rows, const int32_t* tokens,
+                                      float* out)
+{
+    __shared__ float red[32];
+    const float* x = logits + (int64_t)rows[blockIdx.x] * ldl;
+    float mx = -CUDART_INF_F;
+    for (int v = threadIdx.x; v < n; v += blockDim.x) mx = fmaxf(mx, x[v]);
+    mx = block_reduce_max(mx, red);
+    float s = 0.f;
+    for (int v = threadIdx.x; v < n; v += blockDim.x) s += expf(x[v] - mx);
+    s = block_reduce_sum(s, red);
+    if (threadIdx.x == 0) out[blockIdx.x] = (x[tokens[blockIdx.x]] - mx) - logf(s);
+}
+
 }  // namespace wts
 
 using namespace wts;
@@ -831,6 +847,16 @@ extern "C" int wts_softmax_pick(const float* d_logits, int64_t ldl, int32_t n, i
 {
     if (rows <= 0) return 0;
     softmax_pick_kernel<<<rows, 512, 0, (cudaStream_t)stream>>>(d_logits, ldl, n, index, d_out);
+    WTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int wts_logprob_gather(const float* d_logits, int64_t ldl, int32_t n, const int32_t* d_rows,
+                                  const int32_t* d_tokens, float* d_out, int32_t count, void* stream)
+{
+    if (count <= 0) return 0;
+    if (!d_logits || !d_rows || !d_tokens || !d_out) { set_error("wts_logprob_gather: null pointer"); return -2; }
+    logprob_gather_kernel<<<count, 512, 0, (cudaStream_t)stream>>>(d_logits, ldl, n, d_rows, d_tokens, d_out);
     WTS_LAUNCH_CHECK();
     return 0;
 }

@@ -100,9 +100,10 @@ def _load():
     lib.wts_decode_select.argtypes = [vp, i64, ctypes.POINTER(DecodeCfg), vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, vp]
     lib.wts_step_inputs.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp]
     lib.wts_softmax_pick.argtypes = [vp, i64, i32, i32, vp, i32, vp]
+    lib.wts_logprob_gather.argtypes = [vp, i64, i32, vp, vp, vp, i32, vp]
     for name in ("wts_to_sb16", "wts_layernorm", "wts_softmax_rows", "wts_frames", "wts_power", "wts_logmel_max",
                  "wts_logmel_finish", "wts_window_gather", "wts_embed", "wts_gather_rows", "wts_decoder_attention",
-                 "wts_kv_append", "wts_decode_select", "wts_step_inputs", "wts_softmax_pick", "wts_cross_kv_pack",
+                 "wts_kv_append", "wts_decode_select", "wts_step_inputs", "wts_softmax_pick", "wts_logprob_gather", "wts_cross_kv_pack",
                  "wts_cross_attention_f16"):
         getattr(lib, name).restype = ctypes.c_int
     return lib
@@ -115,7 +116,7 @@ EXPORTED_SYMBOLS = [
     "wts_attn_prep_batch", "wts_dtw_batch", "wts_gemm", "wts_to_sb16", "wts_layernorm", "wts_softmax_rows",
     "wts_frames", "wts_power", "wts_logmel_max", "wts_logmel_finish", "wts_window_gather", "wts_embed",
     "wts_gather_rows", "wts_decoder_attention", "wts_kv_append", "wts_decode_select", "wts_step_inputs",
-    "wts_softmax_pick", "wts_cross_kv_pack", "wts_cross_attention_f16", "wts_enc_attention",
+    "wts_softmax_pick", "wts_logprob_gather", "wts_cross_kv_pack", "wts_cross_attention_f16", "wts_enc_attention",
 ]
 
 

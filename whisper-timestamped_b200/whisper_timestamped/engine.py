@@ -155,16 +155,17 @@ class CudaEngine:
             audio = (audio.pin_memory() if audio.device.type == "cpu" else audio).to(self.dev, non_blocking=True)
         return audio.contiguous()
 
-    def log_mel(self, audio):
+    def log_mel(self, audio, pad_30s=True):
         """float32 time-major log-mel [frames, n_mels] of `audio` + 30 s of zero padding (upstream
-        log_mel_spectrogram(audio, n_mels, padding=N_SAMPLES)); the -8 floor uses this stream's maximum."""
+        log_mel_spectrogram(audio, n_mels, padding=N_SAMPLES)); the -8 floor uses this stream's maximum.
+        pad_30s=False: no padding (the per-segment mel of the two-pass strategy, T.py:1213)."""
         with self.phase("mel"):
-            return self._log_mel(audio)
+            return self._log_mel(audio, N_SAMPLES if pad_30s else 0)
 
-    def _log_mel(self, audio):
+    def _log_mel(self, audio, padding=N_SAMPLES):
         dev, st = self.dev, self._st()
         n = int(audio.numel())
-        total = n + N_SAMPLES
+        total = n + padding
         nf = total // 160
         C = self.dims.n_mels
         frames = torch.empty((nf, 400), dtype=torch.float32, device=dev)
@@ -545,6 +546,61 @@ class CudaEngine:
         hs = st8["hs_fin"]
         self.layernorm(x_rows, w.ln_g, w.ln_b, n_rows, d.n_text_state, out_sb=hs)
         self.gemm(hs, w.emb_sb, n_rows, d.n_vocab, d.n_text_state, out_f32=logits, ldc=d.n_vocab, row_mask=active)
+
+    # ------------------------------------------------------------------ teacher-forced pass (two-pass strategy)
+    @torch.no_grad()
+    def teacher_forced(self, mel, tokens_in, i_start, pairs):
+        """Second pass of the two-pass strategy for ONE segment (T.py:1213-1249): encoder on the segment's own mel,
+        decoder teacher-forced on `tokens_in` (sot sequence + <|0.00|> + text tokens).  The alignment heads' cross-
+        attention rows from position i_start-1 on become a new alignment window; returns (window id, float32
+        log_softmax(logits[step])[token] for every (step, token) in `pairs`)."""
+        d, dev, st, w = self.dims, self.dev, self._st(), self.w
+        tokens_in = [int(t) for t in tokens_in]
+        R, D, V = len(tokens_in), d.n_text_state, d.n_vocab
+        assert 0 < R <= d.n_text_ctx, f"{R} tokens do not fit the decoder context ({d.n_text_ctx})"
+        size = min(N_FRAMES, int(mel.shape[0]))
+        with self.phase("encoder"):
+            xa = self.encode([dict(mel=mel, seek=0, segment_size=size)])
+        st8 = getattr(self, "_tf_state", None)
+        if st8 is None:
+            st8 = self._tf_state = self._alloc_decoder_state(1, d.n_text_ctx)
+        with self.phase("cross_kv"):
+            self._cross_kv(xa, st8, 1)
+        del xa
+        rows = R - (i_start - 1)
+        qk_buf = torch.zeros((1, max(1, len(self.m.heads)), rows, N_CTX_AUDIO), dtype=torch.float32, device=dev)
+        row_seq = _i32([0] * R, dev)
+        row_pos = _i32(list(range(R)), dev)
+        row_tok = _i32(tokens_in, dev)
+        qk_row = _i32([p - (i_start - 1) if p >= i_start - 1 else -1 for p in range(R)], dev)
+        x = torch.empty((R, D), dtype=torch.float32, device=dev)
+        with self.phase("prefill"):
+            nat.check(nat.lib.wts_embed(row_tok.data_ptr(), row_pos.data_ptr(), w.emb.data_ptr(), w.dec_pos.data_ptr(), R, D,
+                                        x.data_ptr(), st), "wts_embed")
+            self.launches += 1
+            self._decoder_rows(st8, x, R, row_seq, row_pos, qk_row, qk_buf)
+            vals = np.zeros(0, dtype=np.float32)
+            if pairs:
+                steps = sorted({int(s_) for (s_, _) in pairs})
+                index = {s_: i for i, s_ in enumerate(steps)}
+                sel = _i32(steps, dev)
+                xr = torch.empty((len(steps), D), dtype=torch.float32, device=dev)
+                nat.check(nat.lib.wts_gather_rows(x.data_ptr(), D, sel.data_ptr(), len(steps), D, xr.data_ptr(), st),
+                          "wts_gather_rows")
+                logits = torch.empty((len(steps), V), dtype=torch.float32, device=dev)
+                self._final_logits(xr, len(steps), logits)
+                d_rows = _i32([index[int(s_)] for (s_, _) in pairs], dev)
+                d_tok = _i32([int(t_) for (_, t_) in pairs], dev)
+                out = torch.empty(len(pairs), dtype=torch.float32, device=dev)
+                nat.check(nat.lib.wts_logprob_gather(logits.data_ptr(), V, V, d_rows.data_ptr(), d_tok.data_ptr(),
+                                                     out.data_ptr(), len(pairs), st), "wts_logprob_gather")
+                self.launches += 2
+                vals = out.cpu().numpy()
+        buf_idx = len(self.qk_buffers)
+        self.qk_buffers.append(qk_buf)
+        gid = len(self.window_index)
+        self.window_index.append((buf_idx, 0))
+        return gid, vals
 
     # ------------------------------------------------------------------ language detection
     @torch.no_grad()

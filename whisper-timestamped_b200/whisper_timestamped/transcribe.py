@@ -156,12 +156,14 @@ def transcribe_timestamped(
     if isinstance(model, str):
         from .model import load_model
         model = load_model(model)
-    if naive_approach:
+    if isinstance(temperature, (list, tuple)) or temperature != 0 or beam_size is not None or (best_of or 1) > 1 \
+            or use_backend_timestamps:
         raise NotImplementedError(
-            "the two-pass (naive) strategy — beam search / temperature fallback / best_of — is not built yet "
-            "in this B200 drop-in (SURVEY.md §8 row A15); use greedy decoding with a scalar temperature")
-    if not trust_whisper_timestamps:
-        raise NotImplementedError("trust_whisper_timestamps=False is not built yet")
+            "beam search / best_of / temperature fallback / backend timestamps are not built in this B200 drop-in "
+            "(upstream decoding strategies, SURVEY.md §8 row A14); the two-pass strategy itself (naive_approach=True, "
+            "row A15) runs with greedy decoding and a scalar temperature of 0")
+    if not trust_whisper_timestamps and not naive_approach:
+        raise NotImplementedError("trust_whisper_timestamps=False is only built for the two-pass strategy (naive_approach=True)")
     if detect_disfluencies:
         raise NotImplementedError("detect_disfluencies is a 'next' row (SURVEY.md §8f) and not built yet")
     if plot_word_alignment:
@@ -225,183 +227,201 @@ def transcribe_timestamped(
             streams[job["stream"]].consume(rec, tokenizer, no_speech_threshold, logprob_threshold,
                                            condition_on_previous_text)
 
-    # ---- replay the reference's segment/flush logic offline and align everything in one batch
     use_space = should_use_space(language)
-    pending = []          # (stream, window idx, plan, AlignRequest)
-    per_window = {}
-    for st in streams:
-        for wi, rec in enumerate(st.records):
-            nxt = st.records[wi + 1].prompt if wi + 1 < len(st.records) else None
-            reqs = {}
+    if naive_approach:
+        # ---- two-pass strategy (T.py:1004-1338): pass 1 above was plain decoding; pass 2 re-runs the decoder teacher-forced
+        # on every segment's own audio window and aligns all of its tokens at once
+        assert chunks is None, "the two-pass strategy works on one sequential stream (chunks=None)"
+        from . import naive as NV
+        st = streams[0]
+        all_segments = list(st.segments)
+        all_words = NV.second_pass(eng, audio, all_segments, tokenizer, language, use_space=use_space,
+                                   refine_nframes=refine_nframes, trust_whisper_timestamps=trust_whisper_timestamps,
+                                   remove_punctuation_from_words=remove_punctuation_from_words,
+                                   compute_word_confidence=compute_word_confidence,
+                                   include_punctuation_in_confidence=include_punctuation_in_confidence,
+                                   min_word_duration=0.0)
+        for w in all_words:
+            w["_stream"] = 0
+        text_parts = [tokenizer.decode(st.all_tokens[st.n_initial_prompt:])]
+    else:
+        # ---- replay the reference's segment/flush logic offline and align everything in one batch
+        use_space = should_use_space(language)
+        pending = []          # (stream, window idx, plan, AlignRequest)
+        per_window = {}
+        for st in streams:
+            for wi, rec in enumerate(st.records):
+                nxt = st.records[wi + 1].prompt if wi + 1 < len(st.records) else None
+                reqs = {}
 
-            def yields_words(plan, reqs=reqs):
-                # T.py:540-559: `ws` is empty when there is nothing between the timestamps or every word is a
-                # special token; this only depends on the tokens, so it is known before the DTW runs
-                req = None
-                if len(plan.tokens) > 1:
-                    req = W.prepare_alignment(plan.tokens, plan.n_rows, tokenizer, use_space=use_space,
-                                              refine_nframes=refine_nframes,
-                                              remove_punctuation_from_words=remove_punctuation_from_words,
-                                              unfinished_decoding=plan.unfinished)
-                reqs[id(plan)] = req
-                if req is None:
-                    return False
-                kept = req.words[1:] if req.unfinished else req.words[1:-1]
-                return any(not w.startswith("<|") for w in kept)
+                def yields_words(plan, reqs=reqs):
+                    # T.py:540-559: `ws` is empty when there is nothing between the timestamps or every word is a
+                    # special token; this only depends on the tokens, so it is known before the DTW runs
+                    req = None
+                    if len(plan.tokens) > 1:
+                        req = W.prepare_alignment(plan.tokens, plan.n_rows, tokenizer, use_space=use_space,
+                                                  refine_nframes=refine_nframes,
+                                                  remove_punctuation_from_words=remove_punctuation_from_words,
+                                                  unfinished_decoding=plan.unfinished)
+                    reqs[id(plan)] = req
+                    if req is None:
+                        return False
+                    kept = req.words[1:] if req.unfinished else req.words[1:-1]
+                    return any(not w.startswith("<|") for w in kept)
 
-            plans, info = plan_window_alignment(rec, setup, nxt, yields_words)
-            per_window[(st.index, wi)] = (plans, info)
-            for plan in plans:
-                req = reqs[id(plan)]
-                for msg in req.warnings:
-                    logger.warning(msg)
-                if rec.max_duration and req.f0 >= rec.max_duration:
-                    logger.warning("Got start time outside of audio boundary")
-                pending.append((st, wi, plan, req))
-    items = []
-    for (st, wi, plan, req) in pending:
-        if req is None:
-            continue
-        rec = st.records[wi]
-        items.append(dict(window=rec.qk_window, row0=plan.row0, last_row=plan.row0 + req.row_offset_last,
-                          T=req.T, f0=req.f0, F=req.F, max_dur=rec.max_duration or 0))
-    jumps_list = eng.align(items) if items else []
-    jit = iter(jumps_list)
+                plans, info = plan_window_alignment(rec, setup, nxt, yields_words)
+                per_window[(st.index, wi)] = (plans, info)
+                for plan in plans:
+                    req = reqs[id(plan)]
+                    for msg in req.warnings:
+                        logger.warning(msg)
+                    if rec.max_duration and req.f0 >= rec.max_duration:
+                        logger.warning("Got start time outside of audio boundary")
+                    pending.append((st, wi, plan, req))
+        items = []
+        for (st, wi, plan, req) in pending:
+            if req is None:
+                continue
+            rec = st.records[wi]
+            items.append(dict(window=rec.qk_window, row0=plan.row0, last_row=plan.row0 + req.row_offset_last,
+                              T=req.T, f0=req.f0, F=req.F, max_dur=rec.max_duration or 0))
+        jumps_list = eng.align(items) if items else []
+        jit = iter(jumps_list)
 
-    # ---- per stream: words, confidences, compile (T.py:712-771, 912-1002)
-    all_segments, all_words = [], []
-    text_parts = []
-    for st in streams:
-        seg_words = []        # words of every flushed segment of this stream, in order
-        seg_logprobs = []     # log-probs of the text tokens of the same segments
-        seg_avglogprob = []
-        seg_tokens = []       # the token list each flushed segment ended up with
-        pend_iter = [p for p in pending if p[0] is st]
-        by_window = {}
-        for p in pend_iter:
-            by_window.setdefault(p[1], []).append(p)
-        for wi, rec in enumerate(st.records):
-            plans, info = per_window[(st.index, wi)]
-            ws_of_window, kept_plans = [], []
-            for (_, _, plan, req) in by_window.get(wi, []):
-                ws = W.words_from_jumps(req, next(jit)) if req is not None else []
-                assert ws, "plan_window_alignment only keeps segments that yield words"
-                ws_of_window.append(ws)
-                kept_plans.append(plan)
-            # chunk-level log-probs and the silence rule (T.py:712-748)
-            should_skip = False
-            if compute_word_confidence or no_speech_threshold is not None:
-                should_skip = (rec.no_speech_prob > no_speech_threshold) if no_speech_threshold is not None else False
-                lp = np.array(rec.logprobs, dtype=np.float32)
-                n = len(lp)
-                last_unfinished = bool(kept_plans) and kept_plans[-1].unfinished and plans and plans[-1] is kept_plans[-1] \
-                    and info["final_unfinished"]
-                if last_unfinished:
-                    fallback = kept_plans[-1].appended_token
-                    chosen_last = rec.tokens[n - 1] if n - 1 < len(rec.tokens) else tokenizer.eot
-                    if fallback != chosen_last:
-                        lp[-1] = rec.last_row_logprobs(fallback)
-                    ws_of_window[-1][-1]["avg_logprob_reliable"] = kept_plans[-1].last_token_reliable
-                    n += 1
-                elif info["reached"] and ws_of_window:
-                    ws_of_window[-1][-1]["avg_logprob_reliable"] = (setup.temperature == 0)
-                assert np.all(np.isfinite(lp)), "Got infinite logprob"
-                avg_logprob = float(lp.sum(dtype=np.float32)) / n if n else 0.0
-                if logprob_threshold is not None and avg_logprob > logprob_threshold:
-                    should_skip = False
-            if should_skip:
-                continue                       # upstream skipped this window too (no segments)
-            for plan, ws in zip(kept_plans, ws_of_window):
-                seg_words.append(ws)
-                seg_tokens.append(list(plan.tokens))
-                if compute_word_confidence:
-                    a = plan.row0 + 1          # skip the start timestamp
-                    b = plan.row0 + len(plan.tokens) - (0 if (plan.unfinished and plan is kept_plans[-1] and info["final_unfinished"]) else 1)
-                    seg_logprobs.append(lp[a:b])
-                    seg_avglogprob.append(avg_logprob)
-                else:
-                    seg_logprobs.append(None)
-                    seg_avglogprob.append(None)
-
-        whisper_segments = [s for s in st.segments if s["text"]] if any(not s["text"] for s in st.segments) \
-            else list(st.segments)
-        l1, l2 = len(whisper_segments), len(seg_words)
-        assert l1 == l2 or l1 == 0, \
-            f"Inconsistent number of segments: whisper_segments ({l1}) != timestamped_word_segments ({l2})"
-        special0 = min(tokenizer.sot, tokenizer.eot)
-
-        def strip_special(toks):
-            toks = list(toks)
-            while toks and toks[0] >= special0:
-                toks = toks[1:]
-            while toks and toks[-1] >= special0:
-                toks = toks[:-1]
-            return toks
-
-        for i, (segment, ws, lps, avglp, flushed) in enumerate(zip(whisper_segments, seg_words, seg_logprobs,
-                                                                    seg_avglogprob, seg_tokens)):
-            # T.py:941-957: the tokens the state machine flushed vs the tokens upstream kept
-            ours, theirs = strip_special(flushed), strip_special(segment["tokens"])
-            if ours != theirs:
-                if len(ours) == len(theirs) + 1:
-                    logger.warning(f"An additional token was added on segment {i}")
-                elif len(theirs) == 0:
-                    logger.warning(f"Whisper has empty segment {i}")
-                    assert segment["end"] == segment["start"], f"Fatal Error: Got empty segment {i} with non-zero duration"
-                    segment["tokens"] = ours
-                    segment["text"] = tokenizer.decode(ours)
-                else:
-                    assert len(ours) < len(theirs) and ours == theirs[:len(ours)], \
-                        f"Fatal Error: Got inconsistent text for segment {i}:\n{ours}\n!=\n{theirs}"
-                    segment["tokens"] = list(flushed)
-                    segment["text"] = tokenizer.decode(segment["tokens"])
-                    logger.warning(f"Text had to be shortned on segment {i}")
-                ws[-1]["avg_logprob_reliable"] = False
-            offset = segment["seek"] * HOP_LENGTH / SAMPLE_RATE
-            for w in ws:
-                w["start"] += offset
-                w["end"] += offset
-                w["idx_segment"] = len(all_segments) + i      # index in the FILTERED list, used on the full list (as T.py:963 / 329-331)
-            if compute_word_confidence:
-                if ws[-1].get("avg_logprob_reliable", True):
-                    if abs(segment["avg_logprob"] - avglp) >= 1e-2:
-                        logger.warning(f"Recomputed different logprob for segment {i}: {avglp} != {segment['avg_logprob']}")
-                if include_punctuation_in_confidence:
-                    segment["confidence"] = W.round_confidence(float(np.exp(lps.mean(dtype=np.float32))))
-                nopunc = []
-                i_end = 0
-                for w in ws:
-                    i_start = i_end
-                    pieces = w["tokens"]
-                    i_end += len(pieces)
-                    assert i_end <= len(lps), f"Fatal Error: Got out-of-bound index for segment {i}: {i_end} > {len(lps)}"
-                    if include_punctuation_in_confidence:
-                        wl = lps[i_start:i_end]
+        # ---- per stream: words, confidences, compile (T.py:712-771, 912-1002)
+        all_segments, all_words = [], []
+        text_parts = []
+        for st in streams:
+            seg_words = []        # words of every flushed segment of this stream, in order
+            seg_logprobs = []     # log-probs of the text tokens of the same segments
+            seg_avglogprob = []
+            seg_tokens = []       # the token list each flushed segment ended up with
+            pend_iter = [p for p in pending if p[0] is st]
+            by_window = {}
+            for p in pend_iter:
+                by_window.setdefault(p[1], []).append(p)
+            for wi, rec in enumerate(st.records):
+                plans, info = per_window[(st.index, wi)]
+                ws_of_window, kept_plans = [], []
+                for (_, _, plan, req) in by_window.get(wi, []):
+                    ws = W.words_from_jumps(req, next(jit)) if req is not None else []
+                    assert ws, "plan_window_alignment only keeps segments that yield words"
+                    ws_of_window.append(ws)
+                    kept_plans.append(plan)
+                # chunk-level log-probs and the silence rule (T.py:712-748)
+                should_skip = False
+                if compute_word_confidence or no_speech_threshold is not None:
+                    should_skip = (rec.no_speech_prob > no_speech_threshold) if no_speech_threshold is not None else False
+                    lp = np.array(rec.logprobs, dtype=np.float32)
+                    n = len(lp)
+                    last_unfinished = bool(kept_plans) and kept_plans[-1].unfinished and plans and plans[-1] is kept_plans[-1] \
+                        and info["final_unfinished"]
+                    if last_unfinished:
+                        fallback = kept_plans[-1].appended_token
+                        chosen_last = rec.tokens[n - 1] if n - 1 < len(rec.tokens) else tokenizer.eot
+                        if fallback != chosen_last:
+                            lp[-1] = rec.last_row_logprobs(fallback)
+                        ws_of_window[-1][-1]["avg_logprob_reliable"] = kept_plans[-1].last_token_reliable
+                        n += 1
+                    elif info["reached"] and ws_of_window:
+                        ws_of_window[-1][-1]["avg_logprob_reliable"] = (setup.temperature == 0)
+                    assert np.all(np.isfinite(lp)), "Got infinite logprob"
+                    avg_logprob = float(lp.sum(dtype=np.float32)) / n if n else 0.0
+                    if logprob_threshold is not None and avg_logprob > logprob_threshold:
+                        should_skip = False
+                if should_skip:
+                    continue                       # upstream skipped this window too (no segments)
+                for plan, ws in zip(kept_plans, ws_of_window):
+                    seg_words.append(ws)
+                    seg_tokens.append(list(plan.tokens))
+                    if compute_word_confidence:
+                        a = plan.row0 + 1          # skip the start timestamp
+                        b = plan.row0 + len(plan.tokens) - (0 if (plan.unfinished and plan is kept_plans[-1] and info["final_unfinished"]) else 1)
+                        seg_logprobs.append(lp[a:b])
+                        seg_avglogprob.append(avg_logprob)
                     else:
-                        while len(pieces) > 1 and len(pieces[-1]) and pieces[-1][-1] in W.PUNCTUATION:
-                            pieces = pieces[:-1]
-                        wl = lps[i_start:i_start + len(pieces)]
-                        nopunc.append(wl)
-                    w["confidence"] = W.round_confidence(float(np.exp(wl.mean(dtype=np.float32))) if len(wl) else 0.0)
-                if i_end not in (len(lps), len(lps) - 1):
-                    logger.warning(f"Got inconsistent length for segment {i} ({len(lps)} != {i_end}). Some words have been ignored.")
-                if not include_punctuation_in_confidence:
-                    cat = np.concatenate(nopunc) if nopunc else np.zeros(0, np.float32)
-                    segment["confidence"] = W.round_confidence(float(np.exp(cat.mean(dtype=np.float32))))
-            for w in ws:
-                w["_stream"] = st.index
-            all_words.extend(ws)
-        # stream time shift (independent cuts) is applied after the per-window offsets
-        if st.time_shift:
-            for w in (w for ws in seg_words for w in ws):
-                w["start"] = W.round_timestamp(w["start"] + st.time_shift)
-                w["end"] = W.round_timestamp(w["end"] + st.time_shift)
-            for s in st.segments:
-                s["start"] += st.time_shift
-                s["end"] += st.time_shift
-                s["seek"] += int(round(st.time_shift * SAMPLE_RATE / HOP_LENGTH))
-        all_segments.extend(st.segments)              # empty-text segments stay in the output, like the reference
-        text_parts.append(tokenizer.decode(st.all_tokens[st.n_initial_prompt:]))
+                        seg_logprobs.append(None)
+                        seg_avglogprob.append(None)
+
+            whisper_segments = [s for s in st.segments if s["text"]] if any(not s["text"] for s in st.segments) \
+                else list(st.segments)
+            l1, l2 = len(whisper_segments), len(seg_words)
+            assert l1 == l2 or l1 == 0, \
+                f"Inconsistent number of segments: whisper_segments ({l1}) != timestamped_word_segments ({l2})"
+            special0 = min(tokenizer.sot, tokenizer.eot)
+
+            def strip_special(toks):
+                toks = list(toks)
+                while toks and toks[0] >= special0:
+                    toks = toks[1:]
+                while toks and toks[-1] >= special0:
+                    toks = toks[:-1]
+                return toks
+
+            for i, (segment, ws, lps, avglp, flushed) in enumerate(zip(whisper_segments, seg_words, seg_logprobs,
+                                                                        seg_avglogprob, seg_tokens)):
+                # T.py:941-957: the tokens the state machine flushed vs the tokens upstream kept
+                ours, theirs = strip_special(flushed), strip_special(segment["tokens"])
+                if ours != theirs:
+                    if len(ours) == len(theirs) + 1:
+                        logger.warning(f"An additional token was added on segment {i}")
+                    elif len(theirs) == 0:
+                        logger.warning(f"Whisper has empty segment {i}")
+                        assert segment["end"] == segment["start"], f"Fatal Error: Got empty segment {i} with non-zero duration"
+                        segment["tokens"] = ours
+                        segment["text"] = tokenizer.decode(ours)
+                    else:
+                        assert len(ours) < len(theirs) and ours == theirs[:len(ours)], \
+                            f"Fatal Error: Got inconsistent text for segment {i}:\n{ours}\n!=\n{theirs}"
+                        segment["tokens"] = list(flushed)
+                        segment["text"] = tokenizer.decode(segment["tokens"])
+                        logger.warning(f"Text had to be shortned on segment {i}")
+                    ws[-1]["avg_logprob_reliable"] = False
+                offset = segment["seek"] * HOP_LENGTH / SAMPLE_RATE
+                for w in ws:
+                    w["start"] += offset
+                    w["end"] += offset
+                    w["idx_segment"] = len(all_segments) + i      # index in the FILTERED list, used on the full list (as T.py:963 / 329-331)
+                if compute_word_confidence:
+                    if ws[-1].get("avg_logprob_reliable", True):
+                        if abs(segment["avg_logprob"] - avglp) >= 1e-2:
+                            logger.warning(f"Recomputed different logprob for segment {i}: {avglp} != {segment['avg_logprob']}")
+                    if include_punctuation_in_confidence:
+                        segment["confidence"] = W.round_confidence(float(np.exp(lps.mean(dtype=np.float32))))
+                    nopunc = []
+                    i_end = 0
+                    for w in ws:
+                        i_start = i_end
+                        pieces = w["tokens"]
+                        i_end += len(pieces)
+                        assert i_end <= len(lps), f"Fatal Error: Got out-of-bound index for segment {i}: {i_end} > {len(lps)}"
+                        if include_punctuation_in_confidence:
+                            wl = lps[i_start:i_end]
+                        else:
+                            while len(pieces) > 1 and len(pieces[-1]) and pieces[-1][-1] in W.PUNCTUATION:
+                                pieces = pieces[:-1]
+                            wl = lps[i_start:i_start + len(pieces)]
+                            nopunc.append(wl)
+                        w["confidence"] = W.round_confidence(float(np.exp(wl.mean(dtype=np.float32))) if len(wl) else 0.0)
+                    if i_end not in (len(lps), len(lps) - 1):
+                        logger.warning(f"Got inconsistent length for segment {i} ({len(lps)} != {i_end}). Some words have been ignored.")
+                    if not include_punctuation_in_confidence:
+                        cat = np.concatenate(nopunc) if nopunc else np.zeros(0, np.float32)
+                        segment["confidence"] = W.round_confidence(float(np.exp(cat.mean(dtype=np.float32))))
+                for w in ws:
+                    w["_stream"] = st.index
+                all_words.extend(ws)
+            # stream time shift (independent cuts) is applied after the per-window offsets
+            if st.time_shift:
+                for w in (w for ws in seg_words for w in ws):
+                    w["start"] = W.round_timestamp(w["start"] + st.time_shift)
+                    w["end"] = W.round_timestamp(w["end"] + st.time_shift)
+                for s in st.segments:
+                    s["start"] += st.time_shift
+                    s["end"] += st.time_shift
+                    s["seek"] += int(round(st.time_shift * SAMPLE_RATE / HOP_LENGTH))
+            all_segments.extend(st.segments)              # empty-text segments stay in the output, like the reference
+            text_parts.append(tokenizer.decode(st.all_tokens[st.n_initial_prompt:]))
 
     transcription = dict(text="".join(text_parts), segments=all_segments, language=language)
     if language_probs:
