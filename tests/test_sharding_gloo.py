@@ -17,6 +17,7 @@ ROOT = os.path.dirname(HERE)
 
 AUDIO = (75.0, 11)
 CHUNK = 30.0
+LANGUAGE = None          # detected on the first 30 s of the whole recording by every rank
 
 
 def _model_and_engine():
@@ -45,7 +46,7 @@ def _worker(rank, world, port, out_path):
         from whisper_timestamped.sharding import transcribe_sharded
         from whisper_timestamped.synthetic_audio import synthetic_speech
         audio = synthetic_speech(*AUDIO)
-        res = transcribe_sharded(shim, audio, CHUNK, rank, world, language="en", engine=eng)
+        res = transcribe_sharded(shim, audio, CHUNK, rank, world, language=LANGUAGE, engine=eng)
         if rank == 0:
             with open(out_path, "w") as f:
                 json.dump(res, f)
@@ -93,13 +94,16 @@ def test_two_gloo_ranks_equal_single_process():
     from whisper_timestamped.synthetic_audio import synthetic_speech
     from whisper_timestamped.transcribe import transcribe_timestamped
     audio = synthetic_speech(*AUDIO)
-    whole = transcribe_timestamped(shim, audio, language="en", engine=eng, chunks=CHUNK)
+    whole = transcribe_timestamped(shim, audio, language=LANGUAGE, engine=eng, chunks=CHUNK)
     assert [s["id"] for s in whole["segments"]] == list(range(len(whole["segments"])))
     with tempfile.TemporaryDirectory() as td:
         out = os.path.join(td, "merged.json")
         mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
         merged = json.load(open(out))
-    assert merged["text"] == whole["text"]
+    assert merged["text"] == whole["text"] and merged["language"] == whole["language"]
+    assert set(merged["language_probs"]) == set(whole["language_probs"])
+    for k, v in whole["language_probs"].items():
+        assert abs(merged["language_probs"][k] - v) < 1e-6
     assert len(merged["segments"]) == len(whole["segments"]) > 2
     for a, b in zip(merged["segments"], whole["segments"]):
         assert a["id"] == b["id"] and a["seek"] == b["seek"] and a["tokens"] == b["tokens"] and a["text"] == b["text"]

@@ -83,8 +83,20 @@ def _np_default(o):
 
 def transcribe_sharded(model, audio, chunk_seconds: float, rank: int, world: int, group=None, **kwargs):
     """transcribe() of this rank's cuts + gather.  `audio` is the WHOLE recording (numpy or tensor) on every rank."""
+    from .tokenizer import get_tokenizer
     from .transcribe import transcribe_timestamped
+    language_probs = None
+    if kwargs.get("language") is None and model.is_multilingual:
+        # every rank detects the language on the FIRST 30 s of the whole recording (what the reference does for a file),
+        # not on its own shard: identical on all ranks without a collective
+        eng = kwargs.get("engine") or model.engine()
+        head = eng.load_audio(audio[..., : 30 * SAMPLE_RATE])
+        tok0 = get_tokenizer(True, num_languages=model.num_languages)
+        language, language_probs = eng.detect_language(eng.log_mel(head), tok0)
+        kwargs = dict(kwargs, language=language)
     mine, offset, _ = shard_audio(audio, chunk_seconds, rank, world)
     res = transcribe_timestamped(model, mine, chunks=chunk_seconds, **kwargs)
+    if language_probs:
+        res["language_probs"] = language_probs
     shift_segments(res["segments"], offset)
     return gather_results(res, rank, world, group)
