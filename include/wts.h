@@ -88,6 +88,13 @@ int wts_dtw_batch(const void* d_cost, int32_t cost_is_f64,
                   int32_t* d_jumps, int32_t* d_path, const int64_t* d_path_off,
                   int32_t* d_path_len, int32_t* d_status, void* stream);
 
+/* detect_disfluencies (T.py:1656-1683): for every token t of every segment, d_out[jumps_off + t] = -1, or — when
+ * scipy.signal.find_peaks(-cost[t, jumps[t]:jumps[t+1]], width=3, prominence=0.02) finds more than one peak —
+ * round(left_ips[-1]), the offset (from jumps[t]) at which the token really starts.  d_cost / d_segs / d_jumps are
+ * the buffers of wts_attn_prep_batch / wts_dtw_batch (float32 costs; descriptors in any order). */
+int wts_disfluency_starts(const float* d_cost, const WtsSegDesc* d_segs, int32_t nseg, const int32_t* d_jumps,
+                          int32_t* d_out, void* stream);
+
 
 /* ------------------------------------------------------------------------------------------------
  * Model forward operators (replace the openai-whisper modules the reference drives through

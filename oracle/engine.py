@@ -153,8 +153,8 @@ class OracleEngine:
         return len(self.qk) - 1, vals
 
     # ---- alignment numerics (oracle)
-    def align(self, items):
-        out = []
+    def align(self, items, disfluencies=False):
+        out, lefts = [], []
         for it in items:
             qk = self.qk[it["window"]]
             T, row0, last_row = it["T"], it["row0"], it["last_row"]
@@ -163,4 +163,13 @@ class OracleEngine:
             cost = attn_cost(sel, it["f0"], it["f0"] + it["F"], max_duration=it["max_dur"] or None)
             _, _, jumps, _ = oracle.dtw_symmetric1(cost)
             out.append(jumps)
-        return out
+            if disfluencies:
+                # reference T.py:1656-1670, with scipy itself
+                from scipy.signal import find_peaks
+                w = -np.asarray(cost, dtype=np.float64)
+                left = []
+                for i_token, (begin, end) in enumerate(zip(jumps[:-1], jumps[1:])):
+                    peaks, props = find_peaks(w[i_token, begin:end], width=3, prominence=0.02)
+                    left.append(int(round(props["left_ips"][-1])) if len(peaks) > 1 else -1)
+                lefts.append(np.asarray(left, dtype=np.int32))
+        return (out, lefts) if disfluencies else out

@@ -1,21 +1,15 @@
 import os
 import sys
 
-import pytest
-
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "whisper-timestamped_b200"), os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
 
-def pytest_configure(config):
-    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu)")
-
-
-@pytest.fixture(scope="session", autouse=True)
-def _built():
-    """Make sure libwts.so and the oracle's C restatement exist (nvcc cross-compiles on CPU)."""
+def _build_everything():
+    """libwts.so and the oracle's C restatement must exist (and be current) BEFORE collection: test modules import
+    the package, which loads the library.  nvcc cross-compiles on a CPU-only box; a no-op when nothing changed."""
     import importlib.util
     spec = importlib.util.spec_from_file_location("wts_build", os.path.join(ROOT, "whisper-timestamped_b200", "build.py"))
     mod = importlib.util.module_from_spec(spec)
@@ -23,4 +17,8 @@ def _built():
     mod.build()
     import oracle
     oracle.build()
-    yield
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu)")
+    _build_everything()

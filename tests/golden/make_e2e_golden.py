@@ -59,6 +59,10 @@ CASES = {
     "tiny_naive_opts": ("tiny", {}, (45.0, 23), {"language": "fr", "naive_approach": True, "temperature": 0.0,
                                                  "include_punctuation_in_confidence": True,
                                                  "remove_punctuation_from_words": True, "refine_whisper_precision": 0.2}),
+    # detect_disfluencies: "[*]" pseudo-words from the peak analysis of the attention rows
+    "tiny_disfluencies": ("tiny", {}, (60.0, 12), {"language": "en", "detect_disfluencies": True}),
+    "tiny_disfluencies_naive": ("tiny", {}, (70.0, 19), {"language": "en", "detect_disfluencies": True,
+                                                         "naive_approach": True, "temperature": 0.0}),
     # explicit-list VAD: speech spans glued, times mapped back, `speech_activity` reported
     "tiny_vad_list": ("tiny", {}, (70.0, 19), {"language": "en", "vad": [(2.0, 21.5), (30.25, 52.0), (58.0, 66.4)]}),
 }

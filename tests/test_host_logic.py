@@ -82,6 +82,47 @@ def test_abi_exports_every_declared_symbol():
     assert nat.lib.wts_version() >= 100
 
 
+def test_disfluency_peaks_match_scipy(tmp_path):
+    """csrc/peaks.h (what the CUDA disfluency kernel runs) against scipy.signal.find_peaks(width=3, prominence=0.02)
+    itself: same 'more than one peak' decision and the same round(left_ips[-1]) on random, plateau and tiny inputs."""
+    from scipy.signal import find_peaks
+    src = tmp_path / "pk.c"
+    src.write_text(f'''
+#include "{CSRC}/peaks.h"
+int disfluency_left(const float* row, int begin, int n) {{ return wts_disfluency_left(row, begin, n, 0.02, 3.0); }}
+''')
+    so = tmp_path / "pk.so"
+    subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", str(so), str(src), "-lm"])
+    lib = ctypes.CDLL(str(so))
+    lib.disfluency_left.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    rng = np.random.default_rng(5)
+    n_multi = 0
+    for trial in range(3000):
+        n = int(rng.integers(0, 60))
+        begin = int(rng.integers(0, 5))
+        kind = trial % 4
+        if kind == 0:                       # smooth bumps (what attention rows look like)
+            t = np.arange(n + begin)
+            v = sum(rng.uniform(0.01, 0.3) * np.exp(-((t - rng.uniform(0, n + begin)) / rng.uniform(1.5, 6)) ** 2)
+                    for _ in range(int(rng.integers(1, 4))))
+            v = np.asarray(v, dtype=np.float64) * np.ones(n + begin)
+        elif kind == 1:                     # noise
+            v = rng.uniform(0, 0.2, n + begin)
+        elif kind == 2:                     # quantised: plateaus and exact ties
+            v = np.round(rng.uniform(0, 0.2, n + begin) * 20) / 20
+        else:                               # smooth + noise
+            t = np.arange(n + begin)
+            v = 0.1 * np.sin(t / rng.uniform(1.0, 5.0)) ** 2 + rng.uniform(0, 0.01, n + begin)
+        cost = (-np.asarray(v)).astype(np.float32)          # the kernel reads float32 costs and negates them
+        x = -cost[begin:begin + n].astype(np.float64)
+        peaks, props = find_peaks(x, width=3, prominence=0.02)
+        want = int(round(props["left_ips"][-1])) if len(peaks) > 1 else -1
+        n_multi += len(peaks) > 1
+        got = lib.disfluency_left(cost.ctypes.data, begin, n)
+        assert got == want, (trial, n, begin, got, want, x.tolist())
+    assert n_multi > 100          # the interesting branch was exercised
+
+
 def test_struct_layouts_match_the_header(tmp_path):
     """The ctypes mirrors (whisper_timestamped/_native.py) must have the size and field offsets gcc gives the structs
     of include/wts.h — this is the C-ABI boundary the reference-side binding relies on."""

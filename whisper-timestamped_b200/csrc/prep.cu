@@ -20,6 +20,7 @@
 // padding mask, running minimum; finally cost[0,0] = min.  Reads the [T,F] mean twice (L2-hot).
 #include "common.cuh"
 #include "median9.h"
+#include "peaks.h"
 
 namespace wts {
 
@@ -118,9 +119,39 @@ prep_cols_kernel(const WtsSegDesc* __restrict__ segs, float* __restrict__ cost)
     }
 }
 
+// detect_disfluencies (T.py:1656-1683): for every token row of every segment, the peak analysis of the (negated) cost
+// row between the token's two DTW jumps (peaks.h = scipy.signal.find_peaks(width=3, prominence=0.02) restated).
+// One thread per (segment, token): the slices are a few dozen frames, the analysis is a handful of short scans.
+__global__ void disfluency_kernel(const float* __restrict__ cost, const WtsSegDesc* __restrict__ segs,
+                                  const int32_t* __restrict__ jumps, int32_t* __restrict__ out)
+{
+    const WtsSegDesc sd = segs[blockIdx.x];
+    const int32_t* j = jumps + sd.jumps_off;
+    int32_t* o = out + sd.jumps_off;
+    for (int t = threadIdx.x; t <= sd.T; t += blockDim.x) {
+        int left = -1;
+        if (t < sd.T) {
+            const int begin = j[t], end = j[t + 1];
+            if (end - begin >= 3 && begin >= 0 && end <= sd.F)
+                left = wts_disfluency_left(cost + sd.cost_off + (int64_t)t * sd.F, begin, end - begin, 0.02, 3.0);
+        }
+        o[t] = left;
+    }
+}
+
 }  // namespace wts
 
 using namespace wts;
+
+extern "C" int wts_disfluency_starts(const float* d_cost, const WtsSegDesc* d_segs, int32_t nseg, const int32_t* d_jumps,
+                                     int32_t* d_out, void* stream)
+{
+    if (nseg <= 0) return 0;
+    if (!d_cost || !d_segs || !d_jumps || !d_out) { set_error("wts_disfluency_starts: null pointer"); return -2; }
+    disfluency_kernel<<<nseg, 64, 0, (cudaStream_t)stream>>>(d_cost, d_segs, d_jumps, d_out);
+    WTS_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int wts_attn_prep_batch(const float* d_qk, int32_t N, int32_t Tmax, int32_t Fmax,
                                    const WtsSegDesc* d_segs, int32_t nseg, int32_t max_T,

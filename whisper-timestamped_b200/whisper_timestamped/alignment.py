@@ -128,6 +128,20 @@ def dtw(cost: torch.Tensor, plan: AlignPlan, want_path=False, want_status=False,
     return out
 
 
+def disfluency_starts(cost: torch.Tensor, plan: AlignPlan, jumps: torch.Tensor, d_segs: torch.Tensor = None) -> torch.Tensor:
+    """Per token: -1, or the offset from its jump at which the token really starts (detect_disfluencies,
+    T.py:1656-1683).  Same layout as `jumps` (T+1 ints per segment, the last one unused)."""
+    nat.require_cuda(cost, "cost")
+    assert cost.dtype == torch.float32 and jumps.dtype == torch.int32
+    if d_segs is None:
+        d_segs = _segs_to_device(plan.segs, cost.device)
+    out = torch.empty_like(jumps)
+    rc = nat.lib.wts_disfluency_starts(nat.ptr(cost), nat.ptr(d_segs), plan.nseg, nat.ptr(jumps), nat.ptr(out),
+                                       nat.stream_ptr(cost.device))
+    nat.check(rc, "wts_disfluency_starts")
+    return out
+
+
 def split_jumps(jumps_host: np.ndarray, plan: AlignPlan):
     """Per-segment views of a host copy of the jumps buffer."""
     return [jumps_host[s["jumps_off"]: s["jumps_off"] + s["T"] + 1] for s in plan.segs]

@@ -629,9 +629,11 @@ class CudaEngine:
         return max(language_probs, key=language_probs.get), language_probs
 
     # ------------------------------------------------------------------ alignment
-    def align(self, items):
-        """items: dicts(window=global window id, row0, last_row, T, f0, F, max_dur) -> list of jumps arrays."""
+    def align(self, items, disfluencies=False):
+        """items: dicts(window=global window id, row0, last_row, T, f0, F, max_dur) -> list of jumps arrays; with
+        disfluencies=True a second list: per token -1 or the start offset found by the peak analysis (T.py:1656-1683)."""
         out = [None] * len(items)
+        lefts = [None] * len(items)
         groups = {}
         for i, it in enumerate(items):
             buf, b = self.window_index[it["window"]]
@@ -648,7 +650,13 @@ class CudaEngine:
             self.launches += 3
             for (i, _, _), j in zip(lst, jumps):
                 out[i] = j
-        return out
+            if disfluencies:
+                from .alignment import disfluency_starts
+                dl = split_jumps(disfluency_starts(cost, plan, res["jumps"]).cpu().numpy(), plan)
+                self.launches += 1
+                for (i, _, _), l_ in zip(lst, dl):
+                    lefts[i] = l_[:-1]
+        return (out, lefts) if disfluencies else out
 
     def release(self):
         self.qk_buffers.clear()

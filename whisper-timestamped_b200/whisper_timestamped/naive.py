@@ -66,7 +66,7 @@ def _listed_words(req):
 
 def second_pass(eng, audio, whisper_segments, tokenizer, language, *, use_space, refine_nframes, trust_whisper_timestamps,
                 remove_punctuation_from_words, compute_word_confidence, include_punctuation_in_confidence,
-                min_word_duration=0.0):
+                min_word_duration=0.0, detect_disfluencies=False):
     """Adds `confidence` (and possibly corrected `tokens` / `text`) to the segments in place; returns the word list
     (each word carries `idx_segment`)."""
     tok = tokenizer
@@ -161,14 +161,22 @@ def second_pass(eng, audio, whisper_segments, tokenizer, language, *, use_space,
                 pairs.extend(sel)
                 step += len(pieces)
             window, lp = eng.teacher_forced(mel, tokens_in, i_start, pairs if compute_word_confidence else [])
-            jumps = eng.align([dict(window=window, row0=0, last_row=req.row_offset_last, T=req.T, f0=req.f0, F=req.F,
-                                    max_dur=max_duration or 0)])[0]
-            ws = W.words_from_jumps(req, jumps)
-            assert len(ws) == len(listed)
+            item = dict(window=window, row0=0, last_row=req.row_offset_last, T=req.T, f0=req.f0, F=req.F,
+                        max_dur=max_duration or 0)
+            if detect_disfluencies:
+                jl, ll = eng.align([item], disfluencies=True)
+                ws = W.words_from_jumps(req, jl[0], ll[0], tokenizer=tok)
+            else:
+                ws = W.words_from_jumps(req, eng.align([item])[0])
+            assert sum(1 for w_ in ws if w_["text"] != W.DISFLUENCY_MARK or w_["tokens"]) == len(listed)
 
         segment_logprobs = []
         i_token = 1
-        for k, word in enumerate(ws):
+        k = -1                                        # index among the words that carry tokens ("[*]" marks have none)
+        for word in ws:
+            is_mark = word["text"] == W.DISFLUENCY_MARK and not word["tokens"]
+            if not is_mark:
+                k += 1
             word["start"] = round(word["start"] + start, 2)
             word["end"] = round(word["end"] + start, 2)
             if trust_whisper_timestamps:
@@ -182,7 +190,7 @@ def second_pass(eng, audio, whisper_segments, tokenizer, language, *, use_space,
                     i_token += 1
             check.extend(word["tokens_indices"])
             if compute_word_confidence:
-                a, n = per_word[k]
+                a, n = (0, 0) if is_mark else per_word[k]
                 wl = np.asarray(lp[a:a + n], dtype=np.float32)
                 if n:
                     segment_logprobs.append(wl)

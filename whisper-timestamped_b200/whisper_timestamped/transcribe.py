@@ -164,8 +164,6 @@ def transcribe_timestamped(
             "row A15) runs with greedy decoding and a scalar temperature of 0")
     if not trust_whisper_timestamps and not naive_approach:
         raise NotImplementedError("trust_whisper_timestamps=False is only built for the two-pass strategy (naive_approach=True)")
-    if detect_disfluencies:
-        raise NotImplementedError("detect_disfluencies is a 'next' row (SURVEY.md §8f) and not built yet")
     if plot_word_alignment:
         raise NotImplementedError("plot_word_alignment is out of scope of the hot path")
     vad = V.check_vad_method(vad)          # explicit (start, end) lists only; detector names raise NotImplementedError
@@ -240,7 +238,7 @@ def transcribe_timestamped(
                                    remove_punctuation_from_words=remove_punctuation_from_words,
                                    compute_word_confidence=compute_word_confidence,
                                    include_punctuation_in_confidence=include_punctuation_in_confidence,
-                                   min_word_duration=0.0)
+                                   min_word_duration=0.0, detect_disfluencies=detect_disfluencies)
         for w in all_words:
             w["_stream"] = 0
         text_parts = [tokenizer.decode(st.all_tokens[st.n_initial_prompt:])]
@@ -285,8 +283,12 @@ def transcribe_timestamped(
             rec = st.records[wi]
             items.append(dict(window=rec.qk_window, row0=plan.row0, last_row=plan.row0 + req.row_offset_last,
                               T=req.T, f0=req.f0, F=req.F, max_dur=rec.max_duration or 0))
-        jumps_list = eng.align(items) if items else []
-        jit = iter(jumps_list)
+        lefts_list = None
+        if items and detect_disfluencies:
+            jumps_list, lefts_list = eng.align(items, disfluencies=True)
+        else:
+            jumps_list = eng.align(items) if items else []
+        jit = iter(zip(jumps_list, lefts_list if lefts_list is not None else [None] * len(jumps_list)))
 
         # ---- per stream: words, confidences, compile (T.py:712-771, 912-1002)
         all_segments, all_words = [], []
@@ -304,7 +306,7 @@ def transcribe_timestamped(
                 plans, info = per_window[(st.index, wi)]
                 ws_of_window, kept_plans = [], []
                 for (_, _, plan, req) in by_window.get(wi, []):
-                    ws = W.words_from_jumps(req, next(jit)) if req is not None else []
+                    ws = W.words_from_jumps(req, *next(jit), tokenizer=tokenizer) if req is not None else []
                     assert ws, "plan_window_alignment only keeps segments that yield words"
                     ws_of_window.append(ws)
                     kept_plans.append(plan)

@@ -174,16 +174,50 @@ def prepare_alignment(tokens, n_rows, tokenizer, use_space=True, refine_nframes=
                         warnings=warnings)
 
 
-def words_from_jumps(req: AlignRequest, jumps) -> List[dict]:
+DISFLUENCY_MARK = "[*]"
+
+
+def words_from_jumps(req: AlignRequest, jumps, lefts=None, tokenizer=None) -> List[dict]:
     """jumps: T+1 frame indices (first frame of every token row on the DTW path, then the last frame).
     Word begin = jump of its first token, end = jump after its last non-punctuation token
-    (T.py:1711-1717); the leading/trailing timestamp pseudo-words are dropped (T.py:1739-1754)."""
+    (T.py:1711-1717); the leading/trailing timestamp pseudo-words are dropped (T.py:1739-1754).
+
+    lefts (detect_disfluencies, T.py:1654-1736): per token -1, or the offset from its jump at which the peak analysis
+    of its attention row says the token really starts; what lies before becomes a "[*]" pseudo-word (no tokens)."""
     jumps = np.asarray(jumps)
     assert len(jumps) == req.T + 1
+    jumps_start = jumps
+    disfluencies = {}
+    if lefts is not None:
+        jumps_start = jumps.copy()
+        for i_token, (tok, begin, end) in enumerate(zip(req.tokens, jumps[:-1], jumps[1:])):
+            if lefts[i_token] < 0:
+                continue
+            new_begin = int(lefts[i_token]) + int(begin)
+            jumps_start[i_token] = new_begin
+            if new_begin != begin:
+                if tokenizer.decode_with_timestamps([tok]) not in PUNCTUATION:
+                    disfluencies[i_token] = (int(begin), new_begin)
+                else:
+                    disfluencies[i_token + 1] = (int(begin), int(end))
     bounds = np.concatenate([[0], np.cumsum([len(p) for p in req.word_pieces])])
-    begin = jumps[bounds[:-1]] * TIME_PER_FRAME
+    begin = jumps_start[bounds[:-1]] * TIME_PER_FRAME
     end = jumps[bounds[1:] - np.asarray(req.punct_at_end, dtype=np.int64)] * TIME_PER_FRAME
     words, pieces, ids = list(req.words), list(req.word_pieces), list(req.word_ids)
+    if lefts is not None:
+        inserts = []
+        first = 0
+        for i_word, toks in enumerate(pieces[:-1]):
+            if first in disfluencies and i_word > 0:
+                b, e = disfluencies[first]
+                inserts.append((i_word, b * TIME_PER_FRAME, e * TIME_PER_FRAME))
+            first += len(toks)
+        for (i_word, b, e) in reversed(inserts):        # from the end, so the indices stay valid
+            words.insert(i_word, DISFLUENCY_MARK)
+            pieces.insert(i_word, [])
+            ids.insert(i_word, [])
+            begin = np.insert(begin, i_word, b)
+            end = np.insert(end, i_word, e)
     if not req.refine_nframes:
         begin[1] = begin[0]
         end[-2] = end[-1]
