@@ -197,8 +197,10 @@ class Tokenizer:
     def non_speech_tokens(self) -> Tuple[int]:
         """Upstream: ids of symbol strings that are not speech.  Synthetic vocabulary: the byte
         tokens of the ASCII symbols upstream lists (single characters only)."""
-        symbols = list('"#()*+/:;<=>@[\\]^_`{|}~')
-        return tuple(sorted({self.encoding.encode(s)[0] for s in symbols}))
+        symbols = list('"#()*+/:;<=>@[\\]^_`{|}~\u300c\u300d\u300e\u300f')
+        # upstream keeps a symbol only when it is ONE token: the CJK corner brackets are, in multilingual.tiktoken;
+        # in the byte-level synthetic vocabulary they are three bytes each and drop out
+        return tuple(sorted({self.encoding.encode(s)[0] for s in symbols if len(self.encoding.encode(s)) == 1}))
 
 
 @lru_cache(maxsize=None)

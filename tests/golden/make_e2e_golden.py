@@ -10,6 +10,7 @@ model = synthetic_state_dict(DIMS[name], seed), audio = synthetic_speech(duratio
 """
 import importlib.util
 import json
+import logging
 import os
 import sys
 import time
@@ -39,6 +40,8 @@ PKG = os.path.join(ROOT, "whisper-timestamped_b200", "whisper_timestamped")
 zoo = _load(os.path.join(PKG, "model_zoo.py"), "wts_model_zoo")
 sa = _load(os.path.join(PKG, "synthetic_audio.py"), "wts_synthetic_audio")
 
+BENCH_KW = {"ts_offset": 4.5, "eot_logit": 14.5}        # == bench.py SYNTH_KW
+
 CASES = {
     # name: (model, model kwargs, audio (duration, seed), transcribe kwargs)
     "tiny_en_30s": ("tiny.en", {}, (30.0, 7), {}),
@@ -65,6 +68,20 @@ CASES = {
                                                          "naive_approach": True, "temperature": 0.0}),
     # explicit-list VAD: speech spans glued, times mapped back, `speech_activity` reported
     "tiny_vad_list": ("tiny", {}, (70.0, 19), {"language": "en", "vad": [(2.0, 21.5), (30.25, 52.0), (58.0, 66.4)]}),
+    # ---- the configurations bench.py measures (BASELINE.json configs 2-4), at their real dimensions
+    # large-v3 with the bench recipe, sequential (two windows: the second-round / prompt carry-over path)
+    "large_v3_45s": ("large-v3", BENCH_KW, (45.0, 31), {"language": "en"}),
+    "base_60s": ("base", {}, (60.0, 32), {"language": "en"}),
+    "medium_30s": ("medium", {}, (30.0, 33), {"language": "en"}),
+}
+
+# `chunks=` mode (the data-parallel unit of work): the reference run INDEPENDENTLY on every fixed cut
+# with condition_on_previous_text=False; the product's transcribe(..., chunks=) must equal the stitched per-cut results.
+# name: (model, model kwargs, audio (duration, seed), chunk seconds, transcribe kwargs)
+CHUNK_CASES = {
+    "chunks_tiny_100s": ("tiny", {}, (100.0, 41), 30.0, {"language": "en"}),
+    # the first 5 minutes of bench.py's 1-h workload (make_audio: 300-s pieces, seed 1234 + k), large-v3, bench recipe
+    "chunks_large_v3_bench300": ("large-v3", BENCH_KW, (300.0, 1234), 30.0, {"language": "en"}),
 }
 
 
@@ -92,24 +109,75 @@ def to_py(o):
     return o
 
 
+class _Capture(logging.Handler):
+    """Warnings the reference logs while it runs: part of the pinned behaviour (e.g. "Got inconsistent length for
+    segment ... Some words have been ignored" on the too-much-text truncation path, T.py:1516-1535 / 993-994)."""
+
+    def __init__(self):
+        super().__init__(level=logging.WARNING)
+        self.messages = []
+
+    def emit(self, record):
+        self.messages.append(record.getMessage())
+
+
+def run_reference(model, audio, **kw):
+    cap = _Capture()
+    lg = logging.getLogger("whisper_timestamped")
+    lg.addHandler(cap)
+    try:
+        res = ref.transcribe(model, audio, **kw)
+    finally:
+        lg.removeHandler(cap)
+    return to_py(res), cap.messages
+
+
 def main():
-    names = sys.argv[1:] or list(CASES)
+    names = sys.argv[1:] or (list(CASES) + list(CHUNK_CASES))
+    models = {}
+
+    def get_model(mname, mkw):
+        key = (mname, json.dumps(mkw, sort_keys=True))
+        if key not in models:
+            models.clear()                       # one big model in memory at a time
+            models[key] = build_model(mname, **mkw)
+        return models[key]
+
     for case in names:
+        if case in CHUNK_CASES:
+            mname, mkw, (dur, aseed), chunk_s, tkw = CHUNK_CASES[case]
+            model = get_model(mname, mkw)
+            audio = sa.synthetic_speech(dur, seed=aseed)
+            step = int(round(chunk_s * 16000))
+            t0 = time.time()
+            cuts = []
+            for s in range(0, len(audio), step):
+                res, warns = run_reference(model, audio[s:s + step], condition_on_previous_text=False, **tkw)
+                cuts.append({"offset": s / 16000.0, "result": res, "warnings": warns})
+                print(f"  {case} cut @{s / 16000.0:.0f}s: {len(res['segments'])} segments, {len(warns)} warnings, "
+                      f"{time.time() - t0:.0f}s", flush=True)
+            dt = time.time() - t0
+            out = {"case": case, "model": mname, "model_seed": 1234, "model_kwargs": mkw, "audio": [dur, aseed],
+                   "chunks": chunk_s, "transcribe_kwargs": tkw, "reference_version": ref.__version__,
+                   "cpu_seconds": round(dt, 2), "cuts": cuts}
+            with open(os.path.join(HERE, f"{case}.json"), "w") as f:
+                json.dump(out, f, indent=1, ensure_ascii=False)
+            continue
         mname, mkw, (dur, aseed), tkw = CASES[case]
-        model = build_model(mname, **mkw)
+        model = get_model(mname, mkw)
         audio = sa.synthetic_speech(dur, seed=aseed)
         t0 = time.time()
-        res = ref.transcribe(model, audio, **tkw)
+        res, warns = run_reference(model, audio, **tkw)
         dt = time.time() - t0
         out = {"case": case, "model": mname, "model_seed": 1234, "model_kwargs": mkw, "audio": [dur, aseed],
                "transcribe_kwargs": tkw, "reference_version": ref.__version__, "cpu_seconds": round(dt, 2),
-               "result": to_py(res)}
+               "warnings": warns, "result": res}
         with open(os.path.join(HERE, f"e2e_{case}.json"), "w") as f:
             json.dump(out, f, indent=1, ensure_ascii=False)
         nseg = len(res["segments"])
         nw = sum(len(s.get("words", [])) for s in res["segments"])
         ntok = sum(len(s["tokens"]) for s in res["segments"])
-        print(f"{case}: {nseg} segments, {nw} words, {ntok} tokens, {dt:.1f}s")
+        print(f"{case}: {nseg} segments, {nw} words, {ntok} tokens, {len(warns)} warnings, {dt:.1f}s", flush=True)
 
 
 if __name__ == "__main__":

@@ -5,6 +5,7 @@ and checks that the offline replay of the reference's hook state machine gives t
 segments, words, timestamps and confidences."""
 import glob
 import json
+import logging
 import os
 from types import SimpleNamespace
 
@@ -17,6 +18,38 @@ from whisper_timestamped.transcribe import transcribe_timestamped
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CASES = sorted(glob.glob(os.path.join(HERE, "golden", "e2e_*.json")))
+CHUNK_CASES = sorted(glob.glob(os.path.join(HERE, "golden", "chunks_*.json")))
+# goldens at medium / large-v3 dimensions take minutes per window through the fp32 CPU stand-in: they are GPU tests
+# (tests/test_gpu_model.py); on the CPU box they only run with WTS_SLOW=1
+BIG = ("medium", "large")
+
+
+def _is_big(path):
+    return any(b in os.path.basename(path) for b in BIG) and os.environ.get("WTS_SLOW") != "1"
+
+
+class CaptureWarnings(logging.Handler):
+    """Collects what the product logs on logger "whisper_timestamped" (the goldens hold the reference's)."""
+
+    def __init__(self):
+        super().__init__(level=logging.WARNING)
+        self.messages = []
+
+    def emit(self, record):
+        self.messages.append(record.getMessage())
+
+    def __enter__(self):
+        logging.getLogger("whisper_timestamped").addHandler(self)
+        return self
+
+    def __exit__(self, *exc):
+        logging.getLogger("whisper_timestamped").removeHandler(self)
+
+
+def norm_warnings(msgs):
+    """First line only (the reference appends decoded text that depends on nothing else), as a sorted multiset:
+    the product replays the state machine offline, so the ORDER of messages differs, not their content."""
+    return sorted(m.split("\n")[0].strip() for m in msgs)
 
 
 def run_case(path, **extra):
@@ -29,8 +62,33 @@ def run_case(path, **extra):
     eng = OracleEngine(om, heads)
     shim = SimpleNamespace(dims=dims, is_multilingual=om.is_multilingual, num_languages=om.num_languages)
     audio = synthetic_speech(*g["audio"])
-    res = transcribe_timestamped(shim, audio, engine=eng, **g["transcribe_kwargs"], **extra)
+    if "chunks" in g:
+        extra = dict(extra, chunks=g["chunks"])
+    with CaptureWarnings() as cap:
+        res = transcribe_timestamped(shim, audio, engine=eng, **g["transcribe_kwargs"], **extra)
+    res["_warnings"] = cap.messages
     return g, res
+
+
+def stitch_cuts(g):
+    """What `chunks=` must reproduce: the reference's result on every cut, shifted by the cut's offset (the same
+    arithmetic as `offset = seek * HOP / SR`, T.py:959-962) and concatenated; ids renumbered over the recording."""
+    segs, text, warns = [], [], []
+    for cut in g["cuts"]:
+        off = cut["offset"]
+        for s in cut["result"]["segments"]:
+            s = json.loads(json.dumps(s))
+            s["start"] = round(s["start"] + off, 2)
+            s["end"] = round(s["end"] + off, 2)
+            s["seek"] = s["seek"] + int(round(off * 100))
+            for w in s.get("words", []):
+                w["start"] = round(w["start"] + off, 2)
+                w["end"] = round(w["end"] + off, 2)
+            s["id"] = len(segs)
+            segs.append(s)
+        text.append(cut["result"]["text"])
+        warns.extend(cut["warnings"])
+    return {"text": "".join(text), "segments": segs, "language": g["cuts"][0]["result"]["language"]}, warns
 
 
 def compare(res, ref, conf_tol=0.0015, time_tol=0.0, prob_tol=1e-5):
@@ -63,8 +121,24 @@ def compare(res, ref, conf_tol=0.0015, time_tol=0.0, prob_tol=1e-5):
 
 @pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[4:-5] for p in CASES])
 def test_host_logic_matches_reference_golden(path):
+    if _is_big(path):
+        pytest.skip("large model: GPU test (WTS_SLOW=1 runs it through the CPU stand-in)")
     g, res = run_case(path)
     compare(res, g["result"])
+    if "warnings" in g:
+        assert norm_warnings(res["_warnings"]) == norm_warnings(g["warnings"])
+
+
+@pytest.mark.parametrize("path", CHUNK_CASES, ids=[os.path.basename(p)[:-5] for p in CHUNK_CASES])
+def test_chunks_mode_equals_reference_on_every_cut(path):
+    """transcribe(..., chunks=30) == the unmodified reference run independently on every 30-s cut
+    (condition_on_previous_text=False), after the offset shift — SURVEY.md §8(e)'s definition of the sharded unit."""
+    if _is_big(path):
+        pytest.skip("large model: GPU test (WTS_SLOW=1 runs it through the CPU stand-in)")
+    g, res = run_case(path)
+    ref, warns = stitch_cuts(g)
+    compare(res, ref, time_tol=1e-6)
+    assert norm_warnings(res["_warnings"]) == norm_warnings(warns)
 
 
 def test_vad_convert_timestamps_hand_cases():

@@ -45,6 +45,9 @@ TO_LANGUAGE_CODE.update({
 
 _PUNCT = (".", ",", "?", "!", "...", ":")
 _NON_SPEECH_SYMBOLS = '"#()*+/:;<=>@[\\]^_`{|}~'
+# upstream's list continues with the CJK corner brackets; they are single tokens in multilingual.tiktoken (never in
+# the byte-level synthetic vocabulary, whose suppress set therefore stays the ASCII one)
+_NON_SPEECH_SYMBOLS_CJK = "\u300c\u300d\u300e\u300f"
 
 
 def synthetic_piece(i: int) -> bytes:
@@ -156,7 +159,7 @@ class Tokenizer:
         if self.vocab.kind == "synthetic-v1":
             return tuple(sorted({ord(c) for c in _NON_SPEECH_SYMBOLS}))
         # upstream: symbols whose (single-token) encodings are suppressed
-        symbols = list(_NON_SPEECH_SYMBOLS) + "<< >> <<< >>> -- --- -( -[ (' (\" (( )) ((( ))) [[ ]] {{ }} ♪♪ ♪♪♪".split()
+        symbols = list(_NON_SPEECH_SYMBOLS + _NON_SPEECH_SYMBOLS_CJK) + "<< >> <<< >>> -- --- -( -[ (' (\" (( )) ((( ))) [[ ]] {{ }} ♪♪ ♪♪♪".split()
         miscellaneous = set("♩♪♫♬♭♮♯")
         result = {self.vocab.encode(" -")[0], self.vocab.encode(" '")[0]}
         for symbol in symbols + list(miscellaneous):
