@@ -231,8 +231,23 @@ def _dist_setup():
     return rank, world, local
 
 
+def _pkg_module(name):
+    """A pure-python module of the product package loaded BY FILE PATH (model_zoo, synthetic_audio): the reference arm
+    needs the synthetic recipe but must never import the product package (that would load libwts.so)."""
+    import importlib.util
+    key = "wts_bench_" + name
+    if key in sys.modules:
+        return sys.modules[key]
+    path = os.path.join(ROOT, "whisper-timestamped_b200", "whisper_timestamped", name + ".py")
+    spec = importlib.util.spec_from_file_location(key, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[key] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def make_audio(seconds, seed=1234):
-    from whisper_timestamped.synthetic_audio import synthetic_speech
+    synthetic_speech = _pkg_module("synthetic_audio").synthetic_speech
     # built in 5-minute pieces so the generator stays cheap; deterministic for every rank
     pieces = []
     t, k = 0.0, 0
@@ -356,7 +371,8 @@ def run_e2e(args, rank, world, local):
            "e2e_value": total_audio / (e2e_ms / args.steps * 1e-3), "stages_ms_per_step": {k: v / args.steps for k, v in stages.items()},
            "clocks": clocks, "launches": launches, "segments": len(res["segments"]), "tokens": ntok, "words": nw,
            "h2d": int(mine.nbytes), "d2h": int(len(json.dumps(res["segments"]))) if rank == 0 else 0, "wall_s": wall,
-           "decode_steps": getattr(eng, "decode_steps_run", 0)}
+           "decode_steps": getattr(eng, "decode_steps_run", 0), "small_batch_steps": eng.small_batch_steps,
+           "result": res if rank == 0 else None}
     if rank == 0 and not args.no_roofline:
         peaks = measured_peaks()
         out["roofline"] = gemm_roofline(eng, peaks)
@@ -400,50 +416,114 @@ def _load_reference():
     return mod
 
 
-def cpu_baseline_e2e(args, seconds=None):
-    """The reference's CPU path (float32, batch 1, sequential windows, per-token hooks) on a bounded sample of the
-    same workload, all host cores.  kind "reference": the unmodified reference from baseline/_ref running over the
-    oracle stand-ins for openai-whisper / dtw-python; kind "port": the oracle engine behind the drop-in's
-    transcribe() when baseline/_ref is absent."""
+def build_reference_model(model_name):
+    """The oracle's stand-in for openai-whisper (oracle/upstream/whisper) carrying the same synthetic weights and the
+    reference's alignment heads — what the unmodified reference is handed as `model`.  Touches nothing of the product."""
     import torch
-    from types import SimpleNamespace
-    from oracle.engine import OracleEngine, build_oracle_model
-    from whisper_timestamped import model_zoo as zoo
-    seconds = seconds or args.cpu_seconds
+    up = os.path.join(ROOT, "oracle", "upstream")
+    if up not in sys.path:
+        sys.path.insert(0, up)
+    import whisper                                        # oracle stand-in
+    zoo = _pkg_module("model_zoo")
+    dims = zoo.DIMS[model_name]
+    sd = zoo.synthetic_state_dict(dims, seed=1234, **SYNTH_KW)
+    model = whisper.Whisper(whisper.ModelDimensions(**dims.asdict()))
+    model.load_state_dict(sd)
+    del sd
+    mask = torch.zeros(dims.n_text_layer, dims.n_text_head, dtype=torch.bool)
+    for l, h in zoo.ALIGNMENT_HEADS[model_name]:
+        mask[l, h] = True
+    model.register_buffer("alignment_heads", mask.to_sparse(), persistent=False)
+    return model.eval()
+
+
+def reference_chunks(args, timed, warm):
+    """Runs the reference's CPU path (float32, batch 1, sequential windows, per-token hooks) on 30-s chunks of the SAME
+    synthetic audio, all usable host cores: `warm` chunk indices untimed, then `timed` chunk indices timed one by one.
+    kind "reference": the unmodified reference from baseline/_ref over the oracle stand-ins for openai-whisper and
+    dtw-python (neither can be installed in this image); kind "port": baseline/_ref missing -> the oracle engine behind
+    the drop-in's host logic.  Returns (kind, cores, per-chunk seconds, per-chunk results)."""
+    import torch
     cores = usable_cores()
     torch.set_num_threads(cores)
     try:
         torch.set_num_interop_threads(1)
     except RuntimeError:
         pass
-    dims = zoo.DIMS[args.model]
-    sd = zoo.synthetic_state_dict(dims, seed=1234, **SYNTH_KW)
-    heads = zoo.ALIGNMENT_HEADS[args.model]
-    om = build_oracle_model(dims, sd, heads)
-    del sd
-    audio = make_audio(seconds)
     step = int(args.chunk_seconds * 16000)
+    need = max(list(timed) + list(warm)) + 1
+    audio = make_audio(min(args.audio_seconds, need * args.chunk_seconds))
     ref = _load_reference()
-    t0 = time.perf_counter()
-    ntok = 0
     if ref is not None:
         kind = "reference"
-        for s in range(0, len(audio), step):
-            r = ref.transcribe(om, audio[s:s + step], language="en", condition_on_previous_text=False)
-            ntok += sum(len(x["tokens"]) for x in r["segments"])
+        model = build_reference_model(args.model)
+
+        def run(piece):
+            return ref.transcribe(model, piece, language="en", condition_on_previous_text=False)
     else:
         kind = "port"
+        from types import SimpleNamespace
+        from oracle.engine import OracleEngine, build_oracle_model
+        from whisper_timestamped import model_zoo as zoo
         from whisper_timestamped.transcribe import transcribe_timestamped
-        eng = OracleEngine(om, heads)
+        dims = zoo.DIMS[args.model]
+        heads = zoo.ALIGNMENT_HEADS[args.model]
+        om = build_oracle_model(dims, zoo.synthetic_state_dict(dims, seed=1234, **SYNTH_KW), heads)
         shim = SimpleNamespace(dims=dims, is_multilingual=om.is_multilingual, num_languages=om.num_languages)
-        r = transcribe_timestamped(shim, audio, language="en", chunks=args.chunk_seconds, engine=eng)
-        ntok = sum(len(x["tokens"]) for x in r["segments"])
-    dt = time.perf_counter() - t0
+
+        def run(piece):
+            return transcribe_timestamped(shim, piece, language="en", condition_on_previous_text=False,
+                                          engine=OracleEngine(om, heads))
+    for c in warm:
+        run(audio[c * step:(c + 1) * step])
+    secs, results = [], []
+    for c in timed:
+        t0 = time.perf_counter()
+        results.append(run(audio[c * step:(c + 1) * step]))
+        secs.append(time.perf_counter() - t0)
+    return kind, cores, secs, results
+
+
+def cpu_baseline_e2e(args, timed=None, warm=None):
+    n_chunks = max(1, int(args.audio_seconds // args.chunk_seconds))
+    if timed is None:
+        n = max(1, min(n_chunks, int(round(args.cpu_seconds / args.chunk_seconds))))
+        timed = list(range(n))
+        warm = [min(n, n_chunks - 1)]                    # one untimed chunk first: thread pools, allocator, lazy imports
+    kind, cores, secs, results = reference_chunks(args, timed, warm)
+    dt = float(sum(secs))
+    ntok = sum(len(x["tokens"]) for r in results for x in r["segments"])
     how = ("unmodified reference (baseline/_ref) over the oracle stand-ins for openai-whisper/dtw-python" if kind == "reference"
            else "oracle engine (stand-in for openai-whisper + scipy/torch/oracle-DTW alignment)")
-    return {"value": seconds / dt, "unit": "audio-sec/s", "cores": cores, "kind": kind, "wall_s": dt,
-            "sample": f"first {seconds:.0f} s of the same synthetic audio in {args.chunk_seconds:.0f}-s chunks, {args.model} "
-                      f"float32 on CPU, {how}; {dt:.1f} s wall, {ntok} tokens"}
+    return {"value": len(timed) * args.chunk_seconds / dt, "unit": "audio-sec/s", "cores": cores, "kind": kind, "wall_s": dt,
+            "chunk_seconds_each": [round(x, 2) for x in secs],
+            "sample": f"{len(timed)} x {args.chunk_seconds:.0f}-s chunks (indices {timed[0]}..{timed[-1]}) of the same synthetic audio after "
+                      f"{len(warm)} untimed warm-up chunk(s), {args.model} float32 on CPU, {how}; {dt:.1f} s, {ntok} tokens",
+            "_results": results, "_timed": list(timed)}
+
+
+def parity_vs_reference(ours, ref_results, timed, chunk_seconds):
+    """Our stitched result against the reference's own output on the same chunks (run on this box a moment ago)."""
+    eq_tokens, eq_words, max_dt, max_dc, n_seg, n_words = True, True, 0.0, 0.0, 0, 0
+    for c, r in zip(timed, ref_results):
+        lo, hi = int(c * chunk_seconds * 100), int((c + 1) * chunk_seconds * 100)
+        mine = [s for s in ours["segments"] if lo <= s["seek"] < hi]
+        theirs = r["segments"]
+        n_seg += len(theirs)
+        if [s["tokens"] for s in mine] != [s["tokens"] for s in theirs]:
+            eq_tokens = False
+            continue
+        for a, b in zip(mine, theirs):
+            wa, wb = a.get("words", []), b.get("words", [])
+            if [w["text"] for w in wa] != [w["text"] for w in wb]:
+                eq_words = False
+                continue
+            for x, y in zip(wa, wb):
+                n_words += 1
+                max_dt = max(max_dt, abs(x["start"] - (y["start"] + c * chunk_seconds)), abs(x["end"] - (y["end"] + c * chunk_seconds)))
+                max_dc = max(max_dc, abs(x["confidence"] - y["confidence"]))
+    return {"chunks": len(timed), "segments": n_seg, "words": n_words, "tokens_equal": eq_tokens, "word_texts_equal": eq_words,
+            "max_word_dt": round(max_dt, 6), "max_confidence_diff": round(max_dc, 6)}
 
 
 def main():
@@ -469,19 +549,36 @@ def main():
 
     workload_name = (f"{args.model}, {args.audio_seconds:.0f} s synthetic 16 kHz audio in independent "
                      f"{args.chunk_seconds:.0f}-s chunks, greedy, word timestamps + confidences")
+    metric_name = "audio-sec/s (RTF) large-v3 1h synthetic @1/2/4/8 B200; DTW GB/s vs HBM peak"
+    # identical in both arms (the driver compares them): what is computed, not how
+    e2e_config = {"workload": workload_name, "model": args.model, "audio_seconds": args.audio_seconds,
+                  "chunk_seconds": args.chunk_seconds, "decoding": "greedy, temperature 0, chunks independent",
+                  "weights": "synthetic seed 1234 " + json.dumps(SYNTH_KW, sort_keys=True), "audio": "synthetic seed 1234",
+                  "l2": "weights + KV caches + activations far larger than L2; every step re-reads them from memory"}
     if args.impl == "reference":
         if rank != 0:
             return
         if args.workload == "align":
             cb = cpu_baseline_align(args)
-            metric, cfg = "alignment segments/s (prep+DTW)", {"workload": f"align T={args.align_T} F={args.align_F}"}
-        else:
-            cb = cpu_baseline_e2e(args)
-            metric, cfg = "audio-sec/s (RTF) large-v3 1h synthetic @1/2/4/8 B200; DTW GB/s vs HBM peak", {"workload": workload_name}
-        print(json.dumps({"impl": "reference", "metric": metric, "value": cb["value"], "unit": cb["unit"],
-                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
-                          "ms_per_step": cb.get("wall_s", 0.0) * 1e3, "scaling": "strong", "vs_baseline": None,
-                          "cpu_baseline": cb, "config": cfg, "data": "synthetic", "dtype": "f32",
+            print(json.dumps({"impl": "reference", "metric": "alignment segments/s (prep+DTW); DTW GB/s vs HBM peak",
+                              "value": cb["value"], "unit": cb["unit"], "n_gpus": args.gpus, "steps": args.steps,
+                              "warmup": args.warmup, "higher_is_better": True, "ms_per_step": None, "scaling": "weak",
+                              "vs_baseline": None, "cpu_baseline": cb, "data": "synthetic", "dtype": "f64 accumulate / f32 cost",
+                              "config": {"workload": f"align: {args.align_batch} segments/GPU, T={args.align_T}, F={args.align_F}, N=10 heads"},
+                              "e2e": {"value": cb["value"], "unit": cb["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+            return
+        # one step of this arm = ONE 30-s chunk of the workload through the reference's transcribe() (the whole hour would take
+        # ~20 min per step on host cores): W untimed chunks, then K timed chunks, all distinct, taken in order from the recording
+        n_chunks = max(1, int(args.audio_seconds // args.chunk_seconds))
+        K = max(1, min(args.steps, n_chunks))
+        W = max(0, min(args.warmup, n_chunks - K))
+        cb = cpu_baseline_e2e(args, timed=list(range(K)), warm=list(range(K, K + W)))
+        cb.pop("_results"), cb.pop("_timed")
+        print(json.dumps({"impl": "reference", "metric": metric_name, "value": cb["value"], "unit": cb["unit"],
+                          "n_gpus": args.gpus, "steps": K, "warmup": W, "higher_is_better": True,
+                          "ms_per_step": cb["wall_s"] * 1e3 / K, "scaling": "strong", "vs_baseline": None,
+                          "step_unit": f"one {args.chunk_seconds:.0f}-s chunk through the reference's transcribe() on {cb['cores']} host cores",
+                          "cpu_baseline": cb, "config": e2e_config, "data": "synthetic", "dtype": "f32", "gpu_launches": 0,
                           "e2e": {"value": cb["value"], "unit": cb["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -495,15 +592,15 @@ def main():
         res = run_e2e(args, rank, world, local)
         if rank == 0:
             line = {
-                "metric": "audio-sec/s (RTF) large-v3 1h synthetic @1/2/4/8 B200; DTW GB/s vs HBM peak",
+                "metric": metric_name,
                 "value": res["value"], "unit": "audio-sec/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "bf16x3 tensor-core GEMMs (float32-accurate), f32 elsewhere, f64 DTW accumulate",
                 "data": "synthetic audio, synthetic (seeded) weights of the exact architecture (recipe %s)" % json.dumps(SYNTH_KW),
-                "config": {"workload": workload_name, "max_batch": args.max_batch,
-                           "l2": "weights + KV caches + activations far larger than L2; every step re-reads them from HBM",
-                           "segments": res["segments"], "tokens": res["tokens"], "words": res["words"],
-                           "decode_steps": res["decode_steps"]},
+                "config": e2e_config,
+                "workload_stats": {"max_batch": args.max_batch, "segments": res["segments"], "tokens": res["tokens"],
+                                   "words": res["words"], "decode_steps": res["decode_steps"],
+                                   "small_batch_steps": res["small_batch_steps"]},
                 "e2e": {"value": res["e2e_value"], "unit": "audio-sec/s", "h2d_bytes_per_step": res["h2d"],
                         "d2h_bytes_per_step": res["d2h"]},
                 "gpu_launches": res["launches"], "clocks": res["clocks"], "stages_ms_per_step": res["stages_ms_per_step"],
@@ -525,7 +622,11 @@ def main():
                 except Exception as err:                                   # noqa: BLE001
                     line["dtw_roofline"] = {"error": f"{type(err).__name__}: {err}"[:200]}
             if not args.no_cpu_baseline:
-                line["cpu_baseline"] = cpu_baseline_e2e(args)
+                cb = cpu_baseline_e2e(args)
+                # the reference's own output on those chunks (computed on this box a moment ago) vs ours
+                line["parity_vs_reference"] = parity_vs_reference(res["result"], cb.pop("_results"), cb.pop("_timed"),
+                                                                  args.chunk_seconds)
+                line["cpu_baseline"] = cb
             print(json.dumps(line))
     else:
         res = run_align(args, rank, world)

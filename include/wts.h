@@ -213,7 +213,10 @@ int wts_kv_append(const float* d_k, const float* d_v, int64_t ld, const int32_t*
 
 /* Logit filters + greedy choice for one decode step — replaces SuppressBlank / SuppressTokens /
  * ApplyTimestampRules / GreedyDecoder.update (upstream whisper.decoding; rebuilt by the reference at
- * T.py:1371-1393 and re-applied in hook_output_logits T.py:871-875).  One CTA per sequence. */
+ * T.py:1371-1393 and re-applied in hook_output_logits T.py:871-875).  One CTA per sequence.
+ * d_full_logprobs (optional, [B, lp_ld, V]): every filtered log-softmax row (tests).  d_last_full (optional, [B, V]):
+ * the filtered log-softmax row of the step that reaches the decoding limit — the reference reads
+ * chunk_logprobs[-1][fallback token] there (T.py:529-538, 735). */
 typedef struct WtsDecodeCfg {
     int32_t n_vocab, eot, timestamp_begin, no_timestamps, max_initial_ts;   /* max_initial_ts < 0: none */
     int32_t sample_len, n_ctx, tokens_ld;
@@ -221,7 +224,43 @@ typedef struct WtsDecodeCfg {
 int wts_decode_select(float* d_logits, int64_t ldl, const WtsDecodeCfg* cfg, const uint8_t* d_suppress,
                       const uint8_t* d_blank, int32_t* d_tokens, int32_t* d_n_tokens, const int32_t* d_n_prompt,
                       int32_t* d_done, float* d_logprobs, int32_t lp_ld, float* d_full_logprobs,
-                      int32_t B, void* stream);
+                      float* d_last_full, int32_t B, void* stream);
+
+/* ---- Persistent decode steps for small active batches (csrc/decode_steps.cu).
+ * One cooperative kernel runs up to n_steps whole decoder steps (embed, all blocks with KV-cache append, causal
+ * self-attention, fp16 cross-attention with the alignment heads' pre-softmax rows written into qk_buf, final LayerNorm,
+ * tied-embedding logits, logit filters + log-softmax + greedy choice) for the sequences whose done flag is 0 — at most 32.
+ * Replaces upstream DecodingTask._main_loop driven through the reference's hooks (T.py:783-793, 849-881), for the whole
+ * batch at once.  Weights are float32 [out, in] row-major; q/k projections carry the d_head^-1/4 scale; the self K/V
+ * caches, cross K/V caches, token buffers, log-prob rows and qk_buf are the SAME buffers the per-operator path uses, so
+ * the two paths can alternate between steps. */
+typedef struct WtsDecLayer {
+    const float *ln1_g, *ln1_b, *w_qkv, *b_qkv, *w_o, *b_o;          /* self-attention block */
+    const float *ln2_g, *ln2_b, *w_cq, *b_cq, *w_co, *b_co;          /* cross-attention block (K/V are cached) */
+    const float *ln3_g, *ln3_b, *w_fc1, *b_fc1, *w_fc2, *b_fc2;      /* MLP */
+    float *self_k, *self_v;                                          /* [cap, H, n_ctx, 64] float32 */
+    const void *cross_k16, *cross_v16;                               /* [cap, H, n_audio_ctx, 64] fp16 */
+    const float* cross_k_align;                                      /* [cap, n_slots, n_audio_ctx, 64] float32 */
+    const int32_t* head_slot;                                        /* [H]: alignment slot of each head or -1 */
+} WtsDecLayer;
+
+typedef struct WtsDecodeSteps {
+    const WtsDecLayer* layers;                                       /* device array [n_layer] */
+    const float *emb, *pos, *ln_g, *ln_b;                            /* [V, D], [n_ctx, D], final LayerNorm */
+    int32_t *tokens, *n_tokens;
+    const int32_t* n_prompt;
+    int32_t* done;
+    float *logprobs, *full, *last_full, *qk_buf;                     /* full / last_full optional */
+    const uint8_t *suppress, *blank;
+    float *x, *qkv, *att, *q, *mid, *logits;                         /* scratch: [cap, D], [cap, 3D], [cap, D], [cap, D], [cap, 4D], [cap, V] */
+    uint32_t* sync;                                                  /* [4]: barrier counter, error flag, steps completed, spare */
+    WtsDecodeCfg cfg;
+    int32_t n_layer, D, H, n_ctx, n_audio_ctx, n_slots, cap, lp_ld, qk_rows, n_steps, max_rows, reserved;
+} WtsDecodeSteps;
+
+/* Runs up to n_steps steps (stops early when every sequence is done).  After the launch sync[1] != 0 means the grid
+ * barrier timed out (results invalid), sync[2] = steps completed.  Returns < 0 for unsupported dimensions. */
+int wts_decode_steps(const WtsDecodeSteps* p, void* stream);
 
 /* Per-step decoder inputs from the token buffers: tok[b] = last token, pos[b] = its position,
  * qk_row[b] = number of tokens sampled so far (row that the step predicts), or -1 when the sequence is done. */

@@ -48,6 +48,9 @@ CASES = {
     "tiny_75s_cond": ("tiny", {}, (75.0, 11), {"language": "en"}),
     "tiny_60s_nocond": ("tiny", {}, (60.0, 12), {"language": "en", "condition_on_previous_text": False}),
     "tiny_detect_lang": ("tiny", {}, (35.0, 13), {}),
+    # < 30 s of audio with language detection: the first window is aligned against the detection mel, so the
+    # reference applies NO padding mask (T.py:795-799, 708) although the window's own mel is zero-padded
+    "tiny_detect_lang_short": ("tiny", {}, (20.0, 24), {}),
     "tiny_stuck": ("tiny", {"eot_logit": 4.0, "ts_offset": 0.5}, (45.0, 14), {"language": "en"}),
     "tiny_opts": ("tiny", {}, (50.0, 15), {"language": "fr", "remove_punctuation_from_words": True,
                                             "include_punctuation_in_confidence": True,

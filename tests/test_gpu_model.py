@@ -255,15 +255,18 @@ def test_encoder_matches_oracle(tiny, backend):
         assert err <= TOL, (k, err)
 
 
+@pytest.mark.parametrize("small_rows", [32, 0, 2])
 @pytest.mark.parametrize("backend", BACKENDS)
-def test_decode_windows_matches_oracle(tiny, backend):
+def test_decode_windows_matches_oracle(tiny, backend, small_rows):
     """Same windows through the CUDA engine and the oracle engine: identical tokens, log-probs, no-speech
-    probability and alignment-head cross-attention rows within 1e-3."""
+    probability and alignment-head cross-attention rows within 1e-3.  small_rows: 32 = every step by the persistent
+    small-batch kernel (wts_decode_steps), 0 = every step by the per-operator CUDA graph, 2 = the graph until only two
+    windows are left, then the persistent kernel (the two paths share caches and token state)."""
     from whisper_timestamped.synthetic_audio import synthetic_speech
     from whisper_timestamped.tokenizer import get_tokenizer
     from whisper_timestamped.windows import make_decode_setup
     gm, om, oe = tiny
-    eng = _engine(gm, backend, keep_full_logprobs=True)
+    eng = _engine(gm, backend, keep_full_logprobs=True, small_batch_rows=small_rows)
     tok = get_tokenizer(True, num_languages=gm.num_languages, language="en", task="transcribe")
     setup = make_decode_setup(tok, gm.dims.n_text_ctx)
     audio = synthetic_speech(65.0, seed=33)
@@ -290,33 +293,82 @@ def test_decode_windows_matches_oracle(tiny, backend):
         finite = np.isfinite(oref)
         assert np.array_equal(finite, np.isfinite(full))
         assert np.max(np.abs(full[finite] - oref[finite])) <= TOL
+        if a.last_row_logprobs is not None and not a.ended_by_eot:
+            # window that ran into the decoding limit: the row the reference reads its fallback token from (T.py:529-538)
+            for t in (tok.eot, tok.timestamp_begin + 700, 1234):
+                want = float(oref[a.n_rows - 1, t])
+                got = a.last_row_logprobs(t)
+                assert (np.isinf(want) and np.isinf(got)) or abs(got - want) <= TOL
+    if small_rows == 32:
+        assert eng.small_batch_steps > 0
+    elif small_rows == 0:
+        assert eng.small_batch_steps == 0
 
 
 CASES = sorted(glob.glob(os.path.join(HERE, "golden", "e2e_*.json")))
-# The two-pass ("naive") goldens exercise CudaEngine.teacher_forced / wts_logprob_gather and the disfluency goldens
-# wts_disfluency_starts, all written at the very end of round 1 when no GPU time was left: their HOST logic is pinned on
-# CPU (tests/test_host_e2e.py; csrc/peaks.h against scipy in tests/test_host_logic.py), their CUDA side has not run on
-# hardware yet.  They go last and are non-strict xfail so that a first-run failure cannot mask the other cases; an
-# XPASS means the path works and the mark can go.
-_UNVALIDATED = [p for p in CASES if "naive" in os.path.basename(p) or "disfluenc" in os.path.basename(p)]
-CASES = [p for p in CASES if p not in _UNVALIDATED]
-_PARAMS = [pytest.param(p, id=os.path.basename(p)[4:-5]) for p in CASES] + \
-          [pytest.param(p, id=os.path.basename(p)[4:-5],
-                        marks=pytest.mark.xfail(reason="CUDA side of this option has not run on a GPU yet", strict=False))
-           for p in _UNVALIDATED]
+CHUNK_CASES = sorted(glob.glob(os.path.join(HERE, "golden", "chunks_*.json")))
 
 
-@pytest.mark.parametrize("backend", BACKENDS)
-@pytest.mark.parametrize("path", _PARAMS)
+def _is_big(path):
+    return any(b in os.path.basename(path) for b in ("medium", "large"))
+
+
+def _backends_for(path):
+    # the SIMT validator backend (1) is only run at tiny / base dimensions; the configurations bench.py measures
+    # (medium, large-v3) go through the tensor-core path that is actually timed
+    return [0] if _is_big(path) else BACKENDS
+
+
+_PARAMS = [pytest.param(p, b, id=f"{os.path.basename(p)[4:-5]}-b{b}") for p in CASES for b in _backends_for(p)]
+_CHUNK_PARAMS = [pytest.param(p, b, id=f"{os.path.basename(p)[:-5]}-b{b}") for p in CHUNK_CASES for b in _backends_for(p)]
+_MODELS = {}
+
+
+def _load(g):
+    """One resident model at a time (large-v3 weights are 12 GB in SB16 + float32)."""
+    import whisper_timestamped as wt
+    key = (g["model"], g["model_seed"], json.dumps(g["model_kwargs"], sort_keys=True))
+    if key not in _MODELS:
+        _MODELS.clear()
+        torch.cuda.empty_cache()
+        _MODELS[key] = wt.load_model(f"synthetic:{g['model']}", device="cuda:0", synthetic_seed=g["model_seed"],
+                                     synthetic_kwargs=g["model_kwargs"])
+    return _MODELS[key]
+
+
+@pytest.mark.parametrize("path,backend", _PARAMS)
 def test_transcribe_matches_reference_golden(path, backend):
-    """whisper_timestamped.transcribe() on the GPU vs the unmodified reference's output (CPU fp32)."""
+    """whisper_timestamped.transcribe() on the GPU vs the unmodified reference's output (CPU fp32): identical tokens,
+    segments, word times; confidences within 2e-3; the same warnings (e.g. the too-much-text truncation and its
+    "Got inconsistent length" follow-up on the large-v3 bench recipe)."""
     import whisper_timestamped as wt
     from whisper_timestamped.synthetic_audio import synthetic_speech
-    from test_host_e2e import compare
+    from test_host_e2e import CaptureWarnings, compare, norm_warnings
     g = json.load(open(path))
-    gm = wt.load_model(f"synthetic:{g['model']}", device="cuda:0", synthetic_seed=g["model_seed"],
-                       synthetic_kwargs=g["model_kwargs"])
+    gm = _load(g)
     eng = _engine(gm, backend)
     audio = synthetic_speech(*g["audio"])
-    res = wt.transcribe(gm, audio, engine=eng, **g["transcribe_kwargs"])
+    with CaptureWarnings() as cap:
+        res = wt.transcribe(gm, audio, engine=eng, **g["transcribe_kwargs"])
     compare(res, g["result"], conf_tol=2e-3, time_tol=0.0, prob_tol=1e-3)
+    if "warnings" in g:
+        assert norm_warnings(cap.messages) == norm_warnings(g["warnings"])
+
+
+@pytest.mark.parametrize("path,backend", _CHUNK_PARAMS)
+def test_chunks_mode_equals_reference_on_every_cut(path, backend):
+    """transcribe(..., chunks=30) — the unit of work bench.py shards over GPUs — against the unmodified reference run
+    independently on every 30-s cut (condition_on_previous_text=False), incl. the first 5 minutes of the bench audio
+    on large-v3 with the bench recipe."""
+    import whisper_timestamped as wt
+    from whisper_timestamped.synthetic_audio import synthetic_speech
+    from test_host_e2e import CaptureWarnings, compare, norm_warnings, stitch_cuts
+    g = json.load(open(path))
+    gm = _load(g)
+    eng = _engine(gm, backend)
+    audio = synthetic_speech(*g["audio"])
+    with CaptureWarnings() as cap:
+        res = wt.transcribe(gm, audio, engine=eng, chunks=g["chunks"], **g["transcribe_kwargs"])
+    ref, warns = stitch_cuts(g)
+    compare(res, ref, conf_tol=2e-3, time_tol=1e-6, prob_tol=1e-3)
+    assert norm_warnings(cap.messages) == norm_warnings(warns)

@@ -129,7 +129,8 @@ def test_struct_layouts_match_the_header(tmp_path):
     import ctypes
     import subprocess
     from whisper_timestamped import _native as nat
-    mirrors = {"WtsSegDesc": nat.SegDesc, "WtsGemm": nat.Gemm, "WtsDecodeCfg": nat.DecodeCfg}
+    mirrors = {"WtsSegDesc": nat.SegDesc, "WtsGemm": nat.Gemm, "WtsDecodeCfg": nat.DecodeCfg,
+               "WtsDecLayer": nat.DecLayer, "WtsDecodeSteps": nat.DecodeSteps}
     src = ["#include <stdio.h>", "#include <stddef.h>", '#include "wts.h"', "int main(void) {"]
     for cname, cls in mirrors.items():
         src.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')

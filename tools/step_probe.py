@@ -1,13 +1,15 @@
-"""Decode-step probe: times one decode step of the large model at a fixed number of active windows,
-either through the captured CUDA graph (default) or as plain launches (--eager, for an ncu launch list).
+"""Decode-step probe: milliseconds per decode step of a model at a fixed number of active windows, for the two step
+implementations that share the session state:
+  graph  : the per-operator step (tensor-core skinny GEMMs, one kernel per operator) replayed as ONE CUDA graph
+  steps  : the persistent small-batch kernel (wts_decode_steps, <= 32 active windows), `--steps` tokens per launch
 
-  python tools/step_probe.py --active 128 --cap 128 --steps 24
-  ncu --cache-control none --metrics gpu__time_duration.sum ... python tools/step_probe.py --eager --steps 2
+  python tools/step_probe.py --active 128,32,16,8,4,1 --cap 128 --steps 24
+  ncu ... python tools/step_probe.py --eager --steps 2        (plain launches, for an ncu launch list)
 """
 import argparse
+import json
 import os
 import sys
-import time
 
 import numpy as np
 import torch
@@ -20,9 +22,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--model", default="synthetic:large-v3")
     ap.add_argument("--cap", type=int, default=128)
-    ap.add_argument("--active", type=str, default="128,32,1")
+    ap.add_argument("--active", type=str, default="128,32,16,8,4,1")
     ap.add_argument("--steps", type=int, default=24)
     ap.add_argument("--eager", action="store_true")
+    ap.add_argument("--only", default="graph,steps")
     args = ap.parse_args()
     import whisper_timestamped as wt
     from whisper_timestamped.engine import CudaEngine
@@ -46,44 +49,53 @@ def main():
     ses["blank"].zero_()
     prompt = list(tok.sot_sequence)
     P = len(prompt)
-    dev = torch.device("cuda")
-    for n_active in [int(a) for a in args.active.split(",")]:
+
+    def reset(n_active):
         tokens = np.zeros((cap, m.dims.n_text_ctx + 1), dtype=np.int32)
         tokens[:, :P] = prompt
         tokens[:, P:P + 8] = 1000
         ses["tokens"].copy_(torch.from_numpy(tokens))
-        nt = np.full(cap, P + 8, dtype=np.int32)
-        ses["n_tokens"].copy_(torch.from_numpy(nt))
+        ses["n_tokens"].copy_(torch.from_numpy(np.full(cap, P + 8, dtype=np.int32)))
         ses["n_prompt"].copy_(torch.from_numpy(np.full(cap, P, dtype=np.int32)))
         dn = np.ones(cap, dtype=np.int32)
         dn[:n_active] = 0
         ses["done"].copy_(torch.from_numpy(dn))
+
+    out = {}
+    for n_active in [int(a) for a in args.active.split(",")]:
+        res = {}
+        reset(n_active)
         if args.eager:
             for _ in range(args.steps):
                 eng._step(ses)
             torch.cuda.synchronize()
             continue
-        if ses["graph"] is None:
-            eng._step(ses)
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            s = torch.cuda.Stream(device=dev)
-            s.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(s):
-                with torch.cuda.graph(graph, stream=s):
-                    eng._step(ses)
-            torch.cuda.current_stream(dev).wait_stream(s)
-            ses["graph"] = graph
-        for _ in range(3):
-            ses["graph"].replay()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            ses["graph"].replay()
-        e1.record()
-        torch.cuda.synchronize()
-        print(f"cap={cap} active={n_active}: {e0.elapsed_time(e1) / args.steps:.3f} ms/step "
-              f"(n_tokens now {int(ses['n_tokens'][0])})", flush=True)
+        if "graph" in args.only:
+            graph = eng._step_graph(ses)
+            for _ in range(3):
+                graph.replay()
+            e0.record()
+            for _ in range(args.steps):
+                graph.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            res["graph_ms_per_step"] = round(e0.elapsed_time(e1) / args.steps, 3)
+        if "steps" in args.only and ses["steps"] is not None and n_active <= eng.small_batch_rows:
+            reset(n_active)
+            eng._run_steps(ses, 3, n_active)
+            torch.cuda.synchronize()
+            e0.record()
+            eng._run_steps(ses, args.steps, n_active)
+            e1.record()
+            torch.cuda.synchronize()
+            flags = ses["steps"]["keep"]["sync"].cpu().numpy()
+            res["steps_ms_per_step"] = round(e0.elapsed_time(e1) / max(1, int(flags[2])), 3)
+            res["steps_completed"] = int(flags[2])
+            res["barrier_timeout"] = int(flags[1])
+        out[n_active] = res
+        print(f"active {n_active:4d} / cap {cap}: {res}", flush=True)
+    print(json.dumps({"model": args.model, "cap": cap, "steps": args.steps, "ms": out}))
 
 
 if __name__ == "__main__":

@@ -1,0 +1,525 @@
+// Persistent decode-step kernel for SMALL active batches (<= 32 windows still decoding).
+//
+// Why: a decoder step of large-v3 is ~355 dependent kernels when every operator is its own launch; at <= 32 active
+// windows each of them sits at its launch + prologue floor and the step costs ~4 ms against a ~1 ms HBM floor
+// (profiles/r1k_summary.md).  Here ONE cooperative kernel (one CTA per SM, all co-resident) walks
+//     embed -> L x [LN+QKV | self-attn | out-proj | LN+Q | cross-attn | out-proj | LN+FC1+GELU | FC2] -> LN+logits -> select
+// for up to `n_steps` tokens, phases separated by a grid-wide barrier (one atomic + one polling thread per CTA).
+// Replaces, for the whole batch at once, upstream's DecodingTask._main_loop step + the reference's per-token hooks
+// (T.py:783-793 hook_attention_weights, 849-881 hook_output_logits).
+//
+// At <= 32 rows the GEMMs are weight-streaming matrix-vector products, so they run on the FP32 pipe (no tensor cores:
+// a 128-row UMMA tile would be >= 75 % padding and its TMEM/barrier prologue is what made the per-kernel version
+// slow): a warp owns 4 output features, streams their float32 weight rows once (coalesced 512-byte loads, L1
+// bypassed), multiplies them with up to 16 activation rows staged in shared memory (LayerNorm fused into the
+// staging), and reduces over the lanes with a transposing butterfly that leaves every lane with its own outputs.
+// Weights of the NEXT phase are prefetched into L2 before each barrier, so HBM keeps streaming while CTAs wait.
+// Results are float32 throughout (weights float32 = the exact values the SB16 tensor-core path carries as hi + lo).
+#include "decode_common.cuh"
+
+namespace wts {
+
+constexpr int MG_THREADS = 256;
+constexpr int MG_WARPS = MG_THREADS / 32;
+constexpr int MG_MAXROWS = 32;          // active rows the staging buffer holds
+constexpr int MG_G = 4;                 // output features per warp task
+constexpr int MG_MAXNI = 10;            // D / 128 <= 10 (D <= 1280)
+
+struct MgShared {
+    int list[MG_MAXROWS];               // active slots, ascending
+    int n_active;
+    int abort_flag;
+    SelectScratch sel;
+};
+
+__device__ __forceinline__ float4 ldg_stream4(const float* p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// ---- grid-wide barrier: monotonic counter, one polling thread per CTA.  A spin limit turns a would-be hang (a bug, or
+// a grid that is not co-resident) into an error flag the host reports, instead of a dead GPU.
+__device__ __forceinline__ void grid_sync(uint32_t* sync, uint32_t& target, MgShared& sh)
+{
+    __syncthreads();
+    target += gridDim.x;
+    if (threadIdx.x == 0 && !sh.abort_flag) {
+        __threadfence();
+        atomicAdd(sync, 1u);
+        uint32_t v;
+        int spins = 0;
+        while (true) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(sync) : "memory");
+            if (v >= target) break;
+            if ((++spins & 1023) == 0) {
+                uint32_t e;
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(e) : "l"(sync + 1) : "memory");
+                if (e != 0 || spins > (1 << 21)) {           // ~1 s of polling: a bug, or a grid that is not co-resident
+                    atomicExch(sync + 1, 1u);
+                    sh.abort_flag = 1;
+                    break;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// ---- transposing warp reduction: v[i] (i < NV) summed over the 32 lanes; afterwards lane l holds in v[0 .. NV/32)
+// the totals of logical indices l * (NV / 32) + j  (NV >= 32), or for NV = 16 in v[0] the total of index l >> 1.
+template <int N, int MASK>
+__device__ __forceinline__ void treduce_step(float* v, int lane)
+{
+    if constexpr (N > 1 && MASK >= 1) {
+        const bool up = (lane & MASK) != 0;
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) {
+            const float keep = up ? v[i + N / 2] : v[i];
+            const float send = up ? v[i] : v[i + N / 2];
+            v[i] = keep + __shfl_xor_sync(FULL_MASK, send, MASK);
+        }
+        treduce_step<N / 2, MASK / 2>(v, lane);
+    } else if constexpr (MASK >= 1) {
+        v[0] += __shfl_xor_sync(FULL_MASK, v[0], MASK);
+        treduce_step<1, MASK / 2>(v, lane);
+    }
+}
+
+// ---- staging of activation rows into shared memory (optionally LayerNorm'ed): warp w takes rows w, w + 8, ...
+// src rows are read through L2 (ld.global.cg): they were produced by other SMs earlier in this launch.
+template <bool LN>
+__device__ __forceinline__ void stage_rows(const float* src, int64_t ld, int col0, int NI, const float* __restrict__ gam,
+                                           const float* __restrict__ bet, const MgShared& sh, float* xs)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ncols = NI * 128;
+    for (int i = warp; i < sh.n_active; i += MG_WARPS) {
+        const float* r = src + (int64_t)sh.list[i] * ld + col0;
+        float4 v[MG_MAXNI];
+#pragma unroll
+        for (int k = 0; k < MG_MAXNI; ++k)
+            if (k < NI) v[k] = ldcg4(r + 4 * (lane + 32 * k));
+        if (LN) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < MG_MAXNI; ++k)
+                if (k < NI) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+            const float mean = warp_sum(s) / (float)ncols;
+            float q = 0.f;
+#pragma unroll
+            for (int k = 0; k < MG_MAXNI; ++k)
+                if (k < NI) {
+                    const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+                    q += (a * a + b * b) + (c * c + d * d);
+                }
+            const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)ncols + 1e-5f);
+#pragma unroll
+            for (int k = 0; k < MG_MAXNI; ++k)
+                if (k < NI) {
+                    const float4 g = __ldg(reinterpret_cast<const float4*>(gam) + lane + 32 * k);
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(bet) + lane + 32 * k);
+                    v[k].x = (v[k].x - mean) * rstd * g.x + b.x;
+                    v[k].y = (v[k].y - mean) * rstd * g.y + b.y;
+                    v[k].z = (v[k].z - mean) * rstd * g.z + b.z;
+                    v[k].w = (v[k].w - mean) * rstd * g.w + b.w;
+                }
+        }
+#pragma unroll
+        for (int k = 0; k < MG_MAXNI; ++k)
+            if (k < NI) *reinterpret_cast<float4*>(xs + (int64_t)i * ncols + 4 * (lane + 32 * k)) = v[k];
+    }
+}
+
+// ---- one K chunk (NI * 128 columns) of a warp task: acc[g][b] += W[n0 + g, kc0 ...] . xs[b, ...]
+// The weight slices (4 features x one float4 per lane) run through a 4-slot register ring: three slices are always in
+// flight while the fourth is multiplied with the staged rows (RB shared-memory float4 loads, 16 FMAs each).
+template <int RB>
+__device__ __forceinline__ void gemv_slice(const float4 (&w)[MG_G], const float* xp, int pitch, float (&acc)[MG_G * RB])
+{
+    constexpr int HB = RB > 8 ? 8 : RB;                      // rows per batch of shared-memory loads (bounds live registers)
+#pragma unroll
+    for (int b0 = 0; b0 < RB; b0 += HB) {
+        float4 xv[HB];
+#pragma unroll
+        for (int b = 0; b < HB; ++b) xv[b] = *reinterpret_cast<const float4*>(xp + (b0 + b) * pitch);
+#pragma unroll
+        for (int b = 0; b < HB; ++b) {
+#pragma unroll
+            for (int g = 0; g < MG_G; ++g) {
+                float a = acc[g * RB + b0 + b];
+                a = fmaf(w[g].x, xv[b].x, a);
+                a = fmaf(w[g].y, xv[b].y, a);
+                a = fmaf(w[g].z, xv[b].z, a);
+                a = fmaf(w[g].w, xv[b].w, a);
+                acc[g * RB + b0 + b] = a;
+            }
+        }
+        asm volatile("" ::: "memory");                       // keep the next batch of loads behind this batch's FMAs
+    }
+}
+
+template <int RB>
+__device__ __forceinline__ void gemv_chunk(const float* __restrict__ W, int64_t ldw, int n0, int N, int kc0, int NI,
+                                           const float* xs, int pitch, float (&acc)[MG_G * RB])
+{
+    const int lane = threadIdx.x & 31;
+    const float* wp[MG_G];
+#pragma unroll
+    for (int g = 0; g < MG_G; ++g) wp[g] = W + (int64_t)min(n0 + g, N - 1) * ldw + kc0 + 4 * lane;
+    float4 w[4][MG_G];
+#pragma unroll
+    for (int u = 0; u < 3; ++u)
+        if (u < NI) {
+#pragma unroll
+            for (int g = 0; g < MG_G; ++g) w[u][g] = ldg_stream4(wp[g] + 128 * u);
+        }
+#pragma unroll 1
+    for (int i0 = 0; i0 < NI; i0 += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u;
+            if (i + 3 < NI) {
+#pragma unroll
+                for (int g = 0; g < MG_G; ++g) w[(u + 3) & 3][g] = ldg_stream4(wp[g] + 128 * (i + 3));
+            }
+            if (i < NI) gemv_slice<RB>(w[u], xs + 4 * (lane + 32 * i), pitch, acc);
+        }
+    }
+}
+
+enum { EPI_STORE = 0, EPI_ADD = 1, EPI_GELU = 2 };
+
+// ---- epilogue of a warp task after the transposing reduction
+template <int RB>
+__device__ __forceinline__ void gemv_epilogue(float (&acc)[MG_G * RB], int n0, int N, int row0, const MgShared& sh,
+                                              const float* __restrict__ bias, float* out, int64_t ldo, int epi)
+{
+    const int lane = threadIdx.x & 31;
+    constexpr int NV = MG_G * RB;
+    treduce_step<NV, 16>(acc, lane);
+    constexpr int PER = NV >= 32 ? NV / 32 : 1;
+    const int base = NV >= 32 ? lane * PER : lane / (32 / (NV < 32 ? NV : 32));
+    const bool writer = NV >= 32 ? true : (lane % (32 / (NV < 32 ? NV : 32))) == 0;
+    if (!writer) return;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        const int idx = base + j;
+        const int g = idx / RB, b = idx % RB;
+        const int n = n0 + g;
+        const int ri = row0 + b;
+        if (n < N && ri < sh.n_active) {
+            float t = acc[j] + (bias != nullptr ? __ldg(bias + n) : 0.f);
+            float* dst = out + (int64_t)sh.list[ri] * ldo + n;
+            if (epi == EPI_GELU) t = gelu_erf(t);
+            else if (epi == EPI_ADD) t += __ldcg(dst);
+            *dst = t;
+        }
+    }
+}
+
+// ---- a whole matrix-vector phase: out[row, n] = epi(sum_k W[n, k] * act[row, k] + bias[n]) for the active rows.
+// act rows come from `src` (global, K columns) staged chunk by chunk (D columns each) into shared memory, with
+// LayerNorm(gam, bet) fused when LN (then K == D).  Tasks (4 features) are dealt round-robin to the warps of the grid.
+template <int RB, bool LN>
+__device__ __noinline__ void gemv_phase(const float* __restrict__ W, int N, int K, int D, const float* __restrict__ bias,
+                                           const float* src, int64_t lds, const float* gam, const float* bet, float* out,
+                                           int64_t ldo, int epi, const MgShared& sh, float* xs)
+{
+    const int warp = threadIdx.x >> 5;
+    const int total_warps = gridDim.x * MG_WARPS;
+    const int gw = warp * gridDim.x + blockIdx.x;            // consecutive tasks land on different SMs
+    const int NI = D / 128;
+    const int nchunks = K / D;
+    const int ntasks = (N + MG_G - 1) / MG_G;
+    const int rounds = (ntasks + total_warps - 1) / total_warps;
+    const int npass = (sh.n_active + RB - 1) / RB;
+    if (nchunks == 1) {
+        stage_rows<LN>(src, lds, 0, NI, gam, bet, sh, xs);
+        __syncthreads();
+    }
+    for (int rd = 0; rd < rounds; ++rd) {
+        const int t = gw + rd * total_warps;
+        const bool has = t < ntasks;
+        for (int ps = 0; ps < npass; ++ps) {
+            float acc[MG_G * RB];
+#pragma unroll
+            for (int i = 0; i < MG_G * RB; ++i) acc[i] = 0.f;
+            for (int c = 0; c < nchunks; ++c) {
+                if (nchunks > 1) {
+                    __syncthreads();                         // previous chunk fully consumed
+                    stage_rows<false>(src, lds, c * D, NI, nullptr, nullptr, sh, xs);
+                    __syncthreads();
+                }
+                if (has) gemv_chunk<RB>(W, K, t * MG_G, N, c * D, NI, xs + (int64_t)ps * RB * D, D, acc);
+            }
+            if (has) gemv_epilogue<RB>(acc, t * MG_G, N, ps * RB, sh, bias, out, ldo, epi);
+        }
+    }
+}
+
+// L2 prefetch of the weight rows this warp will stream in a later phase
+__device__ __forceinline__ void prefetch_phase(const float* W, int N, int K)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_warps = gridDim.x * MG_WARPS;
+    const int gw = warp * gridDim.x + blockIdx.x;
+    const int ntasks = (N + MG_G - 1) / MG_G;
+    const int lines_per_row = K / 32;                        // 128-byte lines
+    for (int t = gw; t < ntasks; t += total_warps) {
+        for (int ln = lane; ln < MG_G * lines_per_row; ln += 32) {
+            const int g = ln / lines_per_row, c = ln - g * lines_per_row;
+            const int n = min(t * MG_G + g, N - 1);
+            prefetch_l2(W + (int64_t)n * K + c * 32);
+        }
+    }
+}
+
+// ---- causal self-attention of ONE (row, head) by a warp; appends this position's K/V to the cache first.
+// `sc`: this warp's shared-memory scratch, n_ctx floats (scores, then probabilities).
+__device__ __noinline__ void self_attention_task(const WtsDecodeSteps& P, const WtsDecLayer& Lr, int row, int h, int pos,
+                                                    float* sc)
+{
+    const int lane = threadIdx.x & 31;
+    const int D = P.D, n_ctx = P.n_ctx;
+    float* Kc = Lr.self_k + ((int64_t)row * P.H + h) * n_ctx * 64;
+    float* Vc = Lr.self_v + ((int64_t)row * P.H + h) * n_ctx * 64;
+    const float* qrow = P.qkv + (int64_t)row * 3 * D + h * 64;
+    {   // append (float2 per lane), then make it visible to the lanes that read it back below
+        const float2 kn = __ldcg(reinterpret_cast<const float2*>(qrow + D) + lane);
+        const float2 vn = __ldcg(reinterpret_cast<const float2*>(qrow + 2 * D) + lane);
+        reinterpret_cast<float2*>(Kc + (int64_t)pos * 64)[lane] = kn;
+        reinterpret_cast<float2*>(Vc + (int64_t)pos * 64)[lane] = vn;
+        __threadfence_block();
+        __syncwarp();
+    }
+    float q[64];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+        const float4 t = ldcg4(qrow + 4 * c);
+        q[4 * c] = t.x; q[4 * c + 1] = t.y; q[4 * c + 2] = t.z; q[4 * c + 3] = t.w;
+    }
+    const int nk = pos + 1;
+    float mx = -CUDART_INF_F;
+#pragma unroll 1
+    for (int j = lane; j < nk; j += 32) {                    // a lane owns keys lane, lane + 32, ...
+        const float* kr = Kc + (int64_t)j * 64;
+        float a = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const float4 kv = ldcg4(kr + 4 * c);
+            a += q[4 * c] * kv.x + q[4 * c + 1] * kv.y + q[4 * c + 2] * kv.z + q[4 * c + 3] * kv.w;
+        }
+        sc[j] = a;
+        mx = fmaxf(mx, a);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll 1
+    for (int j = lane; j < nk; j += 32) {
+        const float e = expf(sc[j] - mx);
+        sc[j] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    __syncwarp();
+    float2 o = make_float2(0.f, 0.f);                        // a lane owns channels 2 lane, 2 lane + 1
+#pragma unroll 8
+    for (int j = 0; j < nk; ++j) {
+        const float p = sc[j];
+        const float2 v = __ldcg(reinterpret_cast<const float2*>(Vc + (int64_t)j * 64) + lane);
+        o.x = fmaf(p, v.x, o.x);
+        o.y = fmaf(p, v.y, o.y);
+    }
+    const float inv = 1.0f / sum;
+    reinterpret_cast<float2*>(P.att + (int64_t)row * D + h * 64)[lane] = make_float2(o.x * inv, o.y * inv);
+    __syncwarp();                                            // scratch is reused by this warp's next task
+}
+
+// ---- cross-attention of the active rows: one CTA per (row, head), K/V (fp16; float32 K for the alignment heads) are
+// streamed once; the alignment heads' pre-softmax rows go straight into the alignment buffer (qk_buf).
+__device__ __noinline__ void cross_attention_phase(const WtsDecodeSteps& P, const WtsDecLayer& Lr, const MgShared& sh, float* xs)
+{
+    const int D = P.D, H = P.H;
+    CaScratch& sc = *reinterpret_cast<CaScratch*>(xs);
+    const int c8 = threadIdx.x & 7;
+    for (int t = blockIdx.x; t < sh.n_active * H; t += gridDim.x) {
+        const int row = sh.list[t / H], h = t % H;
+        float qf[8];
+        {
+            const float* qp = P.q + (int64_t)row * D + h * 64 + c8 * 8;
+            const float4 a = ldcg4(qp), b = ldcg4(qp + 4);
+            qf[0] = a.x; qf[1] = a.y; qf[2] = a.z; qf[3] = a.w; qf[4] = b.x; qf[5] = b.y; qf[6] = b.z; qf[7] = b.w;
+        }
+        const int slot = __ldg(Lr.head_slot + h);
+        const int64_t kv_off = ((int64_t)row * H + h) * P.n_audio_ctx * 64;
+        const float* kal = nullptr;
+        float* qk_dst = nullptr;
+        if (slot >= 0) {
+            kal = Lr.cross_k_align + ((int64_t)row * P.n_slots + slot) * P.n_audio_ctx * 64;
+            const int qr = __ldcg(P.n_tokens + row) - __ldg(P.n_prompt + row);
+            qk_dst = P.qk_buf + (((int64_t)row * P.n_slots + slot) * P.qk_rows + qr) * (int64_t)P.n_audio_ctx;
+        }
+        const float y = ca_row_head<4>(qf, reinterpret_cast<const __half*>(Lr.cross_k16) + kv_off,
+                                       reinterpret_cast<const __half*>(Lr.cross_v16) + kv_off, kal, qk_dst,
+                                       P.n_audio_ctx, sc);
+        if (threadIdx.x < 64) P.att[(int64_t)row * D + h * 64 + threadIdx.x] = y;
+        __syncthreads();                                     // scratch reused by the next task
+    }
+}
+
+template <int RB>
+__device__ void decode_layers_and_logits(const WtsDecodeSteps& P, MgShared& sh, float* xs, uint32_t& target)
+{
+    const int D = P.D, H = P.H;
+    const int warp = threadIdx.x >> 5;
+    const int total_warps = gridDim.x * MG_WARPS;
+    const int gw = warp * gridDim.x + blockIdx.x;
+    for (int li = 0; li < P.n_layer; ++li) {
+        const WtsDecLayer& Lr = P.layers[li];
+        // P1: LN + QKV
+        gemv_phase<RB, true>(Lr.w_qkv, 3 * D, D, D, Lr.b_qkv, P.x, D, Lr.ln1_g, Lr.ln1_b, P.qkv, 3 * D, EPI_STORE, sh, xs);
+        prefetch_phase(Lr.w_o, D, D);
+        grid_sync(P.sync, target, sh);
+        // P2: self-attention, one warp per (row, head)
+        for (int t = gw; t < sh.n_active * H; t += total_warps) {
+            const int row = sh.list[t / H];
+            self_attention_task(P, Lr, row, t % H, __ldcg(P.n_tokens + row) - 1, xs + warp * P.n_ctx);
+        }
+        grid_sync(P.sync, target, sh);
+        // P3: out-projection + residual
+        gemv_phase<RB, false>(Lr.w_o, D, D, D, Lr.b_o, P.att, D, nullptr, nullptr, P.x, D, EPI_ADD, sh, xs);
+        prefetch_phase(Lr.w_cq, D, D);
+        grid_sync(P.sync, target, sh);
+        // P4: LN + cross query
+        gemv_phase<RB, true>(Lr.w_cq, D, D, D, Lr.b_cq, P.x, D, Lr.ln2_g, Lr.ln2_b, P.q, D, EPI_STORE, sh, xs);
+        prefetch_phase(Lr.w_co, D, D);
+        grid_sync(P.sync, target, sh);
+        // P5: cross-attention, one CTA per (row, head); scratch aliases the (idle) staging buffer
+        cross_attention_phase(P, Lr, sh, xs);
+        grid_sync(P.sync, target, sh);
+        // P6: cross out-projection + residual
+        gemv_phase<RB, false>(Lr.w_co, D, D, D, Lr.b_co, P.att, D, nullptr, nullptr, P.x, D, EPI_ADD, sh, xs);
+        prefetch_phase(Lr.w_fc1, 4 * D, D);
+        grid_sync(P.sync, target, sh);
+        // P7: LN + FC1 + GELU
+        gemv_phase<RB, true>(Lr.w_fc1, 4 * D, D, D, Lr.b_fc1, P.x, D, Lr.ln3_g, Lr.ln3_b, P.mid, 4 * D, EPI_GELU, sh, xs);
+        prefetch_phase(Lr.w_fc2, D, 4 * D);
+        grid_sync(P.sync, target, sh);
+        // P8: FC2 + residual (K = 4D in D-column chunks)
+        gemv_phase<RB, false>(Lr.w_fc2, D, 4 * D, D, Lr.b_fc2, P.mid, 4 * D, nullptr, nullptr, P.x, D, EPI_ADD, sh, xs);
+        if (li + 1 < P.n_layer) prefetch_phase(P.layers[li + 1].w_qkv, 3 * D, D);
+        grid_sync(P.sync, target, sh);
+    }
+    // final LN + tied-embedding logits
+    gemv_phase<RB, true>(P.emb, P.cfg.n_vocab, D, D, nullptr, P.x, D, P.ln_g, P.ln_b, P.logits, P.cfg.n_vocab, EPI_STORE, sh, xs);
+    grid_sync(P.sync, target, sh);
+}
+
+// RB = activation rows per weight pass (4, 8 or 16): chosen by the host from the number of active rows at launch
+// (it only shrinks during a launch); more rows than RB simply take several passes.
+template <int RB>
+__global__ void __launch_bounds__(MG_THREADS, 1)
+decode_steps_kernel(const WtsDecodeSteps P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MgShared& sh = *reinterpret_cast<MgShared*>(smem_raw);
+    float* xs = reinterpret_cast<float*>(smem_raw + 1024);    // [MG_MAXROWS][D] staging (aliased by the attention scratch)
+    static_assert(sizeof(MgShared) <= 1024, "MgShared must fit its slot");
+    uint32_t target = 0;
+    if (threadIdx.x == 0) sh.abort_flag = 0;
+    const int D = P.D;
+
+    for (int step = 0; step < P.n_steps; ++step) {
+        // ---- active rows (every CTA builds the same list; `done` was settled before the last barrier)
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int count = 0;
+            for (int b0 = 0; b0 < P.cap; b0 += 32) {
+                const int b = b0 + threadIdx.x;
+                const bool act = b < P.cap && __ldcg(P.done + b) == 0;
+                const unsigned bal = __ballot_sync(FULL_MASK, act);
+                const int at = count + __popc(bal & ((1u << threadIdx.x) - 1u));
+                if (act && at < MG_MAXROWS) sh.list[at] = b;
+                count += __popc(bal);
+            }
+            if (threadIdx.x == 0) sh.n_active = count;
+        }
+        __syncthreads();
+        const int nA = sh.n_active;
+        if (nA == 0 || nA > MG_MAXROWS || sh.abort_flag) break;         // uniform over the grid
+
+        // ---- embed: x[row] = token_embedding[last token] + positional_embedding[its position]
+        for (int i = blockIdx.x; i < nA; i += gridDim.x) {
+            const int row = sh.list[i];
+            const int nt = __ldcg(P.n_tokens + row);
+            const int tok = __ldcg(P.tokens + (int64_t)row * P.cfg.tokens_ld + nt - 1);
+            const float* e = P.emb + (int64_t)tok * D;
+            const float* p = P.pos + (int64_t)(nt - 1) * D;
+            for (int c = threadIdx.x; c < D; c += MG_THREADS) P.x[(int64_t)row * D + c] = __ldg(e + c) + __ldg(p + c);
+        }
+        if (step == 0) prefetch_phase(P.layers[0].w_qkv, 3 * D, D);
+        grid_sync(P.sync, target, sh);
+
+        decode_layers_and_logits<RB>(P, sh, xs, target);
+
+        // ---- filters + log-softmax + greedy choice: one CTA per active row
+        for (int i = blockIdx.x; i < nA; i += gridDim.x) {
+            const int row = sh.list[i];
+            select_row<true>(P.logits + (int64_t)row * P.cfg.n_vocab, P.cfg, P.suppress, P.blank,
+                             P.tokens + (int64_t)row * P.cfg.tokens_ld, P.n_tokens + row, __ldg(P.n_prompt + row), P.done + row,
+                             P.logprobs + (int64_t)row * P.lp_ld,
+                             P.full != nullptr ? P.full + (int64_t)row * P.lp_ld * P.cfg.n_vocab : nullptr,
+                             P.last_full != nullptr ? P.last_full + (int64_t)row * P.cfg.n_vocab : nullptr, sh.sel);
+            __syncthreads();
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.sync + 2, 1u);   // steps completed
+        grid_sync(P.sync, target, sh);
+    }
+}
+
+}  // namespace wts
+
+using namespace wts;
+
+extern "C" int wts_decode_steps(const WtsDecodeSteps* p, void* stream)
+{
+    if (!p) { set_error("wts_decode_steps: null argument"); return -2; }
+    const WtsDecodeSteps& P = *p;
+    if (P.D % 128 != 0 || P.D > 128 * MG_MAXNI || P.D != P.H * 64) {
+        set_error("wts_decode_steps: n_text_state %d not supported (multiple of 128, <= %d, 64 per head)", P.D, 128 * MG_MAXNI);
+        return -2;
+    }
+    if (P.max_rows > MG_MAXROWS) { set_error("wts_decode_steps: at most %d active rows", MG_MAXROWS); return -2; }
+    if (P.n_steps <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    static int n_sm = 0;
+    static size_t smem_set = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        WTS_CUDA_CHECK(cudaGetDevice(&dev));
+        WTS_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const size_t stage = (size_t)MG_MAXROWS * P.D * sizeof(float);
+    size_t smem = stage > sizeof(CaScratch) ? stage : sizeof(CaScratch);
+    const size_t sa = (size_t)MG_WARPS * P.n_ctx * sizeof(float);             // self-attention score scratch
+    if (sa > smem) smem = sa;
+    smem += 1024;
+    if (smem > 227 * 1024) { set_error("wts_decode_steps: %zu bytes of shared memory needed", smem); return -2; }
+    if (smem > smem_set) {
+        WTS_CUDA_CHECK(cudaFuncSetAttribute(decode_steps_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        WTS_CUDA_CHECK(cudaFuncSetAttribute(decode_steps_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        WTS_CUDA_CHECK(cudaFuncSetAttribute(decode_steps_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    WTS_CUDA_CHECK(cudaMemsetAsync(P.sync, 0, 4 * sizeof(uint32_t), st));
+    void* args[] = {const_cast<WtsDecodeSteps*>(p)};
+    const void* fn = P.max_rows <= 4 ? (const void*)decode_steps_kernel<4>
+                   : P.max_rows <= 8 ? (const void*)decode_steps_kernel<8> : (const void*)decode_steps_kernel<16>;
+    WTS_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(n_sm), dim3(MG_THREADS), args, smem, st));
+    return 0;
+}

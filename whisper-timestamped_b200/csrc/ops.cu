@@ -3,44 +3,9 @@
 // heads' pre-softmax rows written straight into the alignment buffer), KV-cache append, and the
 // fused logit-filter / log-softmax / greedy-argmax step.  See include/wts.h for the reference
 // interfaces each entry replaces.
-#include <cuda_bf16.h>
-#include <cuda_fp16.h>
-#include <math_constants.h>
-
-#include "common.cuh"
+#include "decode_common.cuh"
 
 namespace wts {
-
-__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo)
-{
-    hi = __float2bfloat16_rn(x);
-    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
-}
-
-__device__ __forceinline__ float block_reduce_sum(float v, float* red)
-{
-    v = warp_sum(v);
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
-    __syncthreads();
-    if (l == 0) red[w] = v;
-    __syncthreads();
-    float r = (threadIdx.x < nw) ? red[threadIdx.x] : 0.f;
-    if (w == 0) { r = warp_sum(r); if (l == 0) red[0] = r; }
-    __syncthreads();
-    return red[0];
-}
-__device__ __forceinline__ float block_reduce_max(float v, float* red)
-{
-    v = warp_max(v);
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
-    __syncthreads();
-    if (l == 0) red[w] = v;
-    __syncthreads();
-    float r = (threadIdx.x < nw) ? red[threadIdx.x] : -CUDART_INF_F;
-    if (w == 0) { r = warp_max(r); if (l == 0) red[0] = r; }
-    __syncthreads();
-    return red[0];
-}
 
 // ------------------------------------------------------------------------------------------ to_sb16
 __global__ void to_sb16_kernel(const float* __restrict__ x, int64_t n, __nv_bfloat16* __restrict__ hi,
@@ -347,73 +312,7 @@ __global__ void cross_kv_pack_kernel(const float* __restrict__ src, __half* __re
 // (The decode-step kernels take plain, not __restrict__, pointers: under programmatic dependent launch a consumer is
 // resident before its producer has finished, so producer-written buffers must not be read through the non-coherent
 // ld.global.nc path the compiler picks for const __restrict__ data.)
-// One CTA per (query row, head); 256 threads = 32 key groups x 8 lanes, a lane owns 8 of the 64 channels.
-// A group streams keys g, g+32, ...: K row (16 B/lane fp16, or 32 B/lane from the float32 alignment copy) and
-// V row (16 B/lane) are both loaded CA_UNROLL keys ahead (coalesced 128-byte rows, >= 128 B in flight per lane),
-// the score is an 8-lane shuffle reduction and softmax x V is accumulated ONLINE (running max / sum), so K and V
-// are streamed exactly once, in one pass, with no score buffer.  The 32 partial (max, sum, acc) triples are
-// merged in shared memory.  Raw scores of the alignment heads go to qk_out on the way.
-constexpr int CA_THREADS = 256;
-constexpr int CA_GROUPS = CA_THREADS / 8;
-constexpr int CA_UNROLL = 4;
-
-template <bool KF32>
-__device__ __forceinline__ void ca_stream(const void* __restrict__ Kbase, const __half* __restrict__ Vbase, int ctx, int g,
-                                          int c8, const float (&qf)[8], float* __restrict__ qk_dst, float& m, float& l,
-                                          float (&acc)[8])
-{
-    for (int j0 = g; j0 < ctx; j0 += CA_GROUPS * CA_UNROLL) {
-        uint4 kr[CA_UNROLL][KF32 ? 2 : 1];
-        uint4 vr[CA_UNROLL];
-#pragma unroll
-        for (int u = 0; u < CA_UNROLL; ++u) {
-            const int j = min(j0 + CA_GROUPS * u, ctx - 1);
-            if (KF32) {
-                const uint4* p = reinterpret_cast<const uint4*>(static_cast<const float*>(Kbase) + (int64_t)j * 64 + c8 * 8);
-                kr[u][0] = __ldcs(p);
-                kr[u][KF32 ? 1 : 0] = __ldcs(p + 1);
-            } else {
-                kr[u][0] = __ldcs(reinterpret_cast<const uint4*>(static_cast<const __half*>(Kbase) + (int64_t)j * 64 + c8 * 8));
-            }
-            vr[u] = __ldcs(reinterpret_cast<const uint4*>(Vbase + (int64_t)j * 64 + c8 * 8));
-        }
-#pragma unroll
-        for (int u = 0; u < CA_UNROLL; ++u) {
-            const int j = j0 + CA_GROUPS * u;
-            const bool valid = j < ctx;
-            float s = 0.f;
-            if (KF32) {
-                const float* kf = reinterpret_cast<const float*>(&kr[u][0]);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) s += qf[e] * kf[e];
-            } else {
-                const __half2* h2 = reinterpret_cast<const __half2*>(&kr[u][0]);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float2 f = __half22float2(h2[e]);
-                    s += qf[2 * e] * f.x + qf[2 * e + 1] * f.y;
-                }
-            }
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            s += __shfl_xor_sync(0xffffffffu, s, 4);
-            if (valid && qk_dst != nullptr && c8 == 0) qk_dst[j] = s;
-            const float mn = fmaxf(m, valid ? s : -1e30f);
-            const float sc = __expf(m - mn);
-            const float p = valid ? __expf(s - mn) : 0.f;
-            l = l * sc + p;
-            const __half2* v2 = reinterpret_cast<const __half2*>(&vr[u]);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float2 f = __half22float2(v2[e]);
-                acc[2 * e] = acc[2 * e] * sc + p * f.x;
-                acc[2 * e + 1] = acc[2 * e + 1] * sc + p * f.y;
-            }
-            m = mn;
-        }
-    }
-}
-
+// One CTA per (query row, head): decode_common.cuh ca_row_head (one pass, online softmax, K/V streamed once).
 __global__ void __launch_bounds__(CA_THREADS)
 cross_attention_f16_kernel(const float* q, int64_t ldq, const __half* k16,
                            const __half* v16, const float* k_align,
@@ -424,51 +323,30 @@ cross_attention_f16_kernel(const float* q, int64_t ldq, const __half* k16,
 {
     pdl_launch();
     pdl_wait();
-    __shared__ float sm_acc[CA_GROUPS][64];
-    __shared__ float sm_m[CA_GROUPS], sm_l[CA_GROUPS], sm_w[CA_GROUPS];
-    __shared__ float sm_L;
+    __shared__ CaScratch sc;
     const int r = blockIdx.x, h = blockIdx.y;
     if (row_active != nullptr && !row_active[r]) return;   // finished sequence: skip its K/V stream
     const int seq = row_seq[r];
     const int slot = head_slot[h];
-    const int c8 = threadIdx.x & 7, g = threadIdx.x >> 3;
+    const int c8 = threadIdx.x & 7;
     float qf[8];
     {
         const float4* qp = reinterpret_cast<const float4*>(q + (int64_t)r * ldq + h * 64 + c8 * 8);
         const float4 a = qp[0], b = qp[1];
         qf[0] = a.x; qf[1] = a.y; qf[2] = a.z; qf[3] = a.w; qf[4] = b.x; qf[5] = b.y; qf[6] = b.z; qf[7] = b.w;
     }
-    float m = -1e30f, l = 0.f;
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const __half* V = v16 + ((int64_t)seq * H + h) * ctx * 64;
+    float* qk_dst = nullptr;
+    const float* kal = nullptr;
     if (slot >= 0) {
-        float* qk_dst = nullptr;
+        kal = k_align + ((int64_t)seq * n_slots + slot) * ctx * 64;
         if (qk_out != nullptr) {
             const int qr = qk_row[r];
             if (qr >= 0) qk_dst = qk_out + (((int64_t)seq * n_slots + slot) * qk_rows + qr) * (int64_t)ctx;
         }
-        ca_stream<true>(k_align + ((int64_t)seq * n_slots + slot) * ctx * 64, V, ctx, g, c8, qf, qk_dst, m, l, acc);
-    } else {
-        ca_stream<false>(k16 + ((int64_t)seq * H + h) * ctx * 64, V, ctx, g, c8, qf, nullptr, m, l, acc);
     }
-    if (c8 == 0) { sm_m[g] = m; sm_l[g] = l; }
-    *reinterpret_cast<float4*>(&sm_acc[g][c8 * 8]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    *reinterpret_cast<float4*>(&sm_acc[g][c8 * 8 + 4]) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        const float mg = sm_m[threadIdx.x];
-        const float M = warp_max(mg);
-        const float w = __expf(mg - M);
-        sm_w[threadIdx.x] = w;
-        const float L = warp_sum(sm_l[threadIdx.x] * w);
-        if (threadIdx.x == 0) sm_L = L;
-    }
-    __syncthreads();
+    const float y = ca_row_head<4>(qf, k16 + ((int64_t)seq * H + h) * ctx * 64, V, kal, qk_dst, ctx, sc);
     if (threadIdx.x < 64) {
-        float y = 0.f;
-#pragma unroll
-        for (int gg = 0; gg < CA_GROUPS; ++gg) y += sm_acc[gg][threadIdx.x] * sm_w[gg];
-        y /= sm_L;
         __nv_bfloat16 hi, lo;
         split_bf16(y, hi, lo);
         o[(int64_t)r * ldo + h * 64 + threadIdx.x] = hi;
@@ -493,122 +371,24 @@ __global__ void kv_append_kernel(const float* k, const float* v, int64_t ld,
 }
 
 // ------------------------------------------------------------------------------------ decode select
+// one CTA per sequence: decode_common.cuh select_row
 constexpr int DS_THREADS = 512;
 __global__ void __launch_bounds__(DS_THREADS)
 decode_select_kernel(float* logits, int64_t ldl, const WtsDecodeCfg cfg,
                      const uint8_t* suppress, const uint8_t* blank,
                      int32_t* tokens, int32_t* n_tokens,
                      const int32_t* n_prompt, int32_t* done,
-                     float* logprobs, int lp_ld, float* full)
+                     float* logprobs, int lp_ld, float* full, float* last_full)
 {
     pdl_launch();
     pdl_wait();
-    __shared__ float red[32];
-    __shared__ int s_flags[8];
-    __shared__ float s_best[DS_THREADS / 32];
-    __shared__ int s_besti[DS_THREADS / 32];
+    __shared__ SelectScratch S;
     const int b = blockIdx.x;
     if (done[b]) return;
-    float* x = logits + (int64_t)b * ldl;
-    int32_t* tk = tokens + (int64_t)b * cfg.tokens_ld;
-    const int nt = n_tokens[b], np = n_prompt[b];
-    const int n = nt - np;                                   // sampled so far
-    const int V = cfg.n_vocab, tsb = cfg.timestamp_begin, eot = cfg.eot;
-    if (threadIdx.x == 0) {
-        const bool last_ts = n >= 1 && tk[nt - 1] >= tsb;
-        const bool pen_ts = n < 2 || tk[nt - 2] >= tsb;
-        int tl = -1;
-        for (int i = nt - 1; i >= np; --i) if (tk[i] >= tsb) { tl = tk[i]; break; }
-        int ts_limit = tsb;                                  // timestamps in [tsb, ts_limit) are forbidden
-        if (tl >= 0) ts_limit = (last_ts && !pen_ts) ? tl : tl + 1;
-        s_flags[0] = (n == 0);
-        s_flags[1] = last_ts && pen_ts;                      // forbid all timestamps
-        s_flags[2] = last_ts && !pen_ts;                     // forbid text below eot
-        s_flags[3] = ts_limit;
-    }
-    __syncthreads();
-    const bool first = s_flags[0], no_ts = s_flags[1], no_text = s_flags[2];
-    const int ts_limit = s_flags[3];
-    const int ts_max = (first && cfg.max_initial_ts >= 0) ? tsb + cfg.max_initial_ts : V;
-
-    auto allowed = [&](int v) -> bool {
-        if (suppress[v]) return false;
-        if (first && blank[v]) return false;
-        if (v == cfg.no_timestamps) return false;
-        if (v >= tsb) {
-            if (no_ts) return false;
-            if (v < ts_limit) return false;
-            if (v > ts_max) return false;
-        } else {
-            if (first) return false;
-            if (no_text && v < eot) return false;
-        }
-        return true;
-    };
-
-    // pass 1: maxima of the text range and of the timestamp range
-    float mt = -CUDART_INF_F, ms = -CUDART_INF_F;
-    for (int v = threadIdx.x; v < V; v += DS_THREADS) {
-        if (!allowed(v)) continue;
-        const float xv = x[v];
-        if (v >= tsb) ms = fmaxf(ms, xv); else mt = fmaxf(mt, xv);
-    }
-    mt = block_reduce_max(mt, red);
-    ms = block_reduce_max(ms, red);
-    // pass 2: sum of exp over timestamps (relative to ms) -> logsumexp of the timestamp range
-    float ss = 0.f;
-    if (ms > -CUDART_INF_F)
-        for (int v = tsb + threadIdx.x; v < V; v += DS_THREADS)
-            if (allowed(v)) ss += expf(x[v] - ms);
-    ss = block_reduce_sum(ss, red);
-    const float lse_ts = (ms > -CUDART_INF_F) ? ms + logf(ss) : -CUDART_INF_F;
-    const bool only_ts = lse_ts > mt;                        // "sum of timestamp probability beats any text token"
-    // pass 3: final normaliser + argmax over the allowed set
-    const float gm = only_ts ? ms : fmaxf(mt, ms);
-    float sum = 0.f, best = -CUDART_INF_F;
-    int besti = 0x7fffffff;
-    for (int v = threadIdx.x; v < V; v += DS_THREADS) {
-        if (!allowed(v) || (only_ts && v < tsb)) continue;
-        const float xv = x[v];
-        sum += expf(xv - gm);
-        if (xv > best) { best = xv; besti = v; }             // ascending v per thread: first max kept
-    }
-    sum = block_reduce_sum(sum, red);
-    // block argmax, lowest index on ties
-    {
-        float bv = best; int bi = besti;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(FULL_MASK, bv, o);
-            const int oi = __shfl_xor_sync(FULL_MASK, bi, o);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-        }
-        if ((threadIdx.x & 31) == 0) { s_best[threadIdx.x >> 5] = bv; s_besti[threadIdx.x >> 5] = bi; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int w = 1; w < DS_THREADS / 32; ++w)
-                if (s_best[w] > bv || (s_best[w] == bv && s_besti[w] < bi)) { bv = s_best[w]; bi = s_besti[w]; }
-            s_best[0] = bv; s_besti[0] = bi;
-        }
-        __syncthreads();
-    }
-    const float lse = gm + logf(sum);
-    const int chosen = s_besti[0];
-    if (full != nullptr) {
-        float* f = full + ((int64_t)b * lp_ld + n) * V;
-        for (int v = threadIdx.x; v < V; v += DS_THREADS)
-            f[v] = (allowed(v) && !(only_ts && v < tsb)) ? x[v] - lse : -CUDART_INF_F;
-    }
-    if (threadIdx.x == 0) {
-        logprobs[(int64_t)b * lp_ld + n] = s_best[0] - lse;
-        if (chosen == eot) {
-            done[b] = 1;
-        } else {
-            tk[nt] = chosen;
-            n_tokens[b] = nt + 1;
-            if (n + 1 >= cfg.sample_len || nt + 1 > cfg.n_ctx) done[b] = 2;   // decoding limit reached
-        }
-    }
+    select_row<false>(logits + (int64_t)b * ldl, cfg, suppress, blank, tokens + (int64_t)b * cfg.tokens_ld, n_tokens + b,
+                      n_prompt[b], done + b, logprobs + (int64_t)b * lp_ld,
+                      full != nullptr ? full + (int64_t)b * lp_ld * cfg.n_vocab : nullptr,
+                      last_full != nullptr ? last_full + (int64_t)b * cfg.n_vocab : nullptr, S);
 }
 
 __global__ void step_inputs_kernel(const int32_t* tokens, int ld, const int32_t* n_tokens,
@@ -821,12 +601,12 @@ extern "C" int wts_kv_append(const float* d_k, const float* d_v, int64_t ld, con
 extern "C" int wts_decode_select(float* d_logits, int64_t ldl, const WtsDecodeCfg* cfg, const uint8_t* d_suppress,
                                  const uint8_t* d_blank, int32_t* d_tokens, int32_t* d_n_tokens,
                                  const int32_t* d_n_prompt, int32_t* d_done, float* d_logprobs, int32_t lp_ld,
-                                 float* d_full_logprobs, int32_t B, void* stream)
+                                 float* d_full_logprobs, float* d_last_full, int32_t B, void* stream)
 {
     if (B <= 0) return 0;
     WTS_CUDA_CHECK(launch_pdl(decode_select_kernel, dim3(B), dim3(DS_THREADS), 0, (cudaStream_t)stream, d_logits, ldl, *cfg, d_suppress, d_blank, d_tokens,
                                                                     d_n_tokens, d_n_prompt, d_done, d_logprobs, lp_ld,
-                                                                    d_full_logprobs));
+                                                                    d_full_logprobs, d_last_full));
     WTS_LAUNCH_CHECK();
     return 0;
 }

@@ -60,6 +60,25 @@ class DecodeCfg(ctypes.Structure):
                 ("n_ctx", ctypes.c_int32), ("tokens_ld", ctypes.c_int32)]
 
 
+class DecLayer(ctypes.Structure):
+    """Mirror of `WtsDecLayer`."""
+    _fields_ = [(n, ctypes.c_void_p) for n in (
+        "ln1_g", "ln1_b", "w_qkv", "b_qkv", "w_o", "b_o",
+        "ln2_g", "ln2_b", "w_cq", "b_cq", "w_co", "b_co",
+        "ln3_g", "ln3_b", "w_fc1", "b_fc1", "w_fc2", "b_fc2",
+        "self_k", "self_v", "cross_k16", "cross_v16", "cross_k_align", "head_slot")]
+
+
+class DecodeSteps(ctypes.Structure):
+    """Mirror of `WtsDecodeSteps`."""
+    _fields_ = [(n, ctypes.c_void_p) for n in (
+        "layers", "emb", "pos", "ln_g", "ln_b", "tokens", "n_tokens", "n_prompt", "done",
+        "logprobs", "full", "last_full", "qk_buf", "suppress", "blank",
+        "x", "qkv", "att", "q", "mid", "logits", "sync")] + [("cfg", DecodeCfg)] + [(n, ctypes.c_int32) for n in (
+        "n_layer", "D", "H", "n_ctx", "n_audio_ctx", "n_slots", "cap", "lp_ld", "qk_rows", "n_steps", "max_rows",
+        "reserved")]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -99,7 +118,9 @@ def _load():
     lib.wts_enc_attention.argtypes = [vp, i64, i64, vp, i64, i64, i32, i32, i32, i32, vp, i64, i64, vp]
     lib.wts_enc_attention.restype = ctypes.c_int
     lib.wts_kv_append.argtypes = [vp, vp, i64, vp, vp, i32, i32, i32, vp, vp, i64, vp]
-    lib.wts_decode_select.argtypes = [vp, i64, ctypes.POINTER(DecodeCfg), vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, vp]
+    lib.wts_decode_select.argtypes = [vp, i64, ctypes.POINTER(DecodeCfg), vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, vp]
+    lib.wts_decode_steps.argtypes = [ctypes.POINTER(DecodeSteps), vp]
+    lib.wts_decode_steps.restype = ctypes.c_int
     lib.wts_step_inputs.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp]
     lib.wts_softmax_pick.argtypes = [vp, i64, i32, i32, vp, i32, vp]
     lib.wts_logprob_gather.argtypes = [vp, i64, i32, vp, vp, vp, i32, vp]
@@ -117,7 +138,7 @@ EXPORTED_SYMBOLS = [
     "wts_version", "wts_last_error", "wts_dtw_dir_words", "wts_dtw_bnd_doubles",
     "wts_attn_prep_batch", "wts_dtw_batch", "wts_disfluency_starts", "wts_gemm", "wts_to_sb16", "wts_layernorm", "wts_softmax_rows",
     "wts_frames", "wts_power", "wts_logmel_max", "wts_logmel_finish", "wts_window_gather", "wts_embed",
-    "wts_gather_rows", "wts_decoder_attention", "wts_kv_append", "wts_decode_select", "wts_step_inputs",
+    "wts_gather_rows", "wts_decoder_attention", "wts_kv_append", "wts_decode_select", "wts_decode_steps", "wts_step_inputs",
     "wts_softmax_pick", "wts_logprob_gather", "wts_cross_kv_pack", "wts_cross_attention_f16", "wts_enc_attention",
 ]
 

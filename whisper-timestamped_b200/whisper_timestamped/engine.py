@@ -33,7 +33,7 @@ def _i32(x, dev):
 
 
 class CudaEngine:
-    def __init__(self, model, max_batch=None, gemm_backend=None, keep_full_logprobs=False):
+    def __init__(self, model, max_batch=None, gemm_backend=None, keep_full_logprobs=False, small_batch_rows=None):
         self.m = model
         self.dev = model.device
         self.w = model.w
@@ -49,6 +49,10 @@ class CudaEngine:
         self.full_logprobs = []         # per call (only when keep_full_logprobs)
         self.launches = 0
         self.use_graph = os.environ.get("WTS_CUDA_GRAPH", "1") != "0"
+        # at most this many sequences still decoding -> the persistent small-batch kernel takes over (0 = never)
+        self.small_batch_rows = min(32, int(os.environ.get("WTS_SMALL_BATCH_ROWS", "32")) if small_batch_rows is None
+                                    else int(small_batch_rows))
+        self.small_batch_steps = 0
         self._graphs = {}
         self.profile = False            # when set, phases are bracketed with CUDA events (stage_ms())
         self._events = []
@@ -343,7 +347,7 @@ class CudaEngine:
         if ses is not None and ses["cap"] >= need:
             cap = ses["cap"]                      # a smaller batch reuses the larger session (and its graph)
         key = (cap, setup.sample_len, tok.eot, tok.timestamp_begin, tok.no_timestamps, setup.max_initial_timestamp_index,
-               self.keep_full_logprobs)
+               self.keep_full_logprobs, self.small_batch_rows)
         if ses is not None and ses["key"] == key:
             return ses
         self._session = ses = None
@@ -367,14 +371,91 @@ class CudaEngine:
         ses["seq_ids"] = _i32(list(range(cap)), dev)
         ses["logits"] = torch.empty((cap, V), dtype=torch.float32, device=dev)
         ses["xs"] = torch.empty((cap, D), dtype=torch.float32, device=dev)
+        ses["last_full"] = torch.zeros((cap, V), dtype=torch.float32, device=dev)   # filtered log-softmax row at the limit
         ses["suppress"] = torch.zeros(V, dtype=torch.uint8, device=dev)
         ses["blank"] = torch.zeros(V, dtype=torch.uint8, device=dev)
         ses["cfg"] = nat.DecodeCfg(n_vocab=V, eot=tok.eot, timestamp_begin=tok.timestamp_begin,
                                    no_timestamps=tok.no_timestamps,
                                    max_initial_ts=-1 if setup.max_initial_timestamp_index is None else setup.max_initial_timestamp_index,
                                    sample_len=setup.sample_len, n_ctx=n_ctx, tokens_ld=n_ctx + 1)
+        ses["steps"] = self._steps_descriptor(ses) if self.small_batch_rows > 0 else None
         self._session = ses
         return ses
+
+    def _steps_descriptor(self, ses):
+        """Arguments of the persistent small-batch decode kernel (wts_decode_steps): float32 weights + this session's
+        caches, token state and scratch.  None when the model's dimensions are outside what the kernel supports."""
+        d, w, dev = self.dims, self.w, self.dev
+        D, H, L, V = d.n_text_state, d.n_text_head, d.n_text_layer, d.n_vocab
+        if D % 128 != 0 or D > 1280 or D != 64 * H:
+            return None
+        st8, cap = ses["st8"], ses["cap"]
+        layers = (nat.DecLayer * L)()
+        for li, blk in enumerate(w.dec):
+            a, c, y = blk.attn, blk.cross, layers[li]
+            y.ln1_g, y.ln1_b, y.w_qkv, y.b_qkv = a.ln_g.data_ptr(), a.ln_b.data_ptr(), a.qkv_f32.data_ptr(), a.qkv_b.data_ptr()
+            y.w_o, y.b_o = a.out_f32.data_ptr(), a.out_b.data_ptr()
+            y.ln2_g, y.ln2_b, y.w_cq, y.b_cq = c.ln_g.data_ptr(), c.ln_b.data_ptr(), c.q_f32.data_ptr(), c.q_b.data_ptr()
+            y.w_co, y.b_co = c.out_f32.data_ptr(), c.out_b.data_ptr()
+            y.ln3_g, y.ln3_b = blk.mlp_ln_g.data_ptr(), blk.mlp_ln_b.data_ptr()
+            y.w_fc1, y.b_fc1, y.w_fc2, y.b_fc2 = blk.fc1_f32.data_ptr(), blk.fc1_b.data_ptr(), blk.fc2_f32.data_ptr(), blk.fc2_b.data_ptr()
+            y.self_k, y.self_v = st8["sk"][li].data_ptr(), st8["sv"][li].data_ptr()
+            y.cross_k16, y.cross_v16 = st8["ck"][li].data_ptr(), st8["cv"][li].data_ptr()
+            y.cross_k_align, y.head_slot = st8["ckal"][li].data_ptr(), w.head_slot[li].data_ptr()
+        raw = np.frombuffer(bytes(layers), dtype=np.uint8).copy()
+        f32 = dict(dtype=torch.float32, device=dev)
+        keep = dict(layers=torch.from_numpy(raw).to(dev), x=torch.zeros((cap, D), **f32), qkv=torch.zeros((cap, 3 * D), **f32),
+                    att=torch.zeros((cap, D), **f32), q=torch.zeros((cap, D), **f32), mid=torch.zeros((cap, 4 * D), **f32),
+                    sync=torch.zeros(4, dtype=torch.int32, device=dev))
+        p = nat.DecodeSteps()
+        p.layers = keep["layers"].data_ptr()
+        p.emb, p.pos, p.ln_g, p.ln_b = w.emb.data_ptr(), w.dec_pos.data_ptr(), w.ln_g.data_ptr(), w.ln_b.data_ptr()
+        p.tokens, p.n_tokens, p.n_prompt, p.done = (ses[k].data_ptr() for k in ("tokens", "n_tokens", "n_prompt", "done"))
+        p.logprobs, p.qk_buf = ses["logprobs"].data_ptr(), ses["qk_buf"].data_ptr()
+        p.full = ses["full"].data_ptr() if ses["full"] is not None else None
+        p.last_full = ses["last_full"].data_ptr()
+        p.suppress, p.blank = ses["suppress"].data_ptr(), ses["blank"].data_ptr()
+        p.x, p.qkv, p.att, p.q, p.mid = (keep[k].data_ptr() for k in ("x", "qkv", "att", "q", "mid"))
+        p.logits, p.sync = ses["logits"].data_ptr(), keep["sync"].data_ptr()
+        p.cfg = ses["cfg"]
+        p.n_layer, p.D, p.H, p.n_ctx, p.n_audio_ctx = L, D, H, d.n_text_ctx, N_CTX_AUDIO
+        p.n_slots, p.cap, p.lp_ld, p.qk_rows = max(1, len(self.m.heads)), cap, ses["qk_rows"], ses["qk_rows"]
+        return dict(args=p, keep=keep)
+
+    def _step_graph(self, ses):
+        """ONE captured CUDA graph of a per-operator decode step (captured on first use; the capture itself runs no
+        step — the warm-up call before it is NOT a decode step of the caller: it is undone by restoring the state)."""
+        if ses["graph"] is not None:
+            return ses["graph"]
+        dev = self.dev
+        # warm-up outside capture on a scratch copy of the token state (every kernel must have run once: lazy module
+        # loading and cudaFuncSetAttribute are not capturable)
+        saved = {k: ses[k].clone() for k in ("tokens", "n_tokens", "done", "logprobs")}
+        self._step(ses)
+        torch.cuda.synchronize(dev)
+        for k, v in saved.items():
+            ses[k].copy_(v)
+        graph = torch.cuda.CUDAGraph()
+        cap_stream = torch.cuda.Stream(device=dev)
+        cap_stream.wait_stream(torch.cuda.current_stream(dev))
+        l0 = self.launches
+        with torch.cuda.stream(cap_stream):
+            with torch.cuda.graph(graph, stream=cap_stream):
+                self._step(ses)      # recorded, not executed
+        ses["per_step"] = self.launches - l0
+        self.launches = l0
+        torch.cuda.current_stream(dev).wait_stream(cap_stream)
+        ses["graph"] = graph
+        return graph
+
+    def _run_steps(self, ses, n_steps, n_active):
+        """Up to n_steps decoder steps for the (<= small_batch_rows) sequences still decoding, in ONE cooperative
+        launch.  Returns nothing; the caller polls `done`."""
+        sd = ses["steps"]
+        p = sd["args"]
+        p.n_steps, p.max_rows = int(n_steps), int(n_active)
+        nat.check(nat.lib.wts_decode_steps(ctypes.byref(p), self._st()), "wts_decode_steps")
+        self.launches += 1
 
     def _select(self, ses, logits, rows):
         d = self.dims
@@ -382,7 +463,7 @@ class CudaEngine:
                                             ses["blank"].data_ptr(), ses["tokens"].data_ptr(), ses["n_tokens"].data_ptr(),
                                             ses["n_prompt"].data_ptr(), ses["done"].data_ptr(), ses["logprobs"].data_ptr(),
                                             ses["qk_rows"], ses["full"].data_ptr() if ses["full"] is not None else None,
-                                            rows, self._st()), "wts_decode_select")
+                                            ses["last_full"].data_ptr(), rows, self._st()), "wts_decode_select")
         self.launches += 1
 
     def _step(self, ses):
@@ -477,34 +558,30 @@ class CudaEngine:
         steps_done = 0
         ph = self.phase("decode_steps")
         ph.__enter__()
-        if self.use_graph and ses["graph"] is None and max_steps > 4:
-            self._step(ses)              # warm-up outside capture
-            steps_done = 1
-            torch.cuda.synchronize(dev)
-            graph = torch.cuda.CUDAGraph()
-            cap_stream = torch.cuda.Stream(device=dev)
-            cap_stream.wait_stream(torch.cuda.current_stream(dev))
-            l0 = self.launches
-            with torch.cuda.stream(cap_stream):
-                with torch.cuda.graph(graph, stream=cap_stream):
-                    self._step(ses)      # recorded, not executed
-            ses["per_step"] = self.launches - l0
-            self.launches = l0
-            torch.cuda.current_stream(dev).wait_stream(cap_stream)
-            ses["graph"] = graph
-        graph = ses["graph"] if self.use_graph else None
         done = ses["done"]
-        while steps_done < max_steps:
-            chunk = min(8, max_steps - steps_done)
-            for _ in range(chunk):
-                if graph is not None:
-                    graph.replay()
-                    self.launches += ses["per_step"]
-                else:
-                    self._step(ses)
+        n_active = B
+        while steps_done < max_steps and n_active > 0:
+            left = max_steps - steps_done
+            if ses["steps"] is not None and n_active <= self.small_batch_rows:
+                # few sequences left: one persistent launch runs up to 32 whole steps (it stops by itself when all are done)
+                chunk = min(32, left)
+                self._run_steps(ses, chunk, n_active)
+                self.small_batch_steps += chunk
+            else:
+                chunk = min(8, left)
+                graph = self._step_graph(ses) if (self.use_graph and max_steps > 4) else None
+                for _ in range(chunk):
+                    if graph is not None:
+                        graph.replay()
+                        self.launches += ses["per_step"]
+                    else:
+                        self._step(ses)
             steps_done += chunk
-            if bool((done != 0).all().item()):
-                break
+            n_active = int((done == 0).sum().item())
+        if ses["steps"] is not None:
+            flags = ses["steps"]["keep"]["sync"].cpu().numpy()
+            if flags[1] != 0:
+                raise nat.WtsError("wts_decode_steps: grid barrier timed out (results invalid)")
         ph.__exit__()
         self.decode_steps_run = getattr(self, "decode_steps_run", 0) + steps_done
         if self.profile:
@@ -524,6 +601,11 @@ class CudaEngine:
         if full is not None:
             self.full_logprobs.append(full[:B, :max_rows].clone())
             full = self.full_logprobs[-1]
+        limit_rows = [b for b in range(B) if int(done_h[b]) == 2]
+        last_full_h = {}
+        if limit_rows:      # windows that ran into the decoding limit: the reference may need chunk_logprobs[-1][fallback]
+            lf = ses["last_full"][torch.as_tensor(limit_rows, device=dev)].cpu()
+            last_full_h = {b: lf[i] for i, b in enumerate(limit_rows)}
         records = []
         for b, job in enumerate(jobs):
             n = int(n_tok_h[b] - P[b])
@@ -533,7 +615,9 @@ class CudaEngine:
             gid = len(self.window_index)
             self.window_index.append((buf_idx, b))
             last_lp = None
-            if full is not None:
+            if b in last_full_h:
+                last_lp = (lambda t, row=last_full_h[b]: float(row[t]))
+            elif full is not None:
                 last_lp = (lambda t, bb=b, rr=rows - 1, ff=full: float(ff[bb, rr, t].item()))
             records.append(WindowRecord(seek=job["seek"], segment_size=job["segment_size"], prompt=prompts[b],
                                         tokens=sampled, logprobs=lp_h[b, :rows].copy(), ended_by_eot=ended,

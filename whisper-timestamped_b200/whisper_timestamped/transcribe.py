@@ -196,10 +196,12 @@ def transcribe_timestamped(
     # ---- language (T.py:811-820 + upstream detection on the first window of the file)
     language_probs = None
     mels = [eng.log_mel(audio[s:e]) for (s, e) in cuts]
+    language_detected = False
     if language is None:
         if not is_multilingual:
             language = "en"
         else:
+            language_detected = True
             tok0 = get_tokenizer(True, num_languages=num_languages)
             language, language_probs = eng.detect_language(mels[0], tok0)
     language = language.lower() if language else language
@@ -222,6 +224,8 @@ def transcribe_timestamped(
             break
         records = eng.decode_windows(jobs, setup)
         for job, rec in zip(jobs, records):
+            if language_detected and job["stream"] == 0 and not streams[0].records:
+                rec.mel_from_language_detection = True        # first window of the file, see WindowRecord.max_duration
             streams[job["stream"]].consume(rec, tokenizer, no_speech_threshold, logprob_threshold,
                                            condition_on_previous_text)
 

@@ -82,6 +82,7 @@ class WindowRecord:
     temperature: float = 0.0
     language: Optional[str] = None
     last_row_logprobs: object = None   # callable(token) -> logprob at the last row (rare fallback path)
+    mel_from_language_detection: bool = False   # see max_duration
 
     @property
     def n_rows(self):
@@ -94,7 +95,15 @@ class WindowRecord:
 
     @property
     def max_duration(self):
-        """find_start_padding(mfcc) // 2 (T.py:1556-1558): None unless the window's mel is zero-padded."""
+        """find_start_padding(mfcc) // 2 (T.py:1556-1558): None unless the window's mel is zero-padded.
+
+        One more None: when the language is auto-detected, the reference's conv1 hook first fires on upstream's
+        detect_language pass (T.py:795-799: `mfcc` is only set while it is None) and `mfcc` is not replaced before
+        the NEXT window starts (T.py:708).  The first window of the file is therefore aligned against the
+        detection mel — the first 30 s of the log-mel of the zero-PADDED AUDIO, whose tail columns are a negative
+        constant, not zero — so find_start_padding() finds no padding and no mask is applied."""
+        if self.mel_from_language_detection:
+            return None
         return self.segment_size // 2 if self.segment_size < N_FRAMES else None
 
 
