@@ -22,7 +22,9 @@
 extern "C" {
 #endif
 
-#define WTS_VERSION 100
+#define WTS_VERSION 101
+#define WTS_SEG_NONPOSITIVE 1
+#define WTS_SEG_PITCH16 2
 
 /* One alignment problem (= one speech segment handed to perform_word_alignment, T.py:1428).
  * Built on the host, copied to the device by the caller, consumed by the kernels. */
@@ -36,8 +38,12 @@ typedef struct WtsSegDesc {
     int32_t F;         /* number of frames in the slice (= end_token - start_token)             */
     int32_t max_dur;   /* padding limit in frames (find_start_padding(mfcc)//2, T.py:1556-1558),
                           <=0 when there is no padding                                          */
-    int32_t flags;     /* bit 0: the float32 cost matrix is <= 0 everywhere with cost[0,0] < 0 (true for the
-                          output of wts_attn_prep_batch): enables the integer-compare DTW fast path  */
+    int32_t flags;     /* bit 0 (WTS_SEG_NONPOSITIVE): the float32 cost matrix is <= 0 everywhere with
+                          cost[0,0] < 0 (true for the output of wts_attn_prep_batch): enables the
+                          integer-compare DTW fast path.
+                          bit 1 (WTS_SEG_PITCH16): rows of the cost matrix are padded to 16 bytes, i.e. the
+                          row pitch is (F + 3) & ~3 elements instead of F (padding columns hold zeros): lets
+                          the DTW kernel stage rows with 16-byte bulk copies                      */
     int64_t cost_off;  /* element offset of this segment's [T,F] matrix in the cost buffer      */
     int64_t jumps_off; /* element offset of this segment's T+1 jumps in the jumps buffer        */
     int64_t dir_off;   /* uint32 offset of this segment's direction words in the DTW workspace  */

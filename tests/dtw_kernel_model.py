@@ -130,3 +130,100 @@ def model_dtw(cost):
         i -= 1
     jumps[0] = 0
     return jumps
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Model of the single-strip fast path (dtw.cu: dtw_small_kernel): un-skewed 3-tile ring + mirror of tile 0, one
+# 128-byte bulk copy per row and tile, per-lane read base p_L = (32 t - L + 1) mod 96 advanced once per tile.
+# `late=True` lets every bulk copy land at the last possible moment (just before the mbarrier wait of its tile),
+# `late=False` at issue time: the kernel must be right for both, i.e. no slot is overwritten while still needed and
+# no slot is read before its tile's wait.
+SM_TC, SM_NT = 32, 3
+SM_RING = SM_TC * SM_NT
+SM_PITCH = SM_RING + SM_TC
+
+
+def model_dtw_small(cost, late=False):
+    cost = np.asarray(cost, dtype=np.float32)
+    T, F = cost.shape
+    assert T <= RS
+    P = (F + 3) & ~3
+    padded = np.zeros((T, P), dtype=np.float32)
+    padded[:, :F] = cost
+    niter = niter_of(F)
+    ntile = (P + SM_TC - 1) // SM_TC
+    lanes = np.arange(32)
+    tile = np.zeros((32, SM_PITCH), dtype=np.float32)
+    dirs = np.zeros((2 * niter, 32), dtype=np.uint32)
+    pending = {}
+
+    def issue(t):
+        ncol = min(SM_TC, P - SM_TC * t)
+        slot = t % SM_NT
+        writes = []
+        for L in range(1, T + 1):
+            data = padded[L - 1, SM_TC * t: SM_TC * t + ncol]
+            writes.append((L, slot * SM_TC, data))
+            if slot == 0:
+                writes.append((L, SM_RING, data))
+        pending[t] = writes
+
+    def land(t):
+        for (L, off, data) in pending.pop(t, []):
+            tile[L, off: off + len(data)] = data
+
+    cur = np.full(32, np.inf)
+    upprev = np.full(32, np.inf)
+    upprev[1] = 0.0
+    acc = np.zeros(32, dtype=np.uint32)
+    p = (SM_RING - lanes + 1) % SM_RING
+    issue(0)
+    for t in range(niter):
+        if t < ntile:
+            land(t)                                    # mbarrier wait: tile t is complete from here on
+        if t + 1 < ntile:
+            issue(t + 1)
+            if not late:
+                land(t + 1)
+        for k in range(32):
+            assert np.all(p + k < SM_PITCH)
+            l = tile[lanes, p + k].astype(np.float64)
+            up = np.concatenate(([cur[0]], cur[:-1]))
+            c1, c2, c3 = upprev + l, cur + l, up + l
+            upprev = up
+            p2 = c2 < c1
+            m = np.where(p2, c2, c1)
+            p3 = c3 < m
+            cur = np.where(p3, c3, m)
+            if k % 16 == 0:
+                acc[:] = 0
+            acc |= (p2.astype(np.uint32) << np.uint32(2 * (k % 16))) | (p3.astype(np.uint32) << np.uint32(2 * (k % 16) + 1))
+            if k % 16 == 15:
+                dirs[2 * t + k // 16] = acc
+        p = (p + SM_TC) % SM_RING
+    # row-wise backtrack on the packed words (same arithmetic as dtw_backtrack_jumps)
+    jumps = np.zeros(T + 1, dtype=np.int32)
+    jumps[T] = F - 1
+    i, j = T - 1, F - 1
+    while i > 0:
+        ln = i + 1
+        s = j + ln - 1
+        w, pos = s >> 4, s & 15
+        while True:
+            x = int(dirs[w, ln])
+            lo, hi = x & 0x55555555, (x >> 1) & 0x55555555
+            nonleft = 0x55555555 & ~(lo & ~hi)
+            msk = nonleft & (0xffffffff >> (30 - 2 * pos))
+            if msk:
+                kf = (msk.bit_length() - 1) >> 1
+                break
+            if w == 0:
+                kf = 0
+                break
+            w, pos = w - 1, 15
+        jj = max(w * 16 + kf - (ln - 1), 0)
+        is_up = (x >> (2 * kf + 1)) & 1
+        jumps[i] = jj
+        j = jj - 1 if (not is_up and jj > 0) else jj
+        i -= 1
+    return jumps

@@ -26,11 +26,11 @@ def _dev():
 
 def run_dtw(mats, dtype=np.float32, want_path=False, want_status=False):
     """mats: list of [T,F] arrays -> list of jumps (and paths) from the CUDA kernel."""
-    from whisper_timestamped.alignment import plan_segments, dtw, split_jumps
+    from whisper_timestamped.alignment import plan_segments, dtw, split_jumps, put_cost_matrix
     plan = plan_segments([(0, 0, None, m.shape[0], 0, m.shape[1], 0) for m in mats])
     host = np.zeros(plan.cost_elems, dtype=dtype)
     for s, m in zip(plan.segs, mats):
-        host[s["cost_off"]: s["cost_off"] + m.size] = m.astype(dtype).reshape(-1)
+        put_cost_matrix(host, s, m.astype(dtype))
     cost = torch.from_numpy(host).to(_dev())
     out = dtw(cost, plan, want_path=want_path, want_status=want_status)
     torch.cuda.synchronize()
@@ -145,8 +145,9 @@ def test_dtw_nonpositive_fast_path_vs_oracle():
             mats.append(c)
     plan = plan_segments([(0, 0, None, m.shape[0], 0, m.shape[1], 0) for m in mats], nonpositive=True)
     host = np.zeros(plan.cost_elems, dtype=np.float32)
+    from whisper_timestamped.alignment import put_cost_matrix
     for s, m in zip(plan.segs, mats):
-        host[s["cost_off"]: s["cost_off"] + m.size] = m.reshape(-1)
+        put_cost_matrix(host, s, m)
     out = dtw(torch.from_numpy(host).to(_dev()), plan)
     torch.cuda.synchronize()
     jl = split_jumps(out["jumps"].cpu().numpy(), plan)
@@ -166,7 +167,7 @@ def test_dtw_status_flags_non_finite():
 def _prep_case(qk_full, N, T, F, f0, max_dur, last_row=None):
     """qk_full [N, Trows, 1500] float32 -> (gpu cost [T,F] float32, gpu jumps).  The DTW runs twice — generic
     float64 compares and the integer-compare fast path for non-positive costs — and both must agree."""
-    from whisper_timestamped.alignment import plan_segments, attn_prep, dtw, split_jumps
+    from whisper_timestamped.alignment import plan_segments, attn_prep, dtw, split_jumps, cost_matrix
     qk = torch.from_numpy(qk_full[None]).to(_dev()).contiguous()
     plan = plan_segments([(0, 0, last_row, T, f0, F, max_dur)])
     cost = attn_prep(qk, plan)
@@ -174,7 +175,7 @@ def _prep_case(qk_full, N, T, F, f0, max_dur, last_row=None):
     plan_fast = plan_segments([(0, 0, last_row, T, f0, F, max_dur)], nonpositive=True)
     out_fast = dtw(cost, plan_fast)
     torch.cuda.synchronize()
-    c = cost.cpu().numpy()[: T * F].reshape(T, F)
+    c = np.ascontiguousarray(cost_matrix(cost.cpu().numpy(), plan.segs[0]))
     j = split_jumps(out["jumps"].cpu().numpy(), plan)[0]
     assert np.array_equal(j, split_jumps(out_fast["jumps"].cpu().numpy(), plan_fast)[0])
     return c, j
@@ -218,7 +219,7 @@ def test_prep_random_vs_oracle_and_truncation_row():
 
 
 def test_prep_batch_many_segments_one_launch():
-    from whisper_timestamped.alignment import plan_segments, attn_prep, dtw, split_jumps
+    from whisper_timestamped.alignment import plan_segments, attn_prep, dtw, split_jumps, cost_matrix
     rng = np.random.default_rng(8)
     N, W, rows = 6, 3, 64
     qk = (2 * rng.standard_normal((W, N, rows, 1500))).astype(np.float32)
@@ -239,7 +240,7 @@ def test_prep_batch_many_segments_one_launch():
     jl = split_jumps(out["jumps"].cpu().numpy(), plan)
     for k, (w, row0, _, T, f0, F, md) in enumerate(items):
         s = plan.segs[k]
-        c = ch[s["cost_off"]: s["cost_off"] + T * F].reshape(T, F)
+        c = np.ascontiguousarray(cost_matrix(ch, s))
         ref = attn_cost(qk[w][:, row0:row0 + T], f0, f0 + F, max_duration=md or None)
         assert np.max(np.abs(c - ref)) <= PREP_ATOL, k
         _, _, j, _ = oracle.dtw_symmetric1(c.astype(np.float64))

@@ -159,7 +159,8 @@ def test_plan_segments_layout():
     plan = plan_segments([(0, 0, None, 24, 10, 300, 0), (1, 5, 40, 33, 0, 90, 50), (0, 30, None, 2, 0, 9, 0)])
     s = plan.segs
     assert s["last_row"].tolist() == [23, 40, 31]
-    assert s["cost_off"].tolist() == [0, 7200, 7200 + 2972]          # 33*90=2970 -> padded to 4
+    assert s["cost_off"].tolist() == [0, 7200, 7200 + 33 * 92]       # rows padded to 16 bytes: pitch 92 for F = 90
+    assert (s["flags"] & 2).all() and plan.cost_elems == 7200 + 33 * 92 + 2 * 12
     assert s["jumps_off"].tolist() == [0, 25, 59]
     assert plan.jumps_elems == 62 and plan.max_T == 33 and plan.max_F == 300
     assert s["dir_off"][1] == nat.lib.wts_dtw_dir_words(24, 300)

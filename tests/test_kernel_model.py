@@ -33,3 +33,23 @@ def test_model_exact_strip_boundaries():
         c = -rng.random((T, T + 17)).astype(np.float32)
         _, _, jumps, _ = oracle.dtw_symmetric1(c.astype(np.float64))
         assert np.array_equal(jumps, model_dtw(c)), T
+
+
+@pytest.mark.parametrize("late", [False, True])
+def test_small_kernel_model_matches_oracle(late):
+    """Index arithmetic of dtw_small_kernel (3-tile ring + mirror, per-tile read base, bulk copies landing early or
+    at the last moment) on negative costs incl. heavy ties, for shapes around every tile / pitch boundary."""
+    from dtw_kernel_model import model_dtw_small
+    rng = np.random.default_rng(5)
+    shapes = [(1, 1), (1, 5), (2, 3), (3, 31), (24, 300), (31, 354), (31, 32), (17, 33), (8, 63), (9, 64), (10, 65), (30, 96),
+              (31, 97), (12, 127), (13, 128), (14, 129), (24, 191), (5, 193), (31, 288), (2, 353)]
+    shapes += [(int(rng.integers(1, 32)), int(rng.integers(1, 355))) for _ in range(25)]
+    for n, (T, F) in enumerate(shapes):
+        if n % 3 == 0:
+            c = -(rng.random((T, F)).astype(np.float32) + np.float32(1e-3))
+        elif n % 3 == 1:
+            c = -np.ones((T, F), np.float32)
+        else:
+            c = -rng.integers(1, 4, (T, F)).astype(np.float32)
+        _, _, jumps, _ = oracle.dtw_symmetric1(c.astype(np.float64))
+        assert np.array_equal(jumps, model_dtw_small(c, late=late)), (T, F, late)

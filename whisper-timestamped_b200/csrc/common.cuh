@@ -38,6 +38,9 @@ void set_error(const char* fmt, ...);
 
 constexpr unsigned FULL_MASK = 0xffffffffu;
 
+// row pitch (elements) of a segment's cost matrix (WtsSegDesc.flags bit 1: rows padded to 16 bytes of float32)
+__host__ __device__ inline int seg_pitch(const WtsSegDesc& sd) { return (sd.flags & WTS_SEG_PITCH16) ? ((sd.F + 3) & ~3) : sd.F; }
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL_MASK, v, o));

@@ -40,6 +40,13 @@ __host__ __device__ inline int dtw_nstrips(int T) { return (T + RS - 1) / RS; }
 __host__ __device__ inline int dtw_niter(int F) { return (F + RS - 1 + 31) / 32; }
 __host__ __device__ inline int dtw_wpr(int F) { return 2 * dtw_niter(F); }   // dir words per lane row
 
+// segments the single-strip fast path (dtw_small_kernel, below) takes over from the general kernel
+__host__ __device__ inline bool dtw_small_eligible(const WtsSegDesc& sd)
+{
+    return (sd.flags & (WTS_SEG_NONPOSITIVE | WTS_SEG_PITCH16)) == (WTS_SEG_NONPOSITIVE | WTS_SEG_PITCH16) &&
+           sd.T >= 1 && sd.T <= RS && sd.F >= 1 && dtw_wpr(sd.F) <= DS_WORDS;
+}
+
 __device__ __forceinline__ double dinf() { return __longlong_as_double(0x7ff0000000000000LL); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -65,7 +72,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // accumulated cost is a strictly negative double (or +inf for "no predecessor") and  a < b  <=>  bits(a) >u bits(b).
 // The two fp64 compares of the dependent chain become integer compares (same results bit for bit).
 template <typename TIn, bool FIRST, bool WRITE_BND, bool NEG>
-__device__ __forceinline__ void dtw_fill_strip(const TIn* __restrict__ C, const int F, const int row0,
+__device__ __forceinline__ void dtw_fill_strip(const TIn* __restrict__ C, const int F, const int P, const int row0,
                                                const int Ts, const int niter, const uint32_t tile_a,
                                                uint32_t* __restrict__ dirs_strip,
                                                double* __restrict__ bnd, const int lane)
@@ -80,8 +87,8 @@ __device__ __forceinline__ void dtw_fill_strip(const TIn* __restrict__ C, const 
     uint32_t acc = 0;
     const uint32_t myrow_a = tile_a + lane * ROWB;
     const uint32_t laneb = lane * ES;
-    const char* Cb = reinterpret_cast<const char*>(C + (int64_t)row0 * F);   // strip row 0 (= tile row 1)
-    const uint32_t Fb = (uint32_t)F * ES;
+    const char* Cb = reinterpret_cast<const char*>(C + (int64_t)row0 * P);   // strip row 0 (= tile row 1); P = row pitch
+    const uint32_t Fb = (uint32_t)P * ES;
 
     // prologue: tile 0 (all rows), one group
     {
@@ -164,6 +171,36 @@ __device__ __forceinline__ uint32_t dtw_nonleft_mask(uint32_t x)
     return 0x55555555u & ~(lo & ~hi);
 }
 
+// ---- backtrack, one step per token row (executed redundantly by all lanes; lane 0 stores): jumps[i] = first path
+// column of token row i (T.py:1648-1652), jumps[T] = F - 1.
+__device__ __forceinline__ void dtw_backtrack_jumps(const uint32_t* dirs, const int W, const int T, const int F,
+                                                    int32_t* __restrict__ jumps, const int lane)
+{
+    int i = T - 1, j = F - 1;
+    if (lane == 0) jumps[T] = F - 1;
+    while (i > 0) {
+        const int strip = i / RS, ln = i - strip * RS + 1;
+        const uint32_t* base = dirs + (int64_t)strip * W * 32 + ln;
+        int s = j + ln - 1;
+        int w = s >> 4, pos = s & 15, kf = 0;
+        uint32_t x = 0;
+        while (true) {
+            x = base[w * 32];
+            const uint32_t m = dtw_nonleft_mask(x) & (0xffffffffu >> (30 - 2 * pos));
+            if (m) { kf = (31 - __clz(m)) >> 1; break; }
+            if (w == 0) { kf = 0; break; }
+            --w; pos = 15;
+        }
+        int jj = w * 16 + kf - (ln - 1);
+        if (jj < 0) jj = 0;
+        const bool is_up = (x >> (2 * kf + 1)) & 1u;
+        if (lane == 0) jumps[i] = jj;
+        j = (!is_up && jj > 0) ? jj - 1 : jj;       // diag or up into the previous row
+        --i;
+    }
+    if (lane == 0) jumps[0] = 0;
+}
+
 // dir field of cell (i, j)
 __device__ __forceinline__ uint32_t dtw_dir_at(const uint32_t* dirs, int W, int i, int j)
 {
@@ -179,7 +216,7 @@ __global__ void __launch_bounds__(DTW_WARPS * 32, DTW_MIN_CTAS)
 dtw_warp_kernel(const TIn* __restrict__ cost, const WtsSegDesc* __restrict__ segs, const int nseg,
                 uint32_t* __restrict__ dir_ws, double* __restrict__ bnd_ws,
                 int32_t* __restrict__ jumps_out, int32_t* __restrict__ path_out,
-                const int64_t* __restrict__ path_off, int32_t* __restrict__ path_len)
+                const int64_t* __restrict__ path_off, int32_t* __restrict__ path_len, const int skip_small)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -190,7 +227,8 @@ dtw_warp_kernel(const TIn* __restrict__ cost, const WtsSegDesc* __restrict__ seg
     if (seg >= nseg) return;
 
     const WtsSegDesc sd = segs[seg];
-    const int T = sd.T, F = sd.F;
+    if (skip_small && dtw_small_eligible(sd)) return;        // owned by dtw_small_kernel
+    const int T = sd.T, F = sd.F, P = seg_pitch(sd);
     const TIn* C = cost + sd.cost_off;
     // directions live in shared memory when the whole matrix fits one strip and DS_WORDS words per row
     // (the typical alignment problem): the row-wise backtrack then never waits on L2
@@ -214,50 +252,25 @@ dtw_warp_kernel(const TIn* __restrict__ cost, const WtsSegDesc* __restrict__ seg
         const bool neg = (sizeof(TIn) == 4) && (sd.flags & 1);
         if (neg) {
             if (strip == 0) {
-                if (more) dtw_fill_strip<TIn, true, true, true>(C, F, row0, Ts, niter, tile_a, ds, bnd, lane);
-                else      dtw_fill_strip<TIn, true, false, true>(C, F, row0, Ts, niter, tile_a, ds, bnd, lane);
+                if (more) dtw_fill_strip<TIn, true, true, true>(C, F, P, row0, Ts, niter, tile_a, ds, bnd, lane);
+                else      dtw_fill_strip<TIn, true, false, true>(C, F, P, row0, Ts, niter, tile_a, ds, bnd, lane);
             } else {
-                if (more) dtw_fill_strip<TIn, false, true, true>(C, F, row0, Ts, niter, tile_a, ds, bnd, lane);
-                else      dtw_fill_strip<TIn, false, false, true>(C, F, row0, Ts, niter, tile_a, ds, bnd, lane);
+                if (more) dtw_fill_strip<TIn, false, true, true>(C, F, P, row0, Ts, niter, tile_a, ds, bnd, lane);
+                else      dtw_fill_strip<TIn, false, false, true>(C, F, P, row0, Ts, niter, tile_a, ds, bnd, lane);
             }
         } else if (strip == 0) {
-            if (more) dtw_fill_strip<TIn, true, true, false>(C, F, row0, Ts, niter, tile_a, ds, bnd, lane);
-            else      dtw_fill_strip<TIn, true, false, false>(C, F, row0, Ts, niter, tile_a, ds, bnd, lane);
+            if (more) dtw_fill_strip<TIn, true, true, false>(C, F, P, row0, Ts, niter, tile_a, ds, bnd, lane);
+            else      dtw_fill_strip<TIn, true, false, false>(C, F, P, row0, Ts, niter, tile_a, ds, bnd, lane);
         } else {
-            if (more) dtw_fill_strip<TIn, false, true, false>(C, F, row0, Ts, niter, tile_a, ds, bnd, lane);
-            else      dtw_fill_strip<TIn, false, false, false>(C, F, row0, Ts, niter, tile_a, ds, bnd, lane);
+            if (more) dtw_fill_strip<TIn, false, true, false>(C, F, P, row0, Ts, niter, tile_a, ds, bnd, lane);
+            else      dtw_fill_strip<TIn, false, false, false>(C, F, P, row0, Ts, niter, tile_a, ds, bnd, lane);
         }
         __syncwarp();
     }
     __threadfence_block();
     __syncwarp();
 
-    // ---- backtrack, one step per token row (executed redundantly by all lanes; lane 0 stores)
-    {
-        int i = T - 1, j = F - 1;
-        if (lane == 0) jumps[T] = F - 1;
-        while (i > 0) {
-            const int strip = i / RS, ln = i - strip * RS + 1;
-            const uint32_t* base = dirs + (int64_t)strip * W * 32 + ln;
-            int s = j + ln - 1;
-            int w = s >> 4, pos = s & 15, kf = 0;
-            uint32_t x = 0;
-            while (true) {
-                x = base[w * 32];
-                const uint32_t m = dtw_nonleft_mask(x) & (0xffffffffu >> (30 - 2 * pos));
-                if (m) { kf = (31 - __clz(m)) >> 1; break; }
-                if (w == 0) { kf = 0; break; }
-                --w; pos = 15;
-            }
-            int jj = w * 16 + kf - (ln - 1);
-            if (jj < 0) jj = 0;
-            const bool is_up = (x >> (2 * kf + 1)) & 1u;
-            if (lane == 0) jumps[i] = jj;
-            j = (!is_up && jj > 0) ? jj - 1 : jj;       // diag or up into the previous row
-            --i;
-        }
-        if (lane == 0) jumps[0] = 0;
-    }
+    dtw_backtrack_jumps(dirs, W, T, F, jumps, lane);
 
     // ---- optional full path (alignment.index1s / index2s), cell by cell; tests & plots only
     if (path_out != nullptr && lane == 0) {
@@ -284,6 +297,135 @@ dtw_warp_kernel(const TIn* __restrict__ cost, const WtsSegDesc* __restrict__ seg
     }
 }
 
+// ------------------------------------------------------------------------------------ single-strip fast path
+// The typical alignment problem (T <= 31 tokens, F <= 354 frames, float32 costs <= 0 from wts_attn_prep_batch with rows
+// padded to 16 bytes) gets its own kernel, built to spend as few issue slots per anti-diagonal as the bit-exact fp64
+// recurrence allows (the general kernel above is ISSUE-bound: ~40 warp instructions per step of which the recurrence
+// needs ~17, profiles/r1c_dtw_summary.md):
+//  * staging is ONE predicated instruction per 32-column tile: every lane L (1..T) issues a 128-byte 1-D bulk copy
+//    (cp.async.bulk, TMA) of its own row's next tile; completion is counted by an mbarrier (two, alternating);
+//  * the row buffers are NOT skewed: a ring of three tiles (the tiles t-1 and t being read, t+1 in flight) plus a
+//    mirror of the first tile behind the ring, so lane L reads `row_base + 4 p_L + 4 k` at step k of a tile — an
+//    immediate offset with no wrap inside the tile (p_L = (32 t - L + 1) mod 96 advances once per tile);
+//    row pitch 128 words: bank (p_L + k) mod 32 = (1 - L + k) mod 32 is distinct over the lanes;
+//  * directions stay in shared memory (2 bits per cell) for the row-wise backtrack.
+// Same recurrence, same tie-breaks, same packed direction words as dtw_fill_strip<float, true, false, true>.
+constexpr int SM_TC = 32;                    // columns per tile
+constexpr int SM_NT = 3;                     // tiles in the ring
+constexpr int SM_RINGB = SM_NT * SM_TC * 4;  // ring bytes per row
+constexpr int SM_PITCHB = (SM_NT + 1) * SM_TC * 4;   // + mirror of tile 0
+constexpr int SM_TILE_BYTES = 32 * SM_PITCHB;        // rows 0..31 (row 0 = the virtual row above, stays zero)
+constexpr int SM_WARP_BYTES = SM_TILE_BYTES + DS_WORDS * 32 * 4 + 16;
+#ifndef DTW_SMALL_WARPS
+#define DTW_SMALL_WARPS 2
+#endif
+
+__device__ __forceinline__ void mbar_init1(uint32_t bar) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar)); }
+__device__ __forceinline__ void mbar_arrive_expect(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "DTW_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DTW_DONE;\n\t"
+        "bra DTW_WAIT;\n\t"
+        "DTW_DONE:\n\t"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(DTW_SMALL_WARPS * 32)
+dtw_small_kernel(const float* __restrict__ cost, const WtsSegDesc* __restrict__ segs, const int nseg,
+                 int32_t* __restrict__ jumps_out)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int seg = blockIdx.x * DTW_SMALL_WARPS + warp;
+    if (seg >= nseg) return;
+    const WtsSegDesc sd = segs[seg];
+    if (!dtw_small_eligible(sd)) return;                     // the general kernel owns this segment
+    unsigned char* my = smem_raw + (size_t)warp * SM_WARP_BYTES;
+    const uint32_t tile_a = smem_u32(my);
+    uint32_t* dirs = reinterpret_cast<uint32_t*>(my + SM_TILE_BYTES);
+    const uint32_t bar0 = tile_a + SM_TILE_BYTES + DS_WORDS * 32 * 4;
+
+    const int T = sd.T, F = sd.F, P = (F + 3) & ~3;
+    const float* C = cost + sd.cost_off;
+    // zero the row buffers once: cells read before their tile arrives (j < 0), rows beyond T and the virtual row 0
+    // must hold finite values (INF + 0 stays INF; they never feed a cell of the matrix)
+    {
+        float4* z = reinterpret_cast<float4*>(my);
+        for (int k = lane; k < SM_TILE_BYTES / 16; k += 32) z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (lane == 0) {
+        mbar_init1(bar0);
+        mbar_init1(bar0 + 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy zeros ordered before async-proxy writes
+    __syncwarp();
+
+    const int niter = dtw_niter(F);                          // 32-step tiles of the wavefront
+    const int ntile = (P + SM_TC - 1) / SM_TC;               // column tiles of the matrix
+    const bool owner = lane >= 1 && lane <= T;
+    const char* myrow = reinterpret_cast<const char*>(C + (int64_t)(lane - 1) * P);
+    const uint32_t myrow_a = tile_a + lane * SM_PITCHB;
+
+    auto issue_tile = [&](int t) {                           // columns [32 t, 32 t + 31] of every row -> ring slot t % 3
+        const int ncol = min(SM_TC, P - SM_TC * t);
+        const uint32_t bytes = (uint32_t)ncol * 4u;
+        const int slot = t % SM_NT;
+        const uint32_t bar = bar0 + 8u * (t & 1);
+        if (lane == 0) mbar_arrive_expect(bar, bytes * (uint32_t)T * (slot == 0 ? 2u : 1u));
+        if (owner) {
+            const char* src = myrow + (size_t)t * SM_TC * 4;
+            bulk_g2s(myrow_a + slot * SM_TC * 4, src, bytes, bar);
+            if (slot == 0) bulk_g2s(myrow_a + SM_RINGB, src, bytes, bar);      // mirror behind the ring
+        }
+    };
+
+    const double INF = dinf();
+    double cur = INF, upprev = INF;
+    if (lane == 1) upprev = 0.0;                             // seeds cm[0,0] = 0 + lm[0,0]
+    uint32_t acc = 0;
+    uint32_t pb = (uint32_t)(((SM_NT * SM_TC) - lane + 1) % (SM_NT * SM_TC)) * 4u;   // 4 * ((32 t - L + 1) mod 96), t = 0
+    issue_tile(0);
+    for (int t = 0; t < niter; ++t) {
+        if (t < ntile) mbar_wait_parity(bar0 + 8u * (t & 1), (uint32_t)((t >> 1) & 1));
+        if (t + 1 < ntile) issue_tile(t + 1);
+        const uint32_t rd = myrow_a + pb;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            const double l = (double)lds<float>(rd + 4 * k);
+            const double up = __shfl_up_sync(FULL_MASK, cur, 1);
+            const double c1 = upprev + l, c2 = cur + l, c3 = up + l;
+            upprev = up;
+            // all sums are strictly negative doubles or +inf: a < b  <=>  bits(a) >u bits(b)
+            const bool p2 = (unsigned long long)__double_as_longlong(c2) > (unsigned long long)__double_as_longlong(c1);
+            const double m = p2 ? c2 : c1;
+            const bool p3 = (unsigned long long)__double_as_longlong(c3) > (unsigned long long)__double_as_longlong(m);
+            cur = p3 ? c3 : m;
+            if ((k & 15) == 0) acc = 0;
+            if (p2) acc |= 1u << (2 * (k & 15));
+            if (p3) acc |= 2u << (2 * (k & 15));
+            if ((k & 15) == 15) dirs[(2 * t + (k >> 4)) * 32 + lane] = acc;
+        }
+        pb += SM_TC * 4;
+        if (pb >= (uint32_t)SM_RINGB) pb -= SM_RINGB;
+    }
+    __syncwarp();
+    dtw_backtrack_jumps(dirs, 2 * niter, T, F, jumps_out + sd.jumps_off, lane);
+}
+
 // status: 1 when the segment's local-cost matrix holds a non-finite value (the situation in which
 // the reference's dtw() can end with "No warping path found").
 template <typename TIn>
@@ -294,7 +436,7 @@ __global__ void dtw_status_kernel(const TIn* __restrict__ cost, const WtsSegDesc
     if (seg >= nseg) return;
     const WtsSegDesc sd = segs[seg];
     const TIn* C = cost + sd.cost_off;
-    const int64_t n = (int64_t)sd.T * sd.F;
+    const int64_t n = (int64_t)sd.T * seg_pitch(sd);       // padding columns hold zeros (finite)
     int bad = 0;
     for (int64_t k = threadIdx.x; k < n; k += blockDim.x) bad |= !isfinite((double)C[k]);
     bad = __syncthreads_or(bad);
@@ -331,15 +473,26 @@ extern "C" int wts_dtw_batch(const void* d_cost, int32_t cost_is_f64, const WtsS
         const size_t smem = (size_t)DTW_WARPS * (TILE_WORDS * sizeof(double) + DS_WORDS * 32 * sizeof(uint32_t));
         WTS_CUDA_CHECK(cudaFuncSetAttribute(dtw_warp_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dtw_warp_kernel<double><<<grid, DTW_WARPS * 32, smem, st>>>(
-            (const double*)d_cost, d_segs, nseg, d_dir_ws, d_bnd_ws, d_jumps, d_path, d_path_off, d_path_len);
+            (const double*)d_cost, d_segs, nseg, d_dir_ws, d_bnd_ws, d_jumps, d_path, d_path_off, d_path_len, 0);
         WTS_LAUNCH_CHECK();
         if (d_status) { dtw_status_kernel<double><<<nseg, 128, 0, st>>>((const double*)d_cost, d_segs, nseg, d_status); WTS_LAUNCH_CHECK(); }
     } else {
+        // single-strip fast path (dtw_small_kernel) for the segments that qualify; it produces jumps only, so a
+        // request for full paths keeps everything in the general kernel.  WTS_DTW_SMALL=0 turns it off.
+        static const int small_on = [] { const char* e = getenv("WTS_DTW_SMALL"); return e ? atoi(e) : 1; }();
+        const int use_small = small_on && d_path == nullptr;
         const size_t smem = (size_t)DTW_WARPS * (TILE_WORDS * sizeof(float) + DS_WORDS * 32 * sizeof(uint32_t));
         WTS_CUDA_CHECK(cudaFuncSetAttribute(dtw_warp_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dtw_warp_kernel<float><<<grid, DTW_WARPS * 32, smem, st>>>(
-            (const float*)d_cost, d_segs, nseg, d_dir_ws, d_bnd_ws, d_jumps, d_path, d_path_off, d_path_len);
+            (const float*)d_cost, d_segs, nseg, d_dir_ws, d_bnd_ws, d_jumps, d_path, d_path_off, d_path_len, use_small);
         WTS_LAUNCH_CHECK();
+        if (use_small) {
+            const size_t smem_s = (size_t)DTW_SMALL_WARPS * SM_WARP_BYTES;
+            WTS_CUDA_CHECK(cudaFuncSetAttribute(dtw_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+            dtw_small_kernel<<<(nseg + DTW_SMALL_WARPS - 1) / DTW_SMALL_WARPS, DTW_SMALL_WARPS * 32, smem_s, st>>>(
+                (const float*)d_cost, d_segs, nseg, d_jumps);
+            WTS_LAUNCH_CHECK();
+        }
         if (d_status) { dtw_status_kernel<float><<<nseg, 128, 0, st>>>((const float*)d_cost, d_segs, nseg, d_status); WTS_LAUNCH_CHECK(); }
     }
     return 0;

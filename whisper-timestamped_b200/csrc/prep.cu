@@ -81,9 +81,10 @@ prep_rows_kernel(const float* __restrict__ qk, const int N, const int Tmax, cons
         else        { for (int c = lane; c < F; c += 32) acc[c] += mbuf[c] * inv; }
         __syncwarp();
     }
-    float* dst = cost + sd.cost_off + (int64_t)t * F;
+    const int P = seg_pitch(sd);
+    float* dst = cost + sd.cost_off + (int64_t)t * P;
     const float fn = (float)N;
-    for (int c = lane; c < F; c += 32) dst[c] = acc[c] / fn;
+    for (int c = lane; c < P; c += 32) dst[c] = c < F ? acc[c] / fn : 0.f;     // padding columns (pitch) hold zeros
 }
 
 __global__ void __launch_bounds__(256)
@@ -91,21 +92,21 @@ prep_cols_kernel(const WtsSegDesc* __restrict__ segs, float* __restrict__ cost)
 {
     __shared__ float red[8];
     const WtsSegDesc sd = segs[blockIdx.x];
-    const int T = sd.T, F = sd.F;
+    const int T = sd.T, F = sd.F, P = seg_pitch(sd);
     float* M = cost + sd.cost_off;
     const bool masked = sd.max_dur > 0 && sd.f0 < sd.max_dur;
     float vmin = INFINITY;
     for (int c = threadIdx.x; c < F; c += blockDim.x) {
         float ss = 0.f;
         for (int t = 0; t < T; ++t) {
-            const float v = M[(int64_t)t * F + c];
+            const float v = M[(int64_t)t * P + c];
             ss += v * v;
         }
         const float nrm = sqrtf(ss);
         for (int t = 0; t < T; ++t) {
-            float v = -(M[(int64_t)t * F + c] / nrm);
+            float v = -(M[(int64_t)t * P + c] / nrm);
             if (masked && t < T - 1 && c >= sd.max_dur) v = 0.f;
-            M[(int64_t)t * F + c] = v;
+            M[(int64_t)t * P + c] = v;
             vmin = fminf(vmin, v);
         }
     }
@@ -133,7 +134,7 @@ __global__ void disfluency_kernel(const float* __restrict__ cost, const WtsSegDe
         if (t < sd.T) {
             const int begin = j[t], end = j[t + 1];
             if (end - begin >= 3 && begin >= 0 && end <= sd.F)
-                left = wts_disfluency_left(cost + sd.cost_off + (int64_t)t * sd.F, begin, end - begin, 0.02, 3.0);
+                left = wts_disfluency_left(cost + sd.cost_off + (int64_t)t * seg_pitch(sd), begin, end - begin, 0.02, 3.0);
         }
         o[t] = left;
     }

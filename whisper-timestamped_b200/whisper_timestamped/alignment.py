@@ -11,6 +11,8 @@ import torch
 
 from . import _native as nat
 
+SEG_NONPOSITIVE, SEG_PITCH16 = 1, 2            # WtsSegDesc.flags (include/wts.h)
+
 
 @dataclass
 class AlignPlan:
@@ -51,10 +53,9 @@ def plan_segments(items, nonpositive=False) -> AlignPlan:
         s = segs[i]
         s["window"], s["row0"], s["last_row"], s["T"], s["f0"], s["F"] = window, row0, last_row, T, f0, F
         s["max_dur"] = max_dur or 0
-        s["flags"] = 1 if nonpositive else 0
+        s["flags"] = (SEG_NONPOSITIVE if nonpositive else 0) | SEG_PITCH16
         s["cost_off"], s["jumps_off"], s["dir_off"], s["bnd_off"] = cost, jumps, dirw, bnd
-        cost += T * F
-        cost = (cost + 3) & ~3                      # keep every matrix 16-byte aligned
+        cost += T * seg_pitch(s)                    # rows padded to 16 bytes: every row (hence every matrix) is 16-byte aligned
         jumps += T + 1
         dirw += nat.lib.wts_dtw_dir_words(T, F)
         bnd += nat.lib.wts_dtw_bnd_doubles(T, F)
@@ -62,6 +63,28 @@ def plan_segments(items, nonpositive=False) -> AlignPlan:
     work = segs["T"].astype(np.int64) * segs["F"].astype(np.int64)
     order = np.argsort(-work, kind="stable")
     return AlignPlan(segs, cost, jumps, max(dirw, 1), max(bnd, 1), max_T, max_F, order)
+
+
+def seg_pitch(seg) -> int:
+    """Row pitch (float32 elements) of a segment's cost matrix: WtsSegDesc.flags bit 1 = rows padded to 16 bytes."""
+    F = int(seg["F"])
+    return (F + 3) & ~3 if int(seg["flags"]) & SEG_PITCH16 else F
+
+
+def cost_matrix(cost_host: np.ndarray, seg) -> np.ndarray:
+    """[T, F] view of one segment's matrix inside a host copy of the cost buffer."""
+    T, F, P = int(seg["T"]), int(seg["F"]), seg_pitch(seg)
+    off = int(seg["cost_off"])
+    return cost_host[off: off + T * P].reshape(T, P)[:, :F]
+
+
+def put_cost_matrix(cost_host: np.ndarray, seg, m) -> None:
+    """Writes a [T, F] matrix into a host cost buffer laid out by plan_segments (padding columns zeroed)."""
+    T, F, P = int(seg["T"]), int(seg["F"]), seg_pitch(seg)
+    off = int(seg["cost_off"])
+    view = cost_host[off: off + T * P].reshape(T, P)
+    view[:, F:] = 0
+    view[:, :F] = np.asarray(m).reshape(T, F)
 
 
 def _segs_to_device(arr: np.ndarray, device) -> torch.Tensor:
