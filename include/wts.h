@@ -260,8 +260,9 @@ typedef struct WtsDecodeSteps {
     const uint8_t *suppress, *blank;
     float *x, *qkv, *att, *q, *mid, *logits;                         /* scratch: [cap, D], [cap, 3D], [cap, D], [cap, D], [cap, 4D], [cap, V] */
     uint32_t* sync;                                                  /* [4]: barrier counter, error flag, steps completed, spare */
+    uint64_t* prof;                                                  /* optional: %globaltimer of CTA 0 after every grid barrier */
     WtsDecodeCfg cfg;
-    int32_t n_layer, D, H, n_ctx, n_audio_ctx, n_slots, cap, lp_ld, qk_rows, n_steps, max_rows, reserved;
+    int32_t n_layer, D, H, n_ctx, n_audio_ctx, n_slots, cap, lp_ld, qk_rows, n_steps, max_rows, prof_cap;
 } WtsDecodeSteps;
 
 /* Runs up to n_steps steps (stops early when every sequence is done).  After the launch sync[1] != 0 means the grid

@@ -86,10 +86,27 @@ class OracleEngine:
             mel = whisper.pad_or_trim(mel, whisper.audio.N_FRAMES)
             prompt = job["prompt"]
             ptoks = prompt[1:-len(tok.sot_sequence)] if prompt[0] == tok.sot_prev else None
-            opts = whisper.DecodingOptions(task=tok.task or "transcribe", language=tok.language or "en", temperature=0.0,
+            opts = whisper.DecodingOptions(task=tok.task or "transcribe", language=tok.language or "en",
+                                           temperature=setup.temperature, beam_size=getattr(setup, "beam_size", None),
+                                           patience=getattr(setup, "patience", None), best_of=getattr(setup, "best_of", None),
+                                           length_penalty=getattr(setup, "length_penalty", None),
                                            sample_len=setup.sample_len, prompt=ptoks or None, fp16=False,
                                            suppress_tokens=list(setup.suppress_tokens) or None)
             task = whisper.decoding.DecodingTask(self.model, opts)
+            if opts.beam_size is not None or opts.temperature > 0:
+                # beam search / sampling (two-pass strategy): only the selected hypothesis matters to the caller
+                for f in task.logit_filters:
+                    if isinstance(f, whisper.decoding.SuppressTokens):
+                        f.suppress_tokens = list(setup.suppress_tokens)
+                assert list(task.initial_tokens) == list(prompt), (task.initial_tokens, prompt)
+                res = task.run(mel.unsqueeze(0))[0]
+                tokens = list(res.tokens)
+                self.qk.append(None)
+                out.append(WindowRecord(seek=job["seek"], segment_size=job["segment_size"], prompt=list(prompt), tokens=tokens,
+                                        logprobs=None, ended_by_eot=True, no_speech_prob=float(res.no_speech_prob),
+                                        qk_window=len(self.qk) - 1, temperature=float(setup.temperature), language=tok.language,
+                                        sum_logprob=float(res.avg_logprob) * (len(tokens) + 1)))
+                continue
             # the product computed the suppress list itself; make the stand-in use exactly that list
             for f in task.logit_filters:
                 if isinstance(f, whisper.decoding.SuppressTokens):

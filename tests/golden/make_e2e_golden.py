@@ -46,7 +46,7 @@ CASES = {
     # name: (model, model kwargs, audio (duration, seed), transcribe kwargs)
     "tiny_en_30s": ("tiny.en", {}, (30.0, 7), {}),
     "tiny_75s_cond": ("tiny", {}, (75.0, 11), {"language": "en"}),
-    "tiny_60s_nocond": ("tiny", {}, (60.0, 12), {"language": "en", "condition_on_previous_text": False}),
+    "tiny_60s_nocond": ("tiny", {}, (60.0, 113), {"language": "en", "condition_on_previous_text": False}),
     "tiny_detect_lang": ("tiny", {}, (35.0, 13), {}),
     # < 30 s of audio with language detection: the first window is aligned against the detection mel, so the
     # reference applies NO padding mask (T.py:795-799, 708) although the window's own mel is zero-padded
@@ -65,6 +65,13 @@ CASES = {
     "tiny_naive_opts": ("tiny", {}, (45.0, 23), {"language": "fr", "naive_approach": True, "temperature": 0.0,
                                                  "include_punctuation_in_confidence": True,
                                                  "remove_punctuation_from_words": True, "refine_whisper_precision": 0.2}),
+    # upstream decoding strategies in front of the two-pass alignment (BASELINE config 4): beam search,
+    # the README's "accurate" setting (beam + best-of sampling under temperature fallback; the log-prob threshold is moved
+    # so that some windows pass at temperature 0 and others fall back), and plain best-of-n sampling
+    "tiny_beam5": ("tiny", {}, (65.0, 25), {"language": "en", "beam_size": 5}),
+    "tiny_accurate": ("tiny", {}, (75.0, 26), {"language": "en", "beam_size": 5, "best_of": 5,
+                                               "temperature": (0.0, 0.2, 0.4, 0.6, 0.8, 1.0), "logprob_threshold": -1.2}),
+    "tiny_bestof3": ("tiny", {}, (50.0, 27), {"language": "en", "temperature": 0.3, "best_of": 3}),
     # detect_disfluencies: "[*]" pseudo-words from the peak analysis of the attention rows
     "tiny_disfluencies": ("tiny", {}, (60.0, 12), {"language": "en", "detect_disfluencies": True}),
     "tiny_disfluencies_naive": ("tiny", {}, (70.0, 19), {"language": "en", "detect_disfluencies": True,

@@ -93,6 +93,22 @@ def main():
             res["steps_ms_per_step"] = round(e0.elapsed_time(e1) / max(1, int(flags[2])), 3)
             res["steps_completed"] = int(flags[2])
             res["barrier_timeout"] = int(flags[1])
+            # phase timeline of ONE step (CTA 0's %globaltimer after every grid barrier)
+            L = m.dims.n_text_layer
+            nb = 8 * L + 3
+            prof = torch.zeros(nb + 2, dtype=torch.int64, device="cuda")
+            p = ses["steps"]["args"]
+            p.prof, p.prof_cap = prof.data_ptr(), nb + 2
+            reset(n_active)
+            eng._run_steps(ses, 1, n_active)
+            torch.cuda.synchronize()
+            p.prof, p.prof_cap = None, 0
+            t = prof.cpu().numpy().astype(np.float64)
+            d = np.diff(t[: nb + 1]) / 1e3                      # microseconds per phase (incl. its closing barrier)
+            names = ["qkv", "self_attn", "out", "cross_q", "cross_attn", "cross_out", "fc1", "fc2"]
+            per = {n: round(float(d[1 + i: 1 + 8 * L: 8].mean()), 2) for i, n in enumerate(names)}
+            res["phase_us"] = dict(embed=round(float(d[0]), 2), **per, logits=round(float(d[1 + 8 * L]), 2),
+                                   select=round(float(d[2 + 8 * L]), 2), total=round(float(d.sum()), 1))
         out[n_active] = res
         print(f"active {n_active:4d} / cap {cap}: {res}", flush=True)
     print(json.dumps({"model": args.model, "cap": cap, "steps": args.steps, "ms": out}))

@@ -29,6 +29,9 @@ struct MgShared {
     int list[MG_MAXROWS];               // active slots, ascending
     int n_active;
     int abort_flag;
+    int prof_idx;                       // next slot of the optional phase timeline (block 0 only)
+    unsigned long long* prof;
+    int prof_cap;
     SelectScratch sel;
 };
 
@@ -66,6 +69,11 @@ __device__ __forceinline__ void grid_sync(uint32_t* sync, uint32_t& target, MgSh
                 }
             }
         }
+    }
+    if (threadIdx.x == 0 && sh.prof != nullptr && sh.prof_idx < sh.prof_cap) {   // phase timeline (probe runs only)
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        sh.prof[sh.prof_idx++] = t;
     }
     __syncthreads();
 }
@@ -431,7 +439,17 @@ decode_steps_kernel(const WtsDecodeSteps P)
     float* xs = reinterpret_cast<float*>(smem_raw + 1024);    // [MG_MAXROWS][D] staging (aliased by the attention scratch)
     static_assert(sizeof(MgShared) <= 1024, "MgShared must fit its slot");
     uint32_t target = 0;
-    if (threadIdx.x == 0) sh.abort_flag = 0;
+    if (threadIdx.x == 0) {
+        sh.abort_flag = 0;
+        sh.prof = blockIdx.x == 0 ? reinterpret_cast<unsigned long long*>(P.prof) : nullptr;
+        sh.prof_cap = P.prof_cap;
+        sh.prof_idx = 0;
+        if (sh.prof != nullptr && sh.prof_cap > 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            sh.prof[sh.prof_idx++] = t;
+        }
+    }
     const int D = P.D;
 
     for (int step = 0; step < P.n_steps; ++step) {

@@ -74,9 +74,9 @@ class DecodeSteps(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in (
         "layers", "emb", "pos", "ln_g", "ln_b", "tokens", "n_tokens", "n_prompt", "done",
         "logprobs", "full", "last_full", "qk_buf", "suppress", "blank",
-        "x", "qkv", "att", "q", "mid", "logits", "sync")] + [("cfg", DecodeCfg)] + [(n, ctypes.c_int32) for n in (
+        "x", "qkv", "att", "q", "mid", "logits", "sync", "prof")] + [("cfg", DecodeCfg)] + [(n, ctypes.c_int32) for n in (
         "n_layer", "D", "H", "n_ctx", "n_audio_ctx", "n_slots", "cap", "lp_ld", "qk_rows", "n_steps", "max_rows",
-        "reserved")]
+        "prof_cap")]
 
 
 def _load():

@@ -89,6 +89,29 @@ class _Stream:
             self.prompt_reset_since = len(self.all_tokens)
 
 
+def decode_with_fallback(eng, jobs, setup, temperatures, tokenizer, compression_ratio_threshold, logprob_threshold,
+                         no_speech_threshold):
+    """Upstream `decode_with_fallback` (reached by the reference through model.transcribe, T.py:904 / 1068, options
+    T.py:111-113) for a BATCH of windows: every window is decoded at the first temperature (beam search or greedy at
+    0, best-of-n sampling above); the windows whose result is too repetitive or too unlikely — and not silence — are
+    decoded again, together, at the next temperature; the last attempt stands."""
+    from .windows import needs_fallback
+    final = [None] * len(jobs)
+    pending = list(range(len(jobs)))
+    for k, t in enumerate(temperatures):
+        recs = eng.decode_windows([jobs[i] for i in pending], setup.at_temperature(t))
+        again = []
+        for i, rec in zip(pending, recs):
+            final[i] = rec
+            if k + 1 < len(temperatures) and needs_fallback(rec, tokenizer, compression_ratio_threshold, logprob_threshold,
+                                                            no_speech_threshold):
+                again.append(i)
+        pending = again
+        if not pending:
+            break
+    return final
+
+
 def transcribe_timestamped(
     model,
     audio,
@@ -156,19 +179,21 @@ def transcribe_timestamped(
     if isinstance(model, str):
         from .model import load_model
         model = load_model(model)
-    if isinstance(temperature, (list, tuple)) or temperature != 0 or beam_size is not None or (best_of or 1) > 1 \
-            or use_backend_timestamps:
+    if use_backend_timestamps:
+        raise NotImplementedError("use_backend_timestamps (upstream whisper.timing / HF token timestamps) is not built in "
+                                  "this B200 drop-in")
+    if not naive_approach and temperature != 0:
         raise NotImplementedError(
-            "beam search / best_of / temperature fallback / backend timestamps are not built in this B200 drop-in "
-            "(upstream decoding strategies, SURVEY.md §8 row A14); the two-pass strategy itself (naive_approach=True, "
-            "row A15) runs with greedy decoding and a scalar temperature of 0")
+            "a scalar temperature > 0 inside the one-pass strategy (sampling under the attention hooks) is not built; "
+            "pass naive_approach=True, best_of > 1 or a temperature tuple (two-pass strategy, SURVEY.md §8 rows A14/A15)")
     if not trust_whisper_timestamps and not naive_approach:
         raise NotImplementedError("trust_whisper_timestamps=False is only built for the two-pass strategy (naive_approach=True)")
     if plot_word_alignment:
         raise NotImplementedError("plot_word_alignment is out of scope of the hot path")
     vad = V.check_vad_method(vad)          # explicit (start, end) lists only; detector names raise NotImplementedError
-    if temperature != 0:
-        raise NotImplementedError("temperature sampling is not built yet; greedy (temperature=0) only")
+    if seed is not None:                   # T.py:223-225: sampling (temperature > 0) draws from torch's global generator
+        import torch
+        torch.manual_seed(seed)
     if word_alignment_most_top_layers is not None:
         raise NotImplementedError("word_alignment_most_top_layers: only the alignment-head tables are built")
 
@@ -208,8 +233,10 @@ def transcribe_timestamped(
     if language not in LANGUAGES and language in TO_LANGUAGE_CODE:
         language = TO_LANGUAGE_CODE[language]
     tokenizer = get_tokenizer(is_multilingual, num_languages=num_languages, language=language, task=task)
+    temperatures = [float(t) for t in temperature] if isinstance(temperature, (list, tuple)) else [float(temperature)]
     setup = make_decode_setup(tokenizer, dims.n_text_ctx, sample_len=sample_len, suppress_tokens=suppress_tokens,
-                              temperature=float(temperature))
+                              temperature=temperatures[0], beam_size=beam_size, patience=patience, best_of=best_of,
+                              length_penalty=length_penalty)
     initial_prompt_tokens = tokenizer.encode(" " + initial_prompt.strip()) if initial_prompt is not None else []
 
     streams = []
@@ -222,7 +249,8 @@ def transcribe_timestamped(
         jobs = [st.next_job(setup) for st in streams if st.active]
         if not jobs:
             break
-        records = eng.decode_windows(jobs, setup)
+        records = decode_with_fallback(eng, jobs, setup, temperatures, tokenizer, compression_ratio_threshold,
+                                       logprob_threshold, no_speech_threshold)
         for job, rec in zip(jobs, records):
             if language_detected and job["stream"] == 0 and not streams[0].records:
                 rec.mel_from_language_detection = True        # first window of the file, see WindowRecord.max_duration

@@ -38,6 +38,23 @@ class DecodeSetup:
     blank_tokens: tuple            # encode(" ") + [eot], suppressed at the first sampled position
     max_initial_timestamp_index: Optional[int]
     temperature: float = 0.0
+    # upstream decoding strategies (DecodingOptions): beam search at temperature 0, best-of-n sampling above
+    beam_size: Optional[int] = None
+    patience: Optional[float] = None
+    best_of: Optional[int] = None
+    length_penalty: Optional[float] = None
+
+    @property
+    def n_group(self):
+        """Hypotheses decoded per window (upstream DecodingTask.n_group)."""
+        return self.beam_size or self.best_of or 1
+
+    def at_temperature(self, t):
+        """Upstream decode_with_fallback: beam search only at temperature 0, best_of only above."""
+        from dataclasses import replace
+        if t > 0:
+            return replace(self, temperature=float(t), beam_size=None, patience=None)
+        return replace(self, temperature=float(t), best_of=None)
 
     def initial_tokens(self, prompt_tokens):
         tok = self.tokenizer
@@ -48,7 +65,13 @@ class DecodeSetup:
 
 
 def make_decode_setup(tokenizer, n_text_ctx, sample_len=None, suppress_tokens="-1", temperature=0.0,
-                      max_initial_timestamp=1.0, suppress_blank=True) -> DecodeSetup:
+                      max_initial_timestamp=1.0, suppress_blank=True, beam_size=None, patience=None, best_of=None,
+                      length_penalty=None) -> DecodeSetup:
+    # upstream DecodingTask._verify_options
+    if patience is not None and beam_size is None:
+        raise ValueError("patience requires beam_size to be given")
+    if length_penalty is not None and not (0 <= length_penalty <= 1):
+        raise ValueError("length_penalty (alpha) should be a value between 0 and 1")
     if isinstance(suppress_tokens, str):
         suppress = [int(t) for t in suppress_tokens.split(",")]
     elif suppress_tokens is None:
@@ -65,7 +88,8 @@ def make_decode_setup(tokenizer, n_text_ctx, sample_len=None, suppress_tokens="-
     mit = round(max_initial_timestamp / TIME_PRECISION) if max_initial_timestamp else None
     return DecodeSetup(tokenizer=tokenizer, n_ctx=n_text_ctx, sample_len=sample_len or n_text_ctx // 2,
                        suppress_tokens=tuple(sorted(set(suppress))), blank_tokens=blank,
-                       max_initial_timestamp_index=mit, temperature=temperature)
+                       max_initial_timestamp_index=mit, temperature=temperature, beam_size=beam_size, patience=patience,
+                       best_of=best_of, length_penalty=length_penalty)
 
 
 @dataclass
@@ -82,15 +106,18 @@ class WindowRecord:
     temperature: float = 0.0
     language: Optional[str] = None
     last_row_logprobs: object = None   # callable(token) -> logprob at the last row (rare fallback path)
+    sum_logprob: Optional[float] = None   # beam search / sampling: cumulative log-prob of the selected hypothesis
     mel_from_language_detection: bool = False   # see max_duration
 
     @property
     def n_rows(self):
-        return len(self.logprobs)
+        return len(self.logprobs) if self.logprobs is not None else 0
 
     @property
     def avg_logprob(self):
         # upstream: sum of the log-probs of every sampled token (EOT included) / (len(tokens) + 1)
+        if self.sum_logprob is not None:
+            return float(self.sum_logprob) / (len(self.tokens) + 1)
         return float(np.sum(self.logprobs.astype(np.float32), dtype=np.float32)) / (len(self.tokens) + 1)
 
     @property
@@ -260,3 +287,18 @@ def _flush(cur, rows, unfinished, rec, setup, next_prompt, last_chunk_token=None
         use_rows = len(rows) - 1
     return AlignedSegmentPlan(tokens=tokens, row0=rows[0], n_rows=use_rows, unfinished=unfinished,
                               last_token_reliable=reliable, appended_token=appended)
+
+
+def needs_fallback(rec: WindowRecord, tokenizer, compression_ratio_threshold, logprob_threshold, no_speech_threshold) -> bool:
+    """Upstream decode_with_fallback's verdict on one decoded window (driven by the reference through T.py:111-113)."""
+    need = False
+    if compression_ratio_threshold is not None:
+        text = tokenizer.decode(list(rec.tokens)).strip()
+        if compression_ratio(text) > compression_ratio_threshold:
+            need = True                                   # too repetitive
+    if logprob_threshold is not None and rec.avg_logprob < logprob_threshold:
+        need = True                                       # average log probability is too low
+    if (no_speech_threshold is not None and rec.no_speech_prob > no_speech_threshold
+            and logprob_threshold is not None and rec.avg_logprob < logprob_threshold):
+        need = False                                      # silence
+    return need
