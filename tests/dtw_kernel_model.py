@@ -133,12 +133,13 @@ def model_dtw(cost):
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# Model of the single-strip fast path (dtw.cu: dtw_small_kernel): un-skewed 3-tile ring + mirror of tile 0, one
-# 128-byte bulk copy per row and tile, per-lane read base p_L = (32 t - L + 1) mod 96 advanced once per tile.
+# Model of the single-strip fast path (dtw.cu: dtw_small_kernel): un-skewed 5-tile ring + mirror of slot 0, one
+# 64-byte bulk copy per row and tile issued two tiles ahead, per-lane read base p_L = (16 t - L + 1) mod 80.
 # `late=True` lets every bulk copy land at the last possible moment (just before the mbarrier wait of its tile),
 # `late=False` at issue time: the kernel must be right for both, i.e. no slot is overwritten while still needed and
 # no slot is read before its tile's wait.
-SM_TC, SM_NT = 32, 3
+SM_TC, SM_LA = 16, 2
+SM_NT = SM_LA + 3
 SM_RING = SM_TC * SM_NT
 SM_PITCH = SM_RING + SM_TC
 
@@ -151,41 +152,46 @@ def model_dtw_small(cost, late=False):
     padded = np.zeros((T, P), dtype=np.float32)
     padded[:, :F] = cost
     niter = niter_of(F)
+    nit = 2 * niter
     ntile = (P + SM_TC - 1) // SM_TC
     lanes = np.arange(32)
     tile = np.zeros((32, SM_PITCH), dtype=np.float32)
-    dirs = np.zeros((2 * niter, 32), dtype=np.uint32)
+    dirs = np.zeros((nit, 32), dtype=np.uint32)
     pending = {}
 
-    def issue(t):
-        ncol = min(SM_TC, P - SM_TC * t)
-        slot = t % SM_NT
+    def issue(u):
+        ncol = min(SM_TC, P - SM_TC * u)
+        slot = u % SM_NT
         writes = []
         for L in range(1, T + 1):
-            data = padded[L - 1, SM_TC * t: SM_TC * t + ncol]
+            data = padded[L - 1, SM_TC * u: SM_TC * u + ncol]
             writes.append((L, slot * SM_TC, data))
             if slot == 0:
                 writes.append((L, SM_RING, data))
-        pending[t] = writes
+        pending[u] = writes
 
-    def land(t):
-        for (L, off, data) in pending.pop(t, []):
+    def land(u):
+        for (L, off, data) in pending.pop(u, []):
             tile[L, off: off + len(data)] = data
 
     cur = np.full(32, np.inf)
     upprev = np.full(32, np.inf)
     upprev[1] = 0.0
-    acc = np.zeros(32, dtype=np.uint32)
     p = (SM_RING - lanes + 1) % SM_RING
-    issue(0)
-    for t in range(niter):
+    for u in range(SM_LA):
+        if u < ntile:
+            issue(u)
+            if not late:
+                land(u)
+    for t in range(nit):
         if t < ntile:
             land(t)                                    # mbarrier wait: tile t is complete from here on
-        if t + 1 < ntile:
-            issue(t + 1)
+        if t + SM_LA < ntile:
+            issue(t + SM_LA)
             if not late:
-                land(t + 1)
-        for k in range(32):
+                land(t + SM_LA)
+        acc = np.zeros(32, dtype=np.uint32)
+        for k in range(SM_TC):
             assert np.all(p + k < SM_PITCH)
             l = tile[lanes, p + k].astype(np.float64)
             up = np.concatenate(([cur[0]], cur[:-1]))
@@ -195,11 +201,8 @@ def model_dtw_small(cost, late=False):
             m = np.where(p2, c2, c1)
             p3 = c3 < m
             cur = np.where(p3, c3, m)
-            if k % 16 == 0:
-                acc[:] = 0
-            acc |= (p2.astype(np.uint32) << np.uint32(2 * (k % 16))) | (p3.astype(np.uint32) << np.uint32(2 * (k % 16) + 1))
-            if k % 16 == 15:
-                dirs[2 * t + k // 16] = acc
+            acc |= (p2.astype(np.uint32) << np.uint32(2 * k)) | (p3.astype(np.uint32) << np.uint32(2 * k + 1))
+        dirs[t] = acc
         p = (p + SM_TC) % SM_RING
     # row-wise backtrack on the packed words (same arithmetic as dtw_backtrack_jumps)
     jumps = np.zeros(T + 1, dtype=np.int32)

@@ -176,11 +176,15 @@ __device__ __forceinline__ void select_row(const float* x, const WtsDecodeCfg& c
     const int nt = ld_i<CG>(n_tokens_b);
     const int n = nt - np;                                   // sampled so far
     const int V = cfg.n_vocab, tsb = cfg.timestamp_begin, eot = cfg.eot;
+    // ---- token history: position of the last sampled timestamp (parallel scan, no dependent chain)
+    int last_pos = -1;
+    for (int i = np + threadIdx.x; i < nt; i += T)
+        if (ld_i<CG>(tk + i) >= tsb) last_pos = i;           // ascending i per thread
+    last_pos = (int)block_reduce_max((float)last_pos, S.red);   // positions < 2^24: exact in float
     if (threadIdx.x == 0) {
         const bool last_ts = n >= 1 && ld_i<CG>(tk + nt - 1) >= tsb;
         const bool pen_ts = n < 2 || ld_i<CG>(tk + nt - 2) >= tsb;
-        int tl = -1;
-        for (int i = nt - 1; i >= np; --i) { const int t = ld_i<CG>(tk + i); if (t >= tsb) { tl = t; break; } }
+        const int tl = last_pos >= 0 ? ld_i<CG>(tk + last_pos) : -1;
         int ts_limit = tsb;                                  // timestamps in [tsb, ts_limit) are forbidden
         if (tl >= 0) ts_limit = (last_ts && !pen_ts) ? tl : tl + 1;
         S.flags[0] = (n == 0);
@@ -193,52 +197,53 @@ __device__ __forceinline__ void select_row(const float* x, const WtsDecodeCfg& c
     const int ts_limit = S.flags[3];
     const int ts_max = (first && cfg.max_initial_ts >= 0) ? tsb + cfg.max_initial_ts : V;
 
-    auto allowed = [&](int v) -> bool {
-        if (suppress[v]) return false;
-        if (first && blank[v]) return false;
+    // rules that only depend on the index (the per-token masks are loaded alongside the logits)
+    auto range_ok = [&](int v) -> bool {
         if (v == cfg.no_timestamps) return false;
-        if (v >= tsb) {
-            if (no_ts) return false;
-            if (v < ts_limit) return false;
-            if (v > ts_max) return false;
-        } else {
-            if (first) return false;
-            if (no_text && v < eot) return false;
-        }
-        return true;
+        if (v >= tsb) return !(no_ts || v < ts_limit || v > ts_max);
+        return !(first || (no_text && v < eot));
     };
 
-    // pass 1: maxima of the text range and of the timestamp range
-    float mt = -CUDART_INF_F, ms = -CUDART_INF_F;
-    for (int v = threadIdx.x; v < V; v += T) {
-        if (!allowed(v)) continue;
-        const float xv = ld_f<CG>(x + v);
-        if (v >= tsb) ms = fmaxf(ms, xv); else mt = fmaxf(mt, xv);
+    // ---- ONE pass over the row, 8 independent loads in flight per thread: running (max, sum of exp, argmax) of the
+    // allowed text tokens and of the allowed timestamp tokens
+    constexpr int UN = 8;
+    float mt = -CUDART_INF_F, st = 0.f, ms = -CUDART_INF_F, ss = 0.f;
+    int bti = 0x7fffffff, bsi = 0x7fffffff;                  // argmax of each set (value = mt / ms)
+    for (int v0 = threadIdx.x; v0 < V; v0 += UN * T) {
+        float xv[UN];
+        unsigned bad = 0;
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int v = v0 + u * T;
+            const bool in = v < V;
+            xv[u] = in ? ld_f<CG>(x + v) : 0.f;
+            const unsigned b = in ? (unsigned)__ldg(suppress + v) | (first ? (unsigned)__ldg(blank + v) : 0u) : 1u;
+            bad |= (b != 0u ? 1u : 0u) << u;
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int v = v0 + u * T;
+            if (((bad >> u) & 1u) || !range_ok(v)) continue;
+            const float xx = xv[u];
+            if (v >= tsb) {                                  // ascending v per thread: the first maximum is kept
+                if (xx > ms) { ss = ss * expf(ms - xx) + 1.f; ms = xx; bsi = v; } else ss += expf(xx - ms);
+            } else {
+                if (xx > mt) { st = st * expf(mt - xx) + 1.f; mt = xx; bti = v; } else st += expf(xx - mt);
+            }
+        }
     }
-    mt = block_reduce_max(mt, S.red);
-    ms = block_reduce_max(ms, S.red);
-    // pass 2: sum of exp over timestamps (relative to ms) -> logsumexp of the timestamp range
-    float ss = 0.f;
-    if (ms > -CUDART_INF_F)
-        for (int v = tsb + threadIdx.x; v < V; v += T)
-            if (allowed(v)) ss += expf(ld_f<CG>(x + v) - ms);
-    ss = block_reduce_sum(ss, S.red);
-    const float lse_ts = (ms > -CUDART_INF_F) ? ms + logf(ss) : -CUDART_INF_F;
-    const bool only_ts = lse_ts > mt;                        // "sum of timestamp probability beats any text token"
-    // pass 3: final normaliser + argmax over the allowed set
-    const float gm = only_ts ? ms : fmaxf(mt, ms);
-    float sum = 0.f, best = -CUDART_INF_F;
-    int besti = 0x7fffffff;
-    for (int v = threadIdx.x; v < V; v += T) {
-        if (!allowed(v) || (only_ts && v < tsb)) continue;
-        const float xv = ld_f<CG>(x + v);
-        sum += expf(xv - gm);
-        if (xv > best) { best = xv; besti = v; }             // ascending v per thread: first max kept
-    }
-    sum = block_reduce_sum(sum, S.red);
-    // block argmax, lowest index on ties
+    const float Mt = block_reduce_max(mt, S.red);
+    const float Ms = block_reduce_max(ms, S.red);
+    const float St = block_reduce_sum(mt > -CUDART_INF_F ? st * expf(mt - Mt) : 0.f, S.red);
+    const float Ss = block_reduce_sum(ms > -CUDART_INF_F ? ss * expf(ms - Ms) : 0.f, S.red);
+    const float lse_ts = (Ms > -CUDART_INF_F) ? Ms + logf(Ss) : -CUDART_INF_F;
+    const bool only_ts = lse_ts > Mt;                        // "sum of timestamp probability beats any text token"
+    // block argmax over the final allowed set, lowest index on ties
     {
-        float bv = best; int bi = besti;
+        const bool take_text = !only_ts && mt >= ms;         // equal values: the lower index (a text token) wins
+        float bv = take_text ? mt : ms;
+        int bi = take_text ? bti : bsi;
+        if (bv == -CUDART_INF_F) bi = 0x7fffffff;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const float ov = __shfl_xor_sync(FULL_MASK, bv, o);
@@ -254,14 +259,22 @@ __device__ __forceinline__ void select_row(const float* x, const WtsDecodeCfg& c
         }
         __syncthreads();
     }
-    const float lse = gm + logf(sum);
+    float lse;
+    if (only_ts) {
+        lse = lse_ts;
+    } else {
+        const float gm = fmaxf(Mt, Ms);
+        const float sum = (Mt > -CUDART_INF_F ? St * expf(Mt - gm) : 0.f) + (Ms > -CUDART_INF_F ? Ss * expf(Ms - gm) : 0.f);
+        lse = gm + logf(sum);
+    }
     const int chosen = S.besti[0];
     const bool at_limit = (n + 1 >= cfg.sample_len || nt + 1 > cfg.n_ctx);
     float* f1 = full_b != nullptr ? full_b + (int64_t)n * V : nullptr;
     float* f2 = (last_full_b != nullptr && at_limit) ? last_full_b : nullptr;
     if (f1 != nullptr || f2 != nullptr) {
         for (int v = threadIdx.x; v < V; v += T) {
-            const float lp = (allowed(v) && !(only_ts && v < tsb)) ? ld_f<CG>(x + v) - lse : -CUDART_INF_F;
+            const bool ok = !__ldg(suppress + v) && !(first && __ldg(blank + v)) && range_ok(v) && !(only_ts && v < tsb);
+            const float lp = ok ? ld_f<CG>(x + v) - lse : -CUDART_INF_F;
             if (f1) f1[v] = lp;
             if (f2) f2[v] = lp;
         }

@@ -45,30 +45,40 @@ __device__ __forceinline__ float4 ldg_stream4(const float* p)
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// ---- grid-wide barrier: monotonic counter, one polling thread per CTA.  A spin limit turns a would-be hang (a bug, or
-// a grid that is not co-resident) into an error flag the host reports, instead of a dead GPU.
-__device__ __forceinline__ void grid_sync(uint32_t* sync, uint32_t& target, MgShared& sh)
+// ---- grid-wide barrier.  Arrivals are one release-add per CTA on a counter; the LAST arriver publishes the new
+// generation on a different 128-byte line, which is the only thing the other CTAs poll (acquire loads with a short
+// back-off) — polls never contend with the arriving atomics (measured: polling the counter itself cost ~6 us per
+// barrier with 148 CTAs).  sync[0] = arrivals, sync[1] = error flag, sync[2] = steps completed, sync[32] = generation.
+// A spin limit turns a would-be hang (a bug, or a grid that is not co-resident) into an error flag the host reports.
+__device__ __forceinline__ void grid_sync(uint32_t* sync, uint32_t& gen, MgShared& sh)
 {
     __syncthreads();
-    target += gridDim.x;
+    gen += 1;
     if (threadIdx.x == 0 && !sh.abort_flag) {
         __threadfence();
-        atomicAdd(sync, 1u);
-        uint32_t v;
-        int spins = 0;
-        while (true) {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(sync) : "memory");
-            if (v >= target) break;
-            if ((++spins & 1023) == 0) {
-                uint32_t e;
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(e) : "l"(sync + 1) : "memory");
-                if (e != 0 || spins > (1 << 21)) {           // ~1 s of polling: a bug, or a grid that is not co-resident
-                    atomicExch(sync + 1, 1u);
-                    sh.abort_flag = 1;
-                    break;
+        uint32_t old;
+        asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(sync) : "memory");
+        if (old + 1 == gen * gridDim.x) {
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(sync + 32), "r"(gen) : "memory");
+        } else {
+            uint32_t g;
+            int spins = 0;
+            while (true) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g) : "l"(sync + 32) : "memory");
+                if (g >= gen) break;
+                __nanosleep(20);
+                if ((++spins & 1023) == 0) {
+                    uint32_t e;
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(e) : "l"(sync + 1) : "memory");
+                    if (e != 0 || spins > (1 << 22)) {       // ~1 s of polling: a bug, or a grid that is not co-resident
+                        atomicExch(sync + 1, 1u);
+                        sh.abort_flag = 1;
+                        break;
+                    }
                 }
             }
         }
+        __threadfence();
     }
     if (threadIdx.x == 0 && sh.prof != nullptr && sh.prof_idx < sh.prof_cap) {   // phase timeline (probe runs only)
         unsigned long long t;
@@ -98,25 +108,42 @@ __device__ __forceinline__ void treduce_step(float* v, int lane)
     }
 }
 
-// ---- staging of activation rows into shared memory (optionally LayerNorm'ed): warp w takes rows w, w + 8, ...
-// src rows are read through L2 (ld.global.cg): they were produced by other SMs earlier in this launch.
+// ---- staging of activation rows into shared memory (optionally LayerNorm'ed).  Warp w takes rows w, w + 8, ... of the
+// pass: all of its 16-byte cp.async.cg copies are issued back to back (one memory round trip for the whole staging;
+// .cg = through L2, the rows were produced by other SMs earlier in this launch), then it normalises its own rows in
+// place.  xs row r (pitch `ncols`) <- src[list[row_first + r], col0 .. col0 + ncols).  Ends with a CTA barrier.
+constexpr int MG_STAGE_FLOATS = MG_MAXROWS * 128 * MG_MAXNI;     // staging capacity: 32 rows x 1280 columns
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
 template <bool LN>
-__device__ __forceinline__ void stage_rows(const float* src, int64_t ld, int col0, int NI, const float* __restrict__ gam,
-                                           const float* __restrict__ bet, const MgShared& sh, float* xs)
+__device__ __forceinline__ void stage_rows(const float* src, int64_t ld, int col0, int ncols, int row_first, int nrows,
+                                           const float* __restrict__ gam, const float* __restrict__ bet, const MgShared& sh,
+                                           float* xs)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ncols = NI * 128;
-    for (int i = warp; i < sh.n_active; i += MG_WARPS) {
-        const float* r = src + (int64_t)sh.list[i] * ld + col0;
-        float4 v[MG_MAXNI];
-#pragma unroll
-        for (int k = 0; k < MG_MAXNI; ++k)
-            if (k < NI) v[k] = ldcg4(r + 4 * (lane + 32 * k));
-        if (LN) {
+    const int c4n = ncols >> 2;
+    const uint32_t xs_a = (uint32_t)__cvta_generic_to_shared(xs);
+    for (int r = warp; r < nrows; r += MG_WARPS) {
+        const float* g = src + (int64_t)sh.list[row_first + r] * ld + col0;
+        const uint32_t d = xs_a + (uint32_t)(r * ncols) * 4u;
+        for (int c4 = lane; c4 < c4n; c4 += 32) cp_async16(d + 16u * c4, g + 4 * c4);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    if (LN) {                                                // ncols == D: the whole row is here
+        const int NI = ncols >> 7;
+        for (int r = warp; r < nrows; r += MG_WARPS) {
+            float4* row = reinterpret_cast<float4*>(xs + (int64_t)r * ncols);
+            float4 v[MG_MAXNI];
             float s = 0.f;
 #pragma unroll
             for (int k = 0; k < MG_MAXNI; ++k)
-                if (k < NI) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+                if (k < NI) { v[k] = row[lane + 32 * k]; s += (v[k].x + v[k].y) + (v[k].z + v[k].w); }
             const float mean = warp_sum(s) / (float)ncols;
             float q = 0.f;
 #pragma unroll
@@ -135,12 +162,11 @@ __device__ __forceinline__ void stage_rows(const float* src, int64_t ld, int col
                     v[k].y = (v[k].y - mean) * rstd * g.y + b.y;
                     v[k].z = (v[k].z - mean) * rstd * g.z + b.z;
                     v[k].w = (v[k].w - mean) * rstd * g.w + b.w;
+                    row[lane + 32 * k] = v[k];
                 }
         }
-#pragma unroll
-        for (int k = 0; k < MG_MAXNI; ++k)
-            if (k < NI) *reinterpret_cast<float4*>(xs + (int64_t)i * ncols + 4 * (lane + 32 * k)) = v[k];
     }
+    __syncthreads();
 }
 
 // ---- one K chunk (NI * 128 columns) of a warp task: acc[g][b] += W[n0 + g, kc0 ...] . xs[b, ...]
@@ -149,7 +175,7 @@ __device__ __forceinline__ void stage_rows(const float* src, int64_t ld, int col
 template <int RB>
 __device__ __forceinline__ void gemv_slice(const float4 (&w)[MG_G], const float* xp, int pitch, float (&acc)[MG_G * RB])
 {
-    constexpr int HB = RB > 8 ? 8 : RB;                      // rows per batch of shared-memory loads (bounds live registers)
+    constexpr int HB = RB > 8 ? 4 : RB;                      // rows per batch of shared-memory loads (bounds live registers)
 #pragma unroll
     for (int b0 = 0; b0 < RB; b0 += HB) {
         float4 xv[HB];
@@ -241,15 +267,16 @@ __device__ __noinline__ void gemv_phase(const float* __restrict__ W, int N, int 
     const int warp = threadIdx.x >> 5;
     const int total_warps = gridDim.x * MG_WARPS;
     const int gw = warp * gridDim.x + blockIdx.x;            // consecutive tasks land on different SMs
-    const int NI = D / 128;
-    const int nchunks = K / D;
+    const int nA = sh.n_active;
     const int ntasks = (N + MG_G - 1) / MG_G;
     const int rounds = (ntasks + total_warps - 1) / total_warps;
-    const int npass = (sh.n_active + RB - 1) / RB;
-    if (nchunks == 1) {
-        stage_rows<LN>(src, lds, 0, NI, gam, bet, sh, xs);
-        __syncthreads();
-    }
+    const int npass = (nA + RB - 1) / RB;
+    // Either every active row with all K columns fits the staging buffer (always when K == D): staged ONCE for all
+    // rounds and passes.  Or (FC2 with more than 8 active rows) each pass stages its own rows in chunks of Kc columns.
+    const bool once = nA * K <= MG_STAGE_FLOATS;
+    const int Kc = once ? K : (MG_STAGE_FLOATS / (RB * D)) * D;
+    const int nchunks = (K + Kc - 1) / Kc;
+    if (once) stage_rows<LN>(src, lds, 0, K, 0, nA, gam, bet, sh, xs);
     for (int rd = 0; rd < rounds; ++rd) {
         const int t = gw + rd * total_warps;
         const bool has = t < ntasks;
@@ -258,12 +285,12 @@ __device__ __noinline__ void gemv_phase(const float* __restrict__ W, int N, int 
 #pragma unroll
             for (int i = 0; i < MG_G * RB; ++i) acc[i] = 0.f;
             for (int c = 0; c < nchunks; ++c) {
-                if (nchunks > 1) {
+                const int kc = min(Kc, K - c * Kc);
+                if (!once) {
                     __syncthreads();                         // previous chunk fully consumed
-                    stage_rows<false>(src, lds, c * D, NI, nullptr, nullptr, sh, xs);
-                    __syncthreads();
+                    stage_rows<false>(src, lds, c * Kc, kc, ps * RB, min(RB, nA - ps * RB), nullptr, nullptr, sh, xs);
                 }
-                if (has) gemv_chunk<RB>(W, K, t * MG_G, N, c * D, NI, xs + (int64_t)ps * RB * D, D, acc);
+                if (has) gemv_chunk<RB>(W, K, t * MG_G, N, c * Kc, kc >> 7, once ? xs + (int64_t)ps * RB * K : xs, kc, acc);
             }
             if (has) gemv_epilogue<RB>(acc, t * MG_G, N, ps * RB, sh, bias, out, ldo, epi);
         }
@@ -283,6 +310,32 @@ __device__ __forceinline__ void prefetch_phase(const float* W, int N, int K)
             const int g = ln / lines_per_row, c = ln - g * lines_per_row;
             const int n = min(t * MG_G + g, N - 1);
             prefetch_l2(W + (int64_t)n * K + c * 32);
+        }
+    }
+}
+
+constexpr int MG_KV_PREFETCH_ROWS = 8;    // <= 8 rows x 7.7 MB of fp16 K/V per layer stay well inside the 126 MB L2
+
+__device__ __forceinline__ void prefetch_cross_kv(const WtsDecodeSteps& P, const WtsDecLayer& Lr, const MgShared& sh)
+{
+    const int64_t per_row = (int64_t)P.H * P.n_audio_ctx * 64 * 2;             // bytes of fp16 K (and of V) per row
+    const int64_t lines_row = per_row / 128;
+    const int64_t nthreads = (int64_t)gridDim.x * MG_THREADS, me = (int64_t)blockIdx.x * MG_THREADS + threadIdx.x;
+    for (int i = 0; i < sh.n_active; ++i) {
+        const char* k = reinterpret_cast<const char*>(Lr.cross_k16) + (int64_t)sh.list[i] * per_row;
+        const char* v = reinterpret_cast<const char*>(Lr.cross_v16) + (int64_t)sh.list[i] * per_row;
+        for (int64_t ln = me; ln < lines_row; ln += nthreads) {
+            prefetch_l2(k + ln * 128);
+            prefetch_l2(v + ln * 128);
+        }
+        // float32 K of the alignment heads of this layer
+        const int64_t al_row = (int64_t)P.n_slots * P.n_audio_ctx * 64 * 4;
+        const char* ka = reinterpret_cast<const char*>(Lr.cross_k_align) + (int64_t)sh.list[i] * al_row;
+        for (int h = 0; h < P.H; ++h) {
+            const int slot = __ldg(Lr.head_slot + h);
+            if (slot < 0) continue;
+            const int64_t lines = (int64_t)P.n_audio_ctx * 64 * 4 / 128;
+            for (int64_t ln = me; ln < lines; ln += nthreads) prefetch_l2(ka + (int64_t)slot * lines * 128 + ln * 128);
         }
     }
 }
@@ -389,6 +442,9 @@ __device__ void decode_layers_and_logits(const WtsDecodeSteps& P, MgShared& sh, 
     const int gw = warp * gridDim.x + blockIdx.x;
     for (int li = 0; li < P.n_layer; ++li) {
         const WtsDecLayer& Lr = P.layers[li];
+        // few active rows: pull this layer's cross-attention K/V into L2 now (the matrix-vector phases in between leave HBM
+        // idle), so the (row, head) streams of P5 — each a single CTA with limited bytes in flight — run at L2 latency
+        if (sh.n_active <= MG_KV_PREFETCH_ROWS) prefetch_cross_kv(P, Lr, sh);
         // P1: LN + QKV
         gemv_phase<RB, true>(Lr.w_qkv, 3 * D, D, D, Lr.b_qkv, P.x, D, Lr.ln1_g, Lr.ln1_b, P.qkv, 3 * D, EPI_STORE, sh, xs);
         prefetch_phase(Lr.w_o, D, D);
@@ -426,6 +482,19 @@ __device__ void decode_layers_and_logits(const WtsDecodeSteps& P, MgShared& sh, 
     // final LN + tied-embedding logits
     gemv_phase<RB, true>(P.emb, P.cfg.n_vocab, D, D, nullptr, P.x, D, P.ln_g, P.ln_b, P.logits, P.cfg.n_vocab, EPI_STORE, sh, xs);
     grid_sync(P.sync, target, sh);
+}
+
+__device__ __noinline__ void select_phase(const WtsDecodeSteps& P, MgShared& sh)
+{
+    for (int i = blockIdx.x; i < sh.n_active; i += gridDim.x) {
+        const int row = sh.list[i];
+        select_row<true>(P.logits + (int64_t)row * P.cfg.n_vocab, P.cfg, P.suppress, P.blank,
+                         P.tokens + (int64_t)row * P.cfg.tokens_ld, P.n_tokens + row, __ldg(P.n_prompt + row), P.done + row,
+                         P.logprobs + (int64_t)row * P.lp_ld,
+                         P.full != nullptr ? P.full + (int64_t)row * P.lp_ld * P.cfg.n_vocab : nullptr,
+                         P.last_full != nullptr ? P.last_full + (int64_t)row * P.cfg.n_vocab : nullptr, sh.sel);
+        __syncthreads();
+    }
 }
 
 // RB = activation rows per weight pass (4, 8 or 16): chosen by the host from the number of active rows at launch
@@ -486,15 +555,7 @@ decode_steps_kernel(const WtsDecodeSteps P)
         decode_layers_and_logits<RB>(P, sh, xs, target);
 
         // ---- filters + log-softmax + greedy choice: one CTA per active row
-        for (int i = blockIdx.x; i < nA; i += gridDim.x) {
-            const int row = sh.list[i];
-            select_row<true>(P.logits + (int64_t)row * P.cfg.n_vocab, P.cfg, P.suppress, P.blank,
-                             P.tokens + (int64_t)row * P.cfg.tokens_ld, P.n_tokens + row, __ldg(P.n_prompt + row), P.done + row,
-                             P.logprobs + (int64_t)row * P.lp_ld,
-                             P.full != nullptr ? P.full + (int64_t)row * P.lp_ld * P.cfg.n_vocab : nullptr,
-                             P.last_full != nullptr ? P.last_full + (int64_t)row * P.cfg.n_vocab : nullptr, sh.sel);
-            __syncthreads();
-        }
+        select_phase(P, sh);
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.sync + 2, 1u);   // steps completed
         grid_sync(P.sync, target, sh);
     }
@@ -534,7 +595,7 @@ extern "C" int wts_decode_steps(const WtsDecodeSteps* p, void* stream)
         WTS_CUDA_CHECK(cudaFuncSetAttribute(decode_steps_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
-    WTS_CUDA_CHECK(cudaMemsetAsync(P.sync, 0, 4 * sizeof(uint32_t), st));
+    WTS_CUDA_CHECK(cudaMemsetAsync(P.sync, 0, 64 * sizeof(uint32_t), st));
     void* args[] = {const_cast<WtsDecodeSteps*>(p)};
     const void* fn = P.max_rows <= 4 ? (const void*)decode_steps_kernel<4>
                    : P.max_rows <= 8 ? (const void*)decode_steps_kernel<8> : (const void*)decode_steps_kernel<16>;

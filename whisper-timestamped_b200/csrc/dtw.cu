@@ -302,22 +302,27 @@ dtw_warp_kernel(const TIn* __restrict__ cost, const WtsSegDesc* __restrict__ seg
 // padded to 16 bytes) gets its own kernel, built to spend as few issue slots per anti-diagonal as the bit-exact fp64
 // recurrence allows (the general kernel above is ISSUE-bound: ~40 warp instructions per step of which the recurrence
 // needs ~17, profiles/r1c_dtw_summary.md):
-//  * staging is ONE predicated instruction per 32-column tile: every lane L (1..T) issues a 128-byte 1-D bulk copy
-//    (cp.async.bulk, TMA) of its own row's next tile; completion is counted by an mbarrier (two, alternating);
-//  * the row buffers are NOT skewed: a ring of three tiles (the tiles t-1 and t being read, t+1 in flight) plus a
-//    mirror of the first tile behind the ring, so lane L reads `row_base + 4 p_L + 4 k` at step k of a tile — an
-//    immediate offset with no wrap inside the tile (p_L = (32 t - L + 1) mod 96 advances once per tile);
-//    row pitch 128 words: bank (p_L + k) mod 32 = (1 - L + k) mod 32 is distinct over the lanes;
+//  * staging is ONE predicated instruction per 16-column tile: every lane L (1..T) issues a 64-byte 1-D bulk copy
+//    (cp.async.bulk, TMA) of its own row's tile, two tiles ahead; completion is counted by mbarriers (three, rotating);
+//  * the row buffers are NOT skewed: a ring of five tiles (t-2 .. t being read — the 31 lanes of skew span two
+//    tiles back —, t+1 and t+2 in flight) plus a mirror of slot 0 behind the ring, so lane L reads
+//    `row_base + 4 p_L + 4 k` at step k of a tile — an immediate offset with no wrap inside the tile
+//    (p_L = (16 t - L + 1) mod 80 advances once per tile); row pitch 96 words: bank (p_L + k) mod 32 =
+//    (1 - L + k + 16 t) mod 32 is distinct over the lanes; 15 KB of shared memory per warp (rows + directions)
+//    keeps 14 warps per SM resident — the dependent fp64 chain needs them;
 //  * directions stay in shared memory (2 bits per cell) for the row-wise backtrack.
 // Same recurrence, same tie-breaks, same packed direction words as dtw_fill_strip<float, true, false, true>.
-constexpr int SM_TC = 32;                    // columns per tile
-constexpr int SM_NT = 3;                     // tiles in the ring
+constexpr int SM_TC = 16;                    // columns per tile = wavefront steps per iteration
+constexpr int SM_LA = 2;                     // tiles in flight ahead of the one being consumed
+constexpr int SM_NT = SM_LA + 3;             // tiles in the ring: t-2, t-1 (still read by the higher lanes: 31 lanes of skew
+                                             // span two 16-column tiles), t, and t+1 .. t+LA in flight
+constexpr int SM_NB = SM_LA + 1;             // mbarriers
 constexpr int SM_RINGB = SM_NT * SM_TC * 4;  // ring bytes per row
-constexpr int SM_PITCHB = (SM_NT + 1) * SM_TC * 4;   // + mirror of tile 0
+constexpr int SM_PITCHB = (SM_NT + 1) * SM_TC * 4;   // + mirror of slot 0 behind the ring (96 words: bank (1 - L + k) mod 32 distinct)
 constexpr int SM_TILE_BYTES = 32 * SM_PITCHB;        // rows 0..31 (row 0 = the virtual row above, stays zero)
-constexpr int SM_WARP_BYTES = SM_TILE_BYTES + DS_WORDS * 32 * 4 + 16;
+constexpr int SM_WARP_BYTES = SM_TILE_BYTES + DS_WORDS * 32 * 4 + 32;
 #ifndef DTW_SMALL_WARPS
-#define DTW_SMALL_WARPS 2
+#define DTW_SMALL_WARPS 1
 #endif
 
 __device__ __forceinline__ void mbar_init1(uint32_t bar) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar)); }
@@ -367,27 +372,28 @@ dtw_small_kernel(const float* __restrict__ cost, const WtsSegDesc* __restrict__ 
         for (int k = lane; k < SM_TILE_BYTES / 16; k += 32) z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (lane == 0) {
-        mbar_init1(bar0);
-        mbar_init1(bar0 + 8);
+#pragma unroll
+        for (int i = 0; i < SM_NB; ++i) mbar_init1(bar0 + 8u * i);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy zeros ordered before async-proxy writes
     __syncwarp();
 
-    const int niter = dtw_niter(F);                          // 32-step tiles of the wavefront
+    const int niter = dtw_niter(F);                          // 32-step tiles of the wavefront (direction layout)
+    const int nit = 2 * niter;                               // 16-step iterations
     const int ntile = (P + SM_TC - 1) / SM_TC;               // column tiles of the matrix
     const bool owner = lane >= 1 && lane <= T;
     const char* myrow = reinterpret_cast<const char*>(C + (int64_t)(lane - 1) * P);
     const uint32_t myrow_a = tile_a + lane * SM_PITCHB;
 
-    auto issue_tile = [&](int t) {                           // columns [32 t, 32 t + 31] of every row -> ring slot t % 3
-        const int ncol = min(SM_TC, P - SM_TC * t);
+    auto issue_tile = [&](int u) {                           // columns [16 u, 16 u + 15] of every row -> ring slot u % NT
+        const int ncol = min(SM_TC, P - SM_TC * u);
         const uint32_t bytes = (uint32_t)ncol * 4u;
-        const int slot = t % SM_NT;
-        const uint32_t bar = bar0 + 8u * (t & 1);
+        const int slot = u % SM_NT;
+        const uint32_t bar = bar0 + 8u * (u % SM_NB);
         if (lane == 0) mbar_arrive_expect(bar, bytes * (uint32_t)T * (slot == 0 ? 2u : 1u));
         if (owner) {
-            const char* src = myrow + (size_t)t * SM_TC * 4;
+            const char* src = myrow + (size_t)u * SM_TC * 4;
             bulk_g2s(myrow_a + slot * SM_TC * 4, src, bytes, bar);
             if (slot == 0) bulk_g2s(myrow_a + SM_RINGB, src, bytes, bar);      // mirror behind the ring
         }
@@ -396,15 +402,17 @@ dtw_small_kernel(const float* __restrict__ cost, const WtsSegDesc* __restrict__ 
     const double INF = dinf();
     double cur = INF, upprev = INF;
     if (lane == 1) upprev = 0.0;                             // seeds cm[0,0] = 0 + lm[0,0]
-    uint32_t acc = 0;
-    uint32_t pb = (uint32_t)(((SM_NT * SM_TC) - lane + 1) % (SM_NT * SM_TC)) * 4u;   // 4 * ((32 t - L + 1) mod 96), t = 0
-    issue_tile(0);
-    for (int t = 0; t < niter; ++t) {
-        if (t < ntile) mbar_wait_parity(bar0 + 8u * (t & 1), (uint32_t)((t >> 1) & 1));
-        if (t + 1 < ntile) issue_tile(t + 1);
-        const uint32_t rd = myrow_a + pb;
+    uint32_t pb = (uint32_t)(((SM_NT * SM_TC) - lane + 1) % (SM_NT * SM_TC)) * 4u;   // 4 * ((16 t - L + 1) mod 80), t = 0
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
+    for (int u = 0; u < SM_LA; ++u)
+        if (u < ntile) issue_tile(u);
+    for (int t = 0; t < nit; ++t) {
+        if (t < ntile) mbar_wait_parity(bar0 + 8u * (t % SM_NB), (uint32_t)((t / SM_NB) & 1));
+        if (t + SM_LA < ntile) issue_tile(t + SM_LA);        // its ring slot held tile t - 3: last read in iteration t - 1
+        const uint32_t rd = myrow_a + pb;
+        uint32_t acc = 0;
+#pragma unroll
+        for (int k = 0; k < SM_TC; ++k) {
             const double l = (double)lds<float>(rd + 4 * k);
             const double up = __shfl_up_sync(FULL_MASK, cur, 1);
             const double c1 = upprev + l, c2 = cur + l, c3 = up + l;
@@ -414,11 +422,10 @@ dtw_small_kernel(const float* __restrict__ cost, const WtsSegDesc* __restrict__ 
             const double m = p2 ? c2 : c1;
             const bool p3 = (unsigned long long)__double_as_longlong(c3) > (unsigned long long)__double_as_longlong(m);
             cur = p3 ? c3 : m;
-            if ((k & 15) == 0) acc = 0;
-            if (p2) acc |= 1u << (2 * (k & 15));
-            if (p3) acc |= 2u << (2 * (k & 15));
-            if ((k & 15) == 15) dirs[(2 * t + (k >> 4)) * 32 + lane] = acc;
+            if (p2) acc |= 1u << (2 * k);
+            if (p3) acc |= 2u << (2 * k);
         }
+        dirs[t * 32 + lane] = acc;
         pb += SM_TC * 4;
         if (pb >= (uint32_t)SM_RINGB) pb -= SM_RINGB;
     }
