@@ -232,6 +232,12 @@ int wts_decode_select(float* d_logits, int64_t ldl, const WtsDecodeCfg* cfg, con
                       int32_t* d_done, float* d_logprobs, int32_t lp_ld, float* d_full_logprobs,
                       float* d_last_full, int32_t B, void* stream);
 
+/* The filtered log-softmax row of every sequence (same filters as wts_decode_select, no choice and no state update):
+ * what upstream's BeamSearchDecoder.update / GreedyDecoder.update (temperature > 0) consume.  d_out: [B, V]. */
+int wts_filtered_logprobs(const float* d_logits, int64_t ldl, const WtsDecodeCfg* cfg, const uint8_t* d_suppress,
+                          const uint8_t* d_blank, int32_t* d_tokens, int32_t* d_n_tokens, const int32_t* d_n_prompt,
+                          float* d_out, int32_t B, void* stream);
+
 /* ---- Persistent decode steps for small active batches (csrc/decode_steps.cu).
  * One cooperative kernel runs up to n_steps whole decoder steps (embed, all blocks with KV-cache append, causal
  * self-attention, fp16 cross-attention with the alignment heads' pre-softmax rows written into qk_buf, final LayerNorm,
@@ -268,6 +274,12 @@ typedef struct WtsDecodeSteps {
 /* Runs up to n_steps steps (stops early when every sequence is done).  After the launch sync[1] != 0 means the grid
  * barrier timed out (results invalid), sync[2] = steps completed.  Returns < 0 for unsupported dimensions. */
 int wts_decode_steps(const WtsDecodeSteps* p, void* stream);
+
+/* The same step as a chain of per-phase kernels under programmatic dependent launch (2 + 8 n_layer + 1 launches; meant to
+ * be captured in a CUDA graph and replayed once per token): a kernel boundary costs less than a software grid barrier
+ * across the B200's two dies, and each kernel pulls its weight rows into L2 while its producer drains.  h_layers: HOST
+ * copy of the layer table p->layers points to.  p->max_rows (1..32) sizes the grids and picks the rows-per-pass variant. */
+int wts_decode_step_kernels(const WtsDecodeSteps* p, const WtsDecLayer* h_layers, void* stream);
 
 /* Per-step decoder inputs from the token buffers: tok[b] = last token, pos[b] = its position,
  * qk_row[b] = number of tokens sampled so far (row that the step predicts), or -1 when the sequence is done. */

@@ -133,18 +133,22 @@ def model_dtw(cost):
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# Model of the single-strip fast path (dtw.cu: dtw_small_kernel): un-skewed 5-tile ring + mirror of slot 0, one
-# 64-byte bulk copy per row and tile issued two tiles ahead, per-lane read base p_L = (16 t - L + 1) mod 80.
+# Model of the single-strip fast path (dtw.cu: dtw_small_kernel<TC, LA, .>): un-skewed ring of NT = LA + 1 + ceil(31/TC)
+# tiles + mirror of slot 0, one bulk copy per row and tile issued LA tiles ahead, per-lane read base
+# p_L = (TC t - L + 1) mod ring.
 # `late=True` lets every bulk copy land at the last possible moment (just before the mbarrier wait of its tile),
 # `late=False` at issue time: the kernel must be right for both, i.e. no slot is overwritten while still needed and
 # no slot is read before its tile's wait.
-SM_TC, SM_LA = 16, 2
-SM_NT = SM_LA + 3
-SM_RING = SM_TC * SM_NT
-SM_PITCH = SM_RING + SM_TC
+def small_geometry(TC, LA):
+    NT = LA + 1 + (31 + TC - 1) // TC
+    ring = NT * TC
+    assert ring % 32 == 0
+    return NT, ring, ring + TC
 
 
-def model_dtw_small(cost, late=False):
+def model_dtw_small(cost, late=False, TC=16, LA=1):
+    SM_TC, SM_LA = TC, LA
+    SM_NT, SM_RING, SM_PITCH = small_geometry(TC, LA)
     cost = np.asarray(cost, dtype=np.float32)
     T, F = cost.shape
     assert T <= RS
@@ -152,12 +156,13 @@ def model_dtw_small(cost, late=False):
     padded = np.zeros((T, P), dtype=np.float32)
     padded[:, :F] = cost
     niter = niter_of(F)
-    nit = 2 * niter
+    nit = niter * (32 // SM_TC)
     ntile = (P + SM_TC - 1) // SM_TC
     lanes = np.arange(32)
     tile = np.zeros((32, SM_PITCH), dtype=np.float32)
-    dirs = np.zeros((nit, 32), dtype=np.uint32)
+    dirs = np.zeros((2 * niter, 32), dtype=np.uint32)
     pending = {}
+    acc = np.zeros(32, dtype=np.uint32)
 
     def issue(u):
         ncol = min(SM_TC, P - SM_TC * u)
@@ -190,9 +195,10 @@ def model_dtw_small(cost, late=False):
             issue(t + SM_LA)
             if not late:
                 land(t + SM_LA)
-        acc = np.zeros(32, dtype=np.uint32)
         for k in range(SM_TC):
             assert np.all(p + k < SM_PITCH)
+            # bank-conflict freedom of the read of this step (the point of the ring / pitch geometry)
+            assert len(set(((lanes * SM_PITCH + p + k) % 32).tolist())) == 32
             l = tile[lanes, p + k].astype(np.float64)
             up = np.concatenate(([cur[0]], cur[:-1]))
             c1, c2, c3 = upprev + l, cur + l, up + l
@@ -201,8 +207,13 @@ def model_dtw_small(cost, late=False):
             m = np.where(p2, c2, c1)
             p3 = c3 < m
             cur = np.where(p3, c3, m)
-            acc |= (p2.astype(np.uint32) << np.uint32(2 * k)) | (p3.astype(np.uint32) << np.uint32(2 * k + 1))
-        dirs[t] = acc
+            step = t * SM_TC + k
+            if step % 16 == 0:
+                acc = np.zeros(32, dtype=np.uint32)
+            sh_ = np.uint32(2 * (step % 16))
+            acc |= (p2.astype(np.uint32) << sh_) | (p3.astype(np.uint32) << (sh_ + np.uint32(1)))
+            if step % 16 == 15:
+                dirs[step // 16] = acc
         p = (p + SM_TC) % SM_RING
     # row-wise backtrack on the packed words (same arithmetic as dtw_backtrack_jumps)
     jumps = np.zeros(T + 1, dtype=np.int32)

@@ -35,8 +35,9 @@ def test_model_exact_strip_boundaries():
         assert np.array_equal(jumps, model_dtw(c)), T
 
 
+@pytest.mark.parametrize("geo", [(16, 1), (8, 3), (32, 1)])
 @pytest.mark.parametrize("late", [False, True])
-def test_small_kernel_model_matches_oracle(late):
+def test_small_kernel_model_matches_oracle(late, geo):
     """Index arithmetic of dtw_small_kernel (3-tile ring + mirror, per-tile read base, bulk copies landing early or
     at the last moment) on negative costs incl. heavy ties, for shapes around every tile / pitch boundary."""
     from dtw_kernel_model import model_dtw_small
@@ -52,4 +53,4 @@ def test_small_kernel_model_matches_oracle(late):
         else:
             c = -rng.integers(1, 4, (T, F)).astype(np.float32)
         _, _, jumps, _ = oracle.dtw_symmetric1(c.astype(np.float64))
-        assert np.array_equal(jumps, model_dtw_small(c, late=late)), (T, F, late)
+        assert np.array_equal(jumps, model_dtw_small(c, late=late, TC=geo[0], LA=geo[1])), (T, F, late, geo)

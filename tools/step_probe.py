@@ -25,7 +25,7 @@ def main():
     ap.add_argument("--active", type=str, default="128,32,16,8,4,1")
     ap.add_argument("--steps", type=int, default=24)
     ap.add_argument("--eager", action="store_true")
-    ap.add_argument("--only", default="graph,steps")
+    ap.add_argument("--only", default="graph,lean,steps")
     args = ap.parse_args()
     import whisper_timestamped as wt
     from whisper_timestamped.engine import CudaEngine
@@ -81,6 +81,17 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             res["graph_ms_per_step"] = round(e0.elapsed_time(e1) / args.steps, 3)
+        if "lean" in args.only and ses["steps"] is not None and n_active <= eng.small_batch_rows:
+            reset(n_active)
+            graph = eng._lean_graph(ses, n_active)
+            for _ in range(3):
+                graph.replay()
+            e0.record()
+            for _ in range(args.steps):
+                graph.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            res["lean_ms_per_step"] = round(e0.elapsed_time(e1) / args.steps, 3)
         if "steps" in args.only and ses["steps"] is not None and n_active <= eng.small_batch_rows:
             reset(n_active)
             eng._run_steps(ses, 3, n_active)

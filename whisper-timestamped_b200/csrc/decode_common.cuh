@@ -170,8 +170,10 @@ template <bool CG>
 __device__ __forceinline__ void select_row(const float* x, const WtsDecodeCfg& cfg, const uint8_t* __restrict__ suppress,
                                            const uint8_t* __restrict__ blank, int32_t* tk, int32_t* n_tokens_b, int np,
                                            int32_t* done_b, float* logprobs_b, float* full_b, float* last_full_b,
-                                           SelectScratch& S)
+                                           SelectScratch& S, const bool rows_only = false)
 {
+    // rows_only: only write the filtered log-softmax row to full_b[0 .. V) — no choice, no state update (what beam
+    // search / sampling consume: upstream BeamSearchDecoder.update / GreedyDecoder.update work on these rows)
     const int T = blockDim.x;
     const int nt = ld_i<CG>(n_tokens_b);
     const int n = nt - np;                                   // sampled so far
@@ -269,8 +271,8 @@ __device__ __forceinline__ void select_row(const float* x, const WtsDecodeCfg& c
     }
     const int chosen = S.besti[0];
     const bool at_limit = (n + 1 >= cfg.sample_len || nt + 1 > cfg.n_ctx);
-    float* f1 = full_b != nullptr ? full_b + (int64_t)n * V : nullptr;
-    float* f2 = (last_full_b != nullptr && at_limit) ? last_full_b : nullptr;
+    float* f1 = full_b != nullptr ? full_b + (rows_only ? 0 : (int64_t)n * V) : nullptr;
+    float* f2 = (last_full_b != nullptr && at_limit && !rows_only) ? last_full_b : nullptr;
     if (f1 != nullptr || f2 != nullptr) {
         for (int v = threadIdx.x; v < V; v += T) {
             const bool ok = !__ldg(suppress + v) && !(first && __ldg(blank + v)) && range_ok(v) && !(only_ts && v < tsb);
@@ -279,7 +281,7 @@ __device__ __forceinline__ void select_row(const float* x, const WtsDecodeCfg& c
             if (f2) f2[v] = lp;
         }
     }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && !rows_only) {
         logprobs_b[n] = S.best[0] - lse;
         if (chosen == eot) {
             *done_b = 1;

@@ -298,14 +298,14 @@ __device__ __noinline__ void gemv_phase(const float* __restrict__ W, int N, int 
 }
 
 // L2 prefetch of the weight rows this warp will stream in a later phase
-__device__ __forceinline__ void prefetch_phase(const float* W, int N, int K)
+__device__ __forceinline__ void prefetch_phase(const float* W, int N, int K, int max_rounds = 1 << 30)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_warps = gridDim.x * MG_WARPS;
     const int gw = warp * gridDim.x + blockIdx.x;
     const int ntasks = (N + MG_G - 1) / MG_G;
     const int lines_per_row = K / 32;                        // 128-byte lines
-    for (int t = gw; t < ntasks; t += total_warps) {
+    for (int t = gw, r = 0; t < ntasks && r < max_rounds; t += total_warps, ++r) {
         for (int ln = lane; ln < MG_G * lines_per_row; ln += 32) {
             const int g = ln / lines_per_row, c = ln - g * lines_per_row;
             const int n = min(t * MG_G + g, N - 1);
@@ -561,6 +561,143 @@ decode_steps_kernel(const WtsDecodeSteps P)
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// The same step as a chain of LEAN kernels (one per phase), launched with programmatic dependent launch and replayed
+// as one CUDA graph.  Measured on the B200 (tools/step_probe.py, phase timeline): a software grid barrier costs ~5 us
+// (atomics + polling across the two dies' L2) — 259 of them per step put the persistent kernel at ~3.8 ms per step
+// even for one active window.  A kernel boundary under PDL is cheaper, and the next kernel's independent prologue
+// (pulling its weight rows into L2) runs while the previous one drains.  Same device code per phase.
+__device__ __forceinline__ void build_row_list(const WtsDecodeSteps& P, MgShared& sh)
+{
+    if (threadIdx.x < 32) {
+        int count = 0;
+        for (int b0 = 0; b0 < P.cap; b0 += 32) {
+            const int b = b0 + threadIdx.x;
+            const bool act = b < P.cap && __ldcg(P.done + b) == 0;
+            const unsigned bal = __ballot_sync(FULL_MASK, act);
+            const int at = count + __popc(bal & ((1u << threadIdx.x) - 1u));
+            if (act && at < MG_MAXROWS) sh.list[at] = b;
+            count += __popc(bal);
+        }
+        if (threadIdx.x == 0) { sh.n_active = count <= MG_MAXROWS ? count : 0; sh.abort_flag = 0; sh.prof = nullptr; }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(MG_THREADS)
+lean_embed_kernel(const WtsDecodeSteps P)
+{
+    pdl_launch();
+    pdl_wait();
+    const int row = blockIdx.x;
+    if (row >= P.cap || __ldcg(P.done + row) != 0) return;
+    const int nt = __ldcg(P.n_tokens + row);
+    const int tok = __ldcg(P.tokens + (int64_t)row * P.cfg.tokens_ld + nt - 1);
+    const float* e = P.emb + (int64_t)tok * P.D;
+    const float* p = P.pos + (int64_t)(nt - 1) * P.D;
+    for (int c = threadIdx.x; c < P.D; c += MG_THREADS) P.x[(int64_t)row * P.D + c] = __ldg(e + c) + __ldg(p + c);
+}
+
+template <int RB, bool LN>
+__global__ void __launch_bounds__(MG_THREADS, 1)
+lean_gemv_kernel(const WtsDecodeSteps P, const float* __restrict__ W, int N, int K, const float* __restrict__ bias,
+                 const float* src, int64_t lds, const float* gam, const float* bet, float* out, int64_t ldo, int epi)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MgShared& sh = *reinterpret_cast<MgShared*>(smem_raw);
+    float* xs = reinterpret_cast<float*>(smem_raw + 1024);
+    pdl_launch();
+    prefetch_phase(W, N, K, 3);                              // this CTA's first weight rows -> L2 while the producer drains
+    pdl_wait();
+    build_row_list(P, sh);
+    if (sh.n_active == 0) return;
+    gemv_phase<RB, LN>(W, N, K, P.D, bias, src, lds, gam, bet, out, ldo, epi, sh, xs);
+}
+
+__global__ void __launch_bounds__(MG_THREADS)
+lean_self_attn_kernel(const WtsDecodeSteps P, const WtsDecLayer* Lr)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MgShared& sh = *reinterpret_cast<MgShared*>(smem_raw);
+    float* xs = reinterpret_cast<float*>(smem_raw + 1024);
+    pdl_launch();
+    pdl_wait();
+    build_row_list(P, sh);
+    const int warp = threadIdx.x >> 5;
+    const int t = blockIdx.x * MG_WARPS + warp;
+    if (t >= sh.n_active * P.H) return;
+    const int row = sh.list[t / P.H];
+    self_attention_task(P, *Lr, row, t % P.H, __ldcg(P.n_tokens + row) - 1, xs + warp * P.n_ctx);
+}
+
+__global__ void __launch_bounds__(MG_THREADS)
+lean_cross_attn_kernel(const WtsDecodeSteps P, const WtsDecLayer* Lr)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MgShared& sh = *reinterpret_cast<MgShared*>(smem_raw);
+    float* xs = reinterpret_cast<float*>(smem_raw + 1024);
+    pdl_launch();
+    pdl_wait();
+    build_row_list(P, sh);
+    if (blockIdx.x >= sh.n_active * P.H) return;
+    cross_attention_phase(P, *Lr, sh, xs);
+}
+
+__global__ void __launch_bounds__(MG_THREADS)
+lean_select_kernel(const WtsDecodeSteps P)
+{
+    __shared__ SelectScratch S;
+    pdl_launch();
+    pdl_wait();
+    const int row = blockIdx.x;
+    if (row >= P.cap || P.done[row] != 0) return;
+    select_row<false>(P.logits + (int64_t)row * P.cfg.n_vocab, P.cfg, P.suppress, P.blank, P.tokens + (int64_t)row * P.cfg.tokens_ld,
+                      P.n_tokens + row, P.n_prompt[row], P.done + row, P.logprobs + (int64_t)row * P.lp_ld,
+                      P.full != nullptr ? P.full + (int64_t)row * P.lp_ld * P.cfg.n_vocab : nullptr,
+                      P.last_full != nullptr ? P.last_full + (int64_t)row * P.cfg.n_vocab : nullptr, S);
+}
+
+template <int RB>
+static int launch_lean_step(const WtsDecodeSteps& P, const WtsDecLayer* h_layers, int n_sm, cudaStream_t st)
+{
+    const int D = P.D, H = P.H, V = P.cfg.n_vocab;
+    const size_t stage = (size_t)MG_STAGE_FLOATS * sizeof(float) + 1024;
+    const size_t sm_self = (size_t)MG_WARPS * P.n_ctx * sizeof(float) + 1024;
+    const size_t sm_cross = sizeof(CaScratch) + 1024;
+    static bool attr = false;
+    if (!attr) {
+        WTS_CUDA_CHECK(cudaFuncSetAttribute(lean_gemv_kernel<RB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage));
+        WTS_CUDA_CHECK(cudaFuncSetAttribute(lean_gemv_kernel<RB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage));
+        attr = true;
+    }
+    const dim3 g_gemv(n_sm), blk(MG_THREADS);
+    const dim3 g_self((P.max_rows * H + MG_WARPS - 1) / MG_WARPS), g_cross(P.max_rows * H);
+    WTS_CUDA_CHECK(launch_pdl(lean_embed_kernel, dim3(P.cap), blk, 0, st, P));
+    const float* nof = nullptr;
+    for (int li = 0; li < P.n_layer; ++li) {
+        const WtsDecLayer& L = h_layers[li];
+        const WtsDecLayer* dL = P.layers + li;
+        WTS_CUDA_CHECK(launch_pdl(lean_gemv_kernel<RB, true>, g_gemv, blk, stage, st, P, L.w_qkv, 3 * D, D, L.b_qkv, (const float*)P.x,
+                                  (int64_t)D, L.ln1_g, L.ln1_b, P.qkv, (int64_t)(3 * D), (int)EPI_STORE));
+        WTS_CUDA_CHECK(launch_pdl(lean_self_attn_kernel, g_self, blk, sm_self, st, P, dL));
+        WTS_CUDA_CHECK(launch_pdl(lean_gemv_kernel<RB, false>, g_gemv, blk, stage, st, P, L.w_o, D, D, L.b_o, (const float*)P.att,
+                                  (int64_t)D, nof, nof, P.x, (int64_t)D, (int)EPI_ADD));
+        WTS_CUDA_CHECK(launch_pdl(lean_gemv_kernel<RB, true>, g_gemv, blk, stage, st, P, L.w_cq, D, D, L.b_cq, (const float*)P.x,
+                                  (int64_t)D, L.ln2_g, L.ln2_b, P.q, (int64_t)D, (int)EPI_STORE));
+        WTS_CUDA_CHECK(launch_pdl(lean_cross_attn_kernel, g_cross, blk, sm_cross, st, P, dL));
+        WTS_CUDA_CHECK(launch_pdl(lean_gemv_kernel<RB, false>, g_gemv, blk, stage, st, P, L.w_co, D, D, L.b_co, (const float*)P.att,
+                                  (int64_t)D, nof, nof, P.x, (int64_t)D, (int)EPI_ADD));
+        WTS_CUDA_CHECK(launch_pdl(lean_gemv_kernel<RB, true>, g_gemv, blk, stage, st, P, L.w_fc1, 4 * D, D, L.b_fc1, (const float*)P.x,
+                                  (int64_t)D, L.ln3_g, L.ln3_b, P.mid, (int64_t)(4 * D), (int)EPI_GELU));
+        WTS_CUDA_CHECK(launch_pdl(lean_gemv_kernel<RB, false>, g_gemv, blk, stage, st, P, L.w_fc2, D, 4 * D, L.b_fc2, (const float*)P.mid,
+                                  (int64_t)(4 * D), nof, nof, P.x, (int64_t)D, (int)EPI_ADD));
+    }
+    WTS_CUDA_CHECK(launch_pdl(lean_gemv_kernel<RB, true>, g_gemv, blk, stage, st, P, P.emb, V, D, nof, (const float*)P.x, (int64_t)D,
+                              P.ln_g, P.ln_b, P.logits, (int64_t)V, (int)EPI_STORE));
+    WTS_CUDA_CHECK(launch_pdl(lean_select_kernel, dim3(P.cap), blk, 0, st, P));
+    return 0;
+}
+
 }  // namespace wts
 
 using namespace wts;
@@ -601,4 +738,29 @@ extern "C" int wts_decode_steps(const WtsDecodeSteps* p, void* stream)
                    : P.max_rows <= 8 ? (const void*)decode_steps_kernel<8> : (const void*)decode_steps_kernel<16>;
     WTS_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(n_sm), dim3(MG_THREADS), args, smem, st));
     return 0;
+}
+
+// One decoder step as a chain of per-phase kernels (same arithmetic as wts_decode_steps; see the comment above
+// lean_embed_kernel).  h_layers: HOST copy of the layer table (weight pointers become kernel arguments).  Capturable in a
+// CUDA graph: no host synchronisation, no memset.  2 + 8 n_layer + 1 launches.
+extern "C" int wts_decode_step_kernels(const WtsDecodeSteps* p, const WtsDecLayer* h_layers, void* stream)
+{
+    if (!p || !h_layers) { set_error("wts_decode_step_kernels: null argument"); return -2; }
+    const WtsDecodeSteps& P = *p;
+    if (P.D % 128 != 0 || P.D > 128 * MG_MAXNI || P.D != P.H * 64) {
+        set_error("wts_decode_step_kernels: n_text_state %d not supported", P.D);
+        return -2;
+    }
+    if (P.max_rows > MG_MAXROWS || P.max_rows < 1) { set_error("wts_decode_step_kernels: 1..%d active rows", MG_MAXROWS); return -2; }
+    if ((size_t)MG_WARPS * P.n_ctx * sizeof(float) + 1024 > 48 * 1024) { set_error("wts_decode_step_kernels: n_text_ctx too large"); return -2; }
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        WTS_CUDA_CHECK(cudaGetDevice(&dev));
+        WTS_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (P.max_rows <= 4) return launch_lean_step<4>(P, h_layers, n_sm, st);
+    if (P.max_rows <= 8) return launch_lean_step<8>(P, h_layers, n_sm, st);
+    return launch_lean_step<16>(P, h_layers, n_sm, st);
 }

@@ -312,18 +312,20 @@ dtw_warp_kernel(const TIn* __restrict__ cost, const WtsSegDesc* __restrict__ seg
 //    keeps 14 warps per SM resident — the dependent fp64 chain needs them;
 //  * directions stay in shared memory (2 bits per cell) for the row-wise backtrack.
 // Same recurrence, same tie-breaks, same packed direction words as dtw_fill_strip<float, true, false, true>.
-constexpr int SM_TC = 16;                    // columns per tile = wavefront steps per iteration
-constexpr int SM_LA = 2;                     // tiles in flight ahead of the one being consumed
-constexpr int SM_NT = SM_LA + 3;             // tiles in the ring: t-2, t-1 (still read by the higher lanes: 31 lanes of skew
-                                             // span two 16-column tiles), t, and t+1 .. t+LA in flight
-constexpr int SM_NB = SM_LA + 1;             // mbarriers
-constexpr int SM_RINGB = SM_NT * SM_TC * 4;  // ring bytes per row
-constexpr int SM_PITCHB = (SM_NT + 1) * SM_TC * 4;   // + mirror of slot 0 behind the ring (96 words: bank (1 - L + k) mod 32 distinct)
-constexpr int SM_TILE_BYTES = 32 * SM_PITCHB;        // rows 0..31 (row 0 = the virtual row above, stays zero)
-constexpr int SM_WARP_BYTES = SM_TILE_BYTES + DS_WORDS * 32 * 4 + 32;
-#ifndef DTW_SMALL_WARPS
-#define DTW_SMALL_WARPS 1
-#endif
+// Geometry of a variant <TC, LA>: TC columns per tile (= wavefront steps per iteration), LA tiles in flight ahead of the
+// one being consumed.  The ring holds the tiles still being read (the current one and ceil(31 / TC) behind it: the 31
+// lanes of skew), plus the LA in flight; a mirror of slot 0 sits behind the ring.  The ring length is a multiple of 32
+// words, which makes bank(L) = (pitch L + 1 - L + k + TC t) mod 32 injective over the lanes for the pitches used.
+template <int TC, int LA> struct SmGeo {
+    static constexpr int NT = LA + 1 + (31 + TC - 1) / TC;
+    static constexpr int NB = LA + 1;                        // mbarriers
+    static constexpr int RING = NT * TC;                     // words
+    static constexpr int PITCH = RING + TC;                  // words
+    static constexpr int TILE_BYTES = 32 * PITCH * 4;        // rows 0..31 (row 0 = the virtual row above, stays zero)
+    static_assert(RING % 32 == 0, "ring must be a multiple of 32 words (bank-conflict-free reads)");
+    static_assert(16 % TC == 0 || TC % 16 == 0, "tile must divide or be a multiple of a direction word");
+    static constexpr int warp_bytes(bool dirs_smem) { return TILE_BYTES + (dirs_smem ? DS_WORDS * 32 * 4 : 0) + 64; }
+};
 
 __device__ __forceinline__ void mbar_init1(uint32_t bar) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar)); }
 __device__ __forceinline__ void mbar_arrive_expect(uint32_t bar, uint32_t bytes)
@@ -348,20 +350,22 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-__global__ void __launch_bounds__(DTW_SMALL_WARPS * 32)
+template <int TC, int LA, bool DIRS_SMEM>
+__global__ void __launch_bounds__(32)
 dtw_small_kernel(const float* __restrict__ cost, const WtsSegDesc* __restrict__ segs, const int nseg,
-                 int32_t* __restrict__ jumps_out)
+                 uint32_t* __restrict__ dir_ws, int32_t* __restrict__ jumps_out)
 {
+    using G = SmGeo<TC, LA>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int seg = blockIdx.x * DTW_SMALL_WARPS + warp;
+    const int lane = threadIdx.x;
+    const int seg = blockIdx.x;                              // one warp (= one CTA) per matrix
     if (seg >= nseg) return;
     const WtsSegDesc sd = segs[seg];
     if (!dtw_small_eligible(sd)) return;                     // the general kernel owns this segment
-    unsigned char* my = smem_raw + (size_t)warp * SM_WARP_BYTES;
+    unsigned char* my = smem_raw;
     const uint32_t tile_a = smem_u32(my);
-    uint32_t* dirs = reinterpret_cast<uint32_t*>(my + SM_TILE_BYTES);
-    const uint32_t bar0 = tile_a + SM_TILE_BYTES + DS_WORDS * 32 * 4;
+    uint32_t* dirs = DIRS_SMEM ? reinterpret_cast<uint32_t*>(my + G::TILE_BYTES) : dir_ws + sd.dir_off;
+    const uint32_t bar0 = tile_a + G::TILE_BYTES + (DIRS_SMEM ? DS_WORDS * 32 * 4 : 0);
 
     const int T = sd.T, F = sd.F, P = (F + 3) & ~3;
     const float* C = cost + sd.cost_off;
@@ -369,50 +373,52 @@ dtw_small_kernel(const float* __restrict__ cost, const WtsSegDesc* __restrict__ 
     // must hold finite values (INF + 0 stays INF; they never feed a cell of the matrix)
     {
         float4* z = reinterpret_cast<float4*>(my);
-        for (int k = lane; k < SM_TILE_BYTES / 16; k += 32) z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = lane; k < G::TILE_BYTES / 16; k += 32) z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < SM_NB; ++i) mbar_init1(bar0 + 8u * i);
+        for (int i = 0; i < G::NB; ++i) mbar_init1(bar0 + 8u * i);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy zeros ordered before async-proxy writes
     __syncwarp();
 
-    const int niter = dtw_niter(F);                          // 32-step tiles of the wavefront (direction layout)
-    const int nit = 2 * niter;                               // 16-step iterations
-    const int ntile = (P + SM_TC - 1) / SM_TC;               // column tiles of the matrix
+    const int niter = dtw_niter(F);                          // 32-step tiles of the wavefront (direction layout: 2 words each)
+    const int nit = niter * (32 / TC);                       // TC-step iterations
+    const int ntile = (P + TC - 1) / TC;                     // column tiles of the matrix
     const bool owner = lane >= 1 && lane <= T;
     const char* myrow = reinterpret_cast<const char*>(C + (int64_t)(lane - 1) * P);
-    const uint32_t myrow_a = tile_a + lane * SM_PITCHB;
+    const uint32_t myrow_a = tile_a + lane * (G::PITCH * 4);
 
-    auto issue_tile = [&](int u) {                           // columns [16 u, 16 u + 15] of every row -> ring slot u % NT
-        const int ncol = min(SM_TC, P - SM_TC * u);
+    auto issue_tile = [&](int u) {                           // columns [TC u, TC u + TC) of every row -> ring slot u % NT
+        const int ncol = min(TC, P - TC * u);
         const uint32_t bytes = (uint32_t)ncol * 4u;
-        const int slot = u % SM_NT;
-        const uint32_t bar = bar0 + 8u * (u % SM_NB);
+        const int slot = u % G::NT;
+        const uint32_t bar = bar0 + 8u * (u % G::NB);
         if (lane == 0) mbar_arrive_expect(bar, bytes * (uint32_t)T * (slot == 0 ? 2u : 1u));
         if (owner) {
-            const char* src = myrow + (size_t)u * SM_TC * 4;
-            bulk_g2s(myrow_a + slot * SM_TC * 4, src, bytes, bar);
-            if (slot == 0) bulk_g2s(myrow_a + SM_RINGB, src, bytes, bar);      // mirror behind the ring
+            const char* src = myrow + (size_t)u * TC * 4;
+            bulk_g2s(myrow_a + slot * TC * 4, src, bytes, bar);
+            if (slot == 0) bulk_g2s(myrow_a + G::RING * 4, src, bytes, bar);   // mirror behind the ring
         }
     };
 
     const double INF = dinf();
     double cur = INF, upprev = INF;
     if (lane == 1) upprev = 0.0;                             // seeds cm[0,0] = 0 + lm[0,0]
-    uint32_t pb = (uint32_t)(((SM_NT * SM_TC) - lane + 1) % (SM_NT * SM_TC)) * 4u;   // 4 * ((16 t - L + 1) mod 80), t = 0
+    uint32_t pb = (uint32_t)((G::RING - lane + 1) % G::RING) * 4u;   // 4 * ((TC t - L + 1) mod RING), t = 0
+    uint32_t acc = 0;
 #pragma unroll
-    for (int u = 0; u < SM_LA; ++u)
+    for (int u = 0; u < LA; ++u)
         if (u < ntile) issue_tile(u);
     for (int t = 0; t < nit; ++t) {
-        if (t < ntile) mbar_wait_parity(bar0 + 8u * (t % SM_NB), (uint32_t)((t / SM_NB) & 1));
-        if (t + SM_LA < ntile) issue_tile(t + SM_LA);        // its ring slot held tile t - 3: last read in iteration t - 1
+        if (t < ntile) mbar_wait_parity(bar0 + 8u * (t % G::NB), (uint32_t)((t / G::NB) & 1));
+        if (t + LA < ntile) issue_tile(t + LA);              // its ring slot held a tile last read in iteration t - 1
         const uint32_t rd = myrow_a + pb;
-        uint32_t acc = 0;
+        const int s0 = (t * TC) & 15;                        // position of this tile inside its direction word
+        if (s0 == 0) acc = 0;
 #pragma unroll
-        for (int k = 0; k < SM_TC; ++k) {
+        for (int k = 0; k < TC; ++k) {
             const double l = (double)lds<float>(rd + 4 * k);
             const double up = __shfl_up_sync(FULL_MASK, cur, 1);
             const double c1 = upprev + l, c2 = cur + l, c3 = up + l;
@@ -422,13 +428,21 @@ dtw_small_kernel(const float* __restrict__ cost, const WtsSegDesc* __restrict__ 
             const double m = p2 ? c2 : c1;
             const bool p3 = (unsigned long long)__double_as_longlong(c3) > (unsigned long long)__double_as_longlong(m);
             cur = p3 ? c3 : m;
-            if (p2) acc |= 1u << (2 * k);
-            if (p3) acc |= 2u << (2 * k);
+            if (TC >= 16) {
+                if ((k & 15) == 0) acc = 0;
+                if (p2) acc |= 1u << (2 * (k & 15));
+                if (p3) acc |= 2u << (2 * (k & 15));
+                if ((k & 15) == 15) dirs[((t * TC + k) >> 4) * 32 + lane] = acc;
+            } else {
+                if (p2) acc |= (1u << (2 * k)) << (2 * s0);
+                if (p3) acc |= (2u << (2 * k)) << (2 * s0);
+            }
         }
-        dirs[t * 32 + lane] = acc;
-        pb += SM_TC * 4;
-        if (pb >= (uint32_t)SM_RINGB) pb -= SM_RINGB;
+        if (TC < 16 && s0 + TC == 16) dirs[((t * TC) >> 4) * 32 + lane] = acc;
+        pb += TC * 4;
+        if (pb >= (uint32_t)(G::RING * 4)) pb -= G::RING * 4;
     }
+    if (!DIRS_SMEM) __threadfence_block();
     __syncwarp();
     dtw_backtrack_jumps(dirs, 2 * niter, T, F, jumps_out + sd.jumps_off, lane);
 }
@@ -494,10 +508,24 @@ extern "C" int wts_dtw_batch(const void* d_cost, int32_t cost_is_f64, const WtsS
             (const float*)d_cost, d_segs, nseg, d_dir_ws, d_bnd_ws, d_jumps, d_path, d_path_off, d_path_len, use_small);
         WTS_LAUNCH_CHECK();
         if (use_small) {
-            const size_t smem_s = (size_t)DTW_SMALL_WARPS * SM_WARP_BYTES;
-            WTS_CUDA_CHECK(cudaFuncSetAttribute(dtw_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
-            dtw_small_kernel<<<(nseg + DTW_SMALL_WARPS - 1) / DTW_SMALL_WARPS, DTW_SMALL_WARPS * 32, smem_s, st>>>(
-                (const float*)d_cost, d_segs, nseg, d_jumps);
+            // geometry variants (WTS_DTW_VARIANT, default 0): <columns per tile, tiles in flight, directions in shared memory>
+            static const int variant = [] { const char* e = getenv("WTS_DTW_VARIANT"); return e ? atoi(e) : 0; }();
+#define WTS_LAUNCH_SMALL(TC_, LA_, DS_)                                                                                   \
+            do {                                                                                                          \
+                const size_t smem_s = SmGeo<TC_, LA_>::warp_bytes(DS_);                                                   \
+                WTS_CUDA_CHECK(cudaFuncSetAttribute(dtw_small_kernel<TC_, LA_, DS_>,                                      \
+                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));          \
+                dtw_small_kernel<TC_, LA_, DS_><<<nseg, 32, smem_s, st>>>((const float*)d_cost, d_segs, nseg, d_dir_ws,  \
+                                                                         d_jumps);                                       \
+            } while (0)
+            switch (variant) {
+                case 1: WTS_LAUNCH_SMALL(16, 1, false); break;
+                case 2: WTS_LAUNCH_SMALL(8, 3, true); break;
+                case 3: WTS_LAUNCH_SMALL(8, 3, false); break;
+                case 4: WTS_LAUNCH_SMALL(32, 1, true); break;
+                default: WTS_LAUNCH_SMALL(16, 1, true); break;
+            }
+#undef WTS_LAUNCH_SMALL
             WTS_LAUNCH_CHECK();
         }
         if (d_status) { dtw_status_kernel<float><<<nseg, 128, 0, st>>>((const float*)d_cost, d_segs, nseg, d_status); WTS_LAUNCH_CHECK(); }

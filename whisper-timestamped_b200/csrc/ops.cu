@@ -391,6 +391,17 @@ decode_select_kernel(float* logits, int64_t ldl, const WtsDecodeCfg cfg,
                       last_full != nullptr ? last_full + (int64_t)b * cfg.n_vocab : nullptr, S);
 }
 
+// filtered log-softmax rows only (beam search / sampling): one CTA per sequence, no state update
+__global__ void __launch_bounds__(DS_THREADS)
+filtered_logprobs_kernel(const float* logits, int64_t ldl, const WtsDecodeCfg cfg, const uint8_t* suppress, const uint8_t* blank,
+                         int32_t* tokens, int32_t* n_tokens, const int32_t* n_prompt, float* out)
+{
+    __shared__ SelectScratch S;
+    const int b = blockIdx.x;
+    select_row<false>(logits + (int64_t)b * ldl, cfg, suppress, blank, tokens + (int64_t)b * cfg.tokens_ld, n_tokens + b,
+                      n_prompt[b], nullptr, nullptr, out + (int64_t)b * cfg.n_vocab, nullptr, S, true);
+}
+
 __global__ void step_inputs_kernel(const int32_t* tokens, int ld, const int32_t* n_tokens,
                                    const int32_t* n_prompt, const int32_t* done, int B,
                                    int32_t* tok, int32_t* pos, int32_t* qk_row,
@@ -607,6 +618,21 @@ extern "C" int wts_decode_select(float* d_logits, int64_t ldl, const WtsDecodeCf
     WTS_CUDA_CHECK(launch_pdl(decode_select_kernel, dim3(B), dim3(DS_THREADS), 0, (cudaStream_t)stream, d_logits, ldl, *cfg, d_suppress, d_blank, d_tokens,
                                                                     d_n_tokens, d_n_prompt, d_done, d_logprobs, lp_ld,
                                                                     d_full_logprobs, d_last_full));
+    WTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int wts_filtered_logprobs(const float* d_logits, int64_t ldl, const WtsDecodeCfg* cfg, const uint8_t* d_suppress,
+                                     const uint8_t* d_blank, int32_t* d_tokens, int32_t* d_n_tokens, const int32_t* d_n_prompt,
+                                     float* d_out, int32_t B, void* stream)
+{
+    if (B <= 0) return 0;
+    if (!d_logits || !cfg || !d_suppress || !d_blank || !d_tokens || !d_n_tokens || !d_n_prompt || !d_out) {
+        set_error("wts_filtered_logprobs: null pointer");
+        return -2;
+    }
+    filtered_logprobs_kernel<<<B, DS_THREADS, 0, (cudaStream_t)stream>>>(d_logits, ldl, *cfg, d_suppress, d_blank, d_tokens,
+                                                                         d_n_tokens, d_n_prompt, d_out);
     WTS_LAUNCH_CHECK();
     return 0;
 }

@@ -119,8 +119,12 @@ def _load():
     lib.wts_enc_attention.restype = ctypes.c_int
     lib.wts_kv_append.argtypes = [vp, vp, i64, vp, vp, i32, i32, i32, vp, vp, i64, vp]
     lib.wts_decode_select.argtypes = [vp, i64, ctypes.POINTER(DecodeCfg), vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, vp]
+    lib.wts_filtered_logprobs.argtypes = [vp, i64, ctypes.POINTER(DecodeCfg), vp, vp, vp, vp, vp, vp, i32, vp]
+    lib.wts_filtered_logprobs.restype = ctypes.c_int
     lib.wts_decode_steps.argtypes = [ctypes.POINTER(DecodeSteps), vp]
     lib.wts_decode_steps.restype = ctypes.c_int
+    lib.wts_decode_step_kernels.argtypes = [ctypes.POINTER(DecodeSteps), vp, vp]
+    lib.wts_decode_step_kernels.restype = ctypes.c_int
     lib.wts_step_inputs.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp]
     lib.wts_softmax_pick.argtypes = [vp, i64, i32, i32, vp, i32, vp]
     lib.wts_logprob_gather.argtypes = [vp, i64, i32, vp, vp, vp, i32, vp]
@@ -138,7 +142,7 @@ EXPORTED_SYMBOLS = [
     "wts_version", "wts_last_error", "wts_dtw_dir_words", "wts_dtw_bnd_doubles",
     "wts_attn_prep_batch", "wts_dtw_batch", "wts_disfluency_starts", "wts_gemm", "wts_to_sb16", "wts_layernorm", "wts_softmax_rows",
     "wts_frames", "wts_power", "wts_logmel_max", "wts_logmel_finish", "wts_window_gather", "wts_embed",
-    "wts_gather_rows", "wts_decoder_attention", "wts_kv_append", "wts_decode_select", "wts_decode_steps", "wts_step_inputs",
+    "wts_gather_rows", "wts_decoder_attention", "wts_kv_append", "wts_decode_select", "wts_filtered_logprobs", "wts_decode_steps", "wts_decode_step_kernels", "wts_step_inputs",
     "wts_softmax_pick", "wts_logprob_gather", "wts_cross_kv_pack", "wts_cross_attention_f16", "wts_enc_attention",
 ]
 

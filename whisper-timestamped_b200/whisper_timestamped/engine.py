@@ -53,6 +53,9 @@ class CudaEngine:
         self.small_batch_rows = min(32, int(os.environ.get("WTS_SMALL_BATCH_ROWS", "32")) if small_batch_rows is None
                                     else int(small_batch_rows))
         self.small_batch_steps = 0
+        # how the small-batch steps run: "lean" = chain of per-phase kernels replayed as a CUDA graph (default),
+        # "persistent" = one cooperative kernel with software grid barriers (measured slower on B200: ~5 us per barrier)
+        self.small_batch_mode = os.environ.get("WTS_SMALL_BATCH_MODE", "lean")
         self._graphs = {}
         self.profile = False            # when set, phases are bracketed with CUDA events (stage_ms())
         self._events = []
@@ -327,6 +330,9 @@ class CudaEngine:
         self.gemm(hs, w.emb_sb, n_rows, V, D, out_f32=logits, ldc=V)
 
     def decode_windows(self, jobs, setup):
+        if getattr(setup, "beam_size", None) is not None or setup.temperature > 0:
+            # upstream decoding strategies (beam search / best-of-n sampling): one window at a time, n_group hypotheses
+            return [self._decode_strategy(job, setup) for job in jobs]
         out = []
         for i in range(0, len(jobs), self.max_batch):
             out.extend(self._decode_batch(jobs[i:i + self.max_batch], setup))
@@ -420,7 +426,36 @@ class CudaEngine:
         p.cfg = ses["cfg"]
         p.n_layer, p.D, p.H, p.n_ctx, p.n_audio_ctx = L, D, H, d.n_text_ctx, N_CTX_AUDIO
         p.n_slots, p.cap, p.lp_ld, p.qk_rows = max(1, len(self.m.heads)), cap, ses["qk_rows"], ses["qk_rows"]
-        return dict(args=p, keep=keep)
+        return dict(args=p, keep=keep, host_layers=layers, graphs={})
+
+    def _lean_graph(self, ses, n_active):
+        """CUDA graph of ONE decoder step as the chain of lean per-phase kernels (wts_decode_step_kernels), for the
+        rows-per-pass variant that fits `n_active` (4 / 8 / 16 / 32 rows); captured on first use."""
+        sd = ses["steps"]
+        rows = 4 if n_active <= 4 else 8 if n_active <= 8 else 16 if n_active <= 16 else 32
+        if rows in sd["graphs"]:
+            return sd["graphs"][rows]
+        dev = self.dev
+        p = sd["args"]
+
+        def launch():
+            p.max_rows, p.n_steps = rows, 1
+            nat.check(nat.lib.wts_decode_step_kernels(ctypes.byref(p), ctypes.byref(sd["host_layers"]), self._st()),
+                      "wts_decode_step_kernels")
+        saved = {k: ses[k].clone() for k in ("tokens", "n_tokens", "done", "logprobs")}
+        launch()                                   # warm-up outside capture (module loading, function attributes) ...
+        torch.cuda.synchronize(dev)
+        for k, v in saved.items():                 # ... undone: it is not a decode step of the caller
+            ses[k].copy_(v)
+        graph = torch.cuda.CUDAGraph()
+        cap_stream = torch.cuda.Stream(device=dev)
+        cap_stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(cap_stream):
+            with torch.cuda.graph(graph, stream=cap_stream):
+                launch()
+        torch.cuda.current_stream(dev).wait_stream(cap_stream)
+        sd["graphs"][rows] = graph
+        return graph
 
     def _step_graph(self, ses):
         """ONE captured CUDA graph of a per-operator decode step (captured on first use; the capture itself runs no
@@ -468,6 +503,12 @@ class CudaEngine:
 
     def _step(self, ses):
         """One decode step for all `cap` slots (identical launch sequence every step: CUDA-graph friendly)."""
+        self._step_logits(ses)
+        self._select(ses, ses["logits"], ses["cap"])
+        self.launches += 1
+
+    def _step_logits(self, ses):
+        """The forward part of a decode step: logits of the next position of every active slot (no choice made)."""
         d, w, st = self.dims, self.w, self._st()
         cap, D = ses["cap"], d.n_text_state
         nat.check(nat.lib.wts_step_inputs(ses["tokens"].data_ptr(), d.n_text_ctx + 1, ses["n_tokens"].data_ptr(),
@@ -479,8 +520,7 @@ class CudaEngine:
         self._decoder_rows(ses["st8"], ses["xs"], cap, ses["seq_ids"], ses["s_pos"], ses["s_qkr"], ses["qk_buf"],
                            active=ses["s_act"])
         self._final_logits_static(ses["xs"], cap, ses["logits"], ses["st8"], active=ses["s_act"])
-        self._select(ses, ses["logits"], cap)
-        self.launches += 2
+        self.launches += 1
 
     @torch.no_grad()
     def _decode_batch(self, jobs, setup):
@@ -562,8 +602,17 @@ class CudaEngine:
         n_active = B
         while steps_done < max_steps and n_active > 0:
             left = max_steps - steps_done
-            if ses["steps"] is not None and n_active <= self.small_batch_rows:
-                # few sequences left: one persistent launch runs up to 32 whole steps (it stops by itself when all are done)
+            if ses["steps"] is not None and n_active <= self.small_batch_rows and self.small_batch_mode == "lean":
+                # few sequences left: the lean per-phase kernels (float32 matrix-vector products, LayerNorm fused into the
+                # staging), one CUDA graph per step
+                chunk = min(8, left)
+                graph = self._lean_graph(ses, n_active)
+                for _ in range(chunk):
+                    graph.replay()
+                self.launches += chunk * (8 * d.n_text_layer + 3)
+                self.small_batch_steps += chunk
+            elif ses["steps"] is not None and n_active <= self.small_batch_rows:
+                # one persistent launch runs up to 32 whole steps (it stops by itself when all are done)
                 chunk = min(32, left)
                 self._run_steps(ses, chunk, n_active)
                 self.small_batch_steps += chunk
@@ -624,6 +673,179 @@ class CudaEngine:
                                         no_speech_prob=float(ns_h[b]), qk_window=gid, temperature=0.0,
                                         language=tok.language, last_row_logprobs=last_lp))
         return records
+
+    # ------------------------------------------------------------------ beam search / sampling (upstream strategies)
+    @torch.no_grad()
+    def _decode_strategy(self, job, setup):
+        """One window through upstream's BeamSearchDecoder (temperature 0, beam_size hypotheses) or GreedyDecoder at a
+        temperature > 0 (best_of sampled hypotheses), MaximumLikelihoodRanker on top — what the reference reaches through
+        model.transcribe() in its two-pass strategy (T.py:1068; options T.py:104-113).
+
+        The forward of every step (all hypotheses = rows of the per-operator step: KV caches, attention, tensor-core
+        GEMMs) and the logit filters + log-softmax (wts_filtered_logprobs) run on the device; the hypothesis
+        bookkeeping is upstream's, on the host: top-(beam+1) candidates per row, de-duplicated per sequence, best
+        beam_size kept, finished pool, patience; sampling draws from torch's global CPU generator exactly like the
+        reference on CPU does (Categorical over the filtered rows).  KV-cache rows follow their source hypothesis."""
+        d, dev, st, w = self.dims, self.dev, self._st(), self.w
+        tok = setup.tokenizer
+        G = setup.n_group
+        beam = setup.beam_size
+        T = float(setup.temperature)
+        ses = self._decoder_session(setup, G)
+        cap, st8 = ses["cap"], ses["st8"]
+        D, V, L, n_ctx = d.n_text_state, d.n_vocab, d.n_text_layer, d.n_text_ctx
+        f32 = dict(dtype=torch.float32, device=dev)
+        with self.phase("encoder"):
+            xa = self.encode([job])
+        with self.phase("cross_kv"):
+            self._cross_kv(xa, st8, 1)
+            for li in range(L):                          # every hypothesis attends to the same audio
+                for name in ("ck", "cv", "ckal"):
+                    t = st8[name][li]
+                    if G > 1:
+                        t[1:G].copy_(t[0:1].expand(G - 1, *t.shape[1:]))
+        del xa
+        prompt = list(job["prompt"])
+        P = len(prompt)
+        tokens_h = np.zeros((cap, n_ctx + 1), dtype=np.int32)
+        tokens_h[:G, :P] = prompt
+        ses["tokens"].copy_(torch.from_numpy(tokens_h))
+        nt = np.ones(cap, dtype=np.int32)
+        nt[:G] = P
+        ses["n_tokens"].copy_(torch.from_numpy(nt))
+        ses["n_prompt"].copy_(torch.from_numpy(nt))
+        dn = np.ones(cap, dtype=np.int32)
+        dn[:G] = 0
+        ses["done"].copy_(torch.from_numpy(dn))
+        ses["suppress"].zero_()
+        ses["suppress"][torch.as_tensor(list(setup.suppress_tokens), dtype=torch.long, device=dev)] = 1
+        ses["blank"].zero_()
+        if setup.blank_tokens:
+            ses["blank"][torch.as_tensor(list(setup.blank_tokens), dtype=torch.long, device=dev)] = 1
+        # ---- prefill of hypothesis 0, then its self-attention cache is shared out
+        with self.phase("prefill"):
+            row_seq = _i32([0] * P, dev)
+            row_pos = _i32(list(range(P)), dev)
+            row_tok = _i32(prompt, dev)
+            qk_row = _i32([-1] * P, dev)
+            pre = dict(st8)
+            pre.update(hs=SB16(P, D, dev), att=SB16(P, D, dev), mid=SB16(P, 4 * D, dev),
+                       qkv=torch.empty((P, 3 * D), **f32), q=torch.empty((P, D), **f32))
+            x = torch.empty((P, D), **f32)
+            nat.check(nat.lib.wts_embed(row_tok.data_ptr(), row_pos.data_ptr(), w.emb.data_ptr(), w.dec_pos.data_ptr(), P, D,
+                                        x.data_ptr(), st), "wts_embed")
+            self._decoder_rows(pre, x, P, row_seq, row_pos, qk_row, ses["qk_buf"])
+            sel = _i32([P - 1, prompt.index(tok.sot)], dev)
+            xr = torch.empty((2, D), **f32)
+            nat.check(nat.lib.wts_gather_rows(x.data_ptr(), D, sel.data_ptr(), 2, D, xr.data_ptr(), st), "wts_gather_rows")
+            logits2 = torch.empty((2, V), **f32)
+            self._final_logits(xr, 2, logits2)
+            no_speech = torch.zeros(1, **f32)
+            if tok.no_speech is not None:
+                nat.check(nat.lib.wts_softmax_pick(logits2.data_ptr() + 4 * V, V, V, tok.no_speech, no_speech.data_ptr(), 1, st),
+                          "wts_softmax_pick")
+            for li in range(L):
+                for name in ("sk", "sv"):
+                    t = st8[name][li]
+                    if G > 1:
+                        t[1:G, :, :P].copy_(t[0:1, :, :P].expand(G - 1, t.shape[1], P, t.shape[3]))
+            ses["logits"][:G].copy_(logits2[0:1].expand(G, V))
+            self.launches += 6
+        del pre, x, xr
+        # ---- upstream's main loop
+        lp_dev = torch.empty((cap, V), **f32)
+        seqs = [list(prompt) for _ in range(G)]
+        sum_lp = torch.zeros(G, dtype=torch.float32)              # float32 arithmetic like upstream's tensor
+        finished = {}                                              # beam search: sequence (tuple) -> cumulative log-prob
+        max_candidates = round(beam * (setup.patience or 1.0)) if beam else 0
+        ph = self.phase("decode_steps")
+        ph.__enter__()
+        for i in range(setup.sample_len):
+            nat.check(nat.lib.wts_filtered_logprobs(ses["logits"].data_ptr(), V, ctypes.byref(ses["cfg"]), ses["suppress"].data_ptr(),
+                                                    ses["blank"].data_ptr(), ses["tokens"].data_ptr(), ses["n_tokens"].data_ptr(),
+                                                    ses["n_prompt"].data_ptr(), lp_dev.data_ptr(), G, st), "wts_filtered_logprobs")
+            self.launches += 1
+            source = list(range(G))
+            if beam:
+                vals, idxs = torch.topk(lp_dev[:G], beam + 1, dim=-1)
+                vals, idxs = vals.cpu(), idxs.cpu()
+                scores, sources = {}, {}
+                for j in range(G):
+                    prefix = seqs[j]
+                    for logprob, token in zip(vals[j], idxs[j]):
+                        sequence = tuple(prefix + [int(token)])
+                        scores[sequence] = (sum_lp[j] + logprob).item()
+                        sources[sequence] = j
+                new_seqs, source, newly_finished = [], [], {}
+                for sequence in sorted(scores, key=scores.get, reverse=True):
+                    if sequence[-1] == tok.eot:
+                        newly_finished[sequence] = scores[sequence]
+                    else:
+                        sum_lp[len(new_seqs)] = scores[sequence]
+                        new_seqs.append(list(sequence))
+                        source.append(sources[sequence])
+                        if len(new_seqs) == beam:
+                            break
+                for seq in sorted(newly_finished, key=newly_finished.get, reverse=True):
+                    if len(finished) >= max_candidates:
+                        break
+                    finished[seq] = newly_finished[seq]
+                seqs = new_seqs
+                completed = len(finished) >= max_candidates
+            else:
+                lp = lp_dev[:G].cpu()
+                nxt = torch.distributions.Categorical(logits=lp / T).sample()
+                last = torch.tensor([s_[-1] for s_ in seqs])
+                sum_lp += lp[torch.arange(G), nxt] * (last != tok.eot)
+                nxt[last == tok.eot] = tok.eot
+                for s_, t_ in zip(seqs, nxt.tolist()):
+                    s_.append(t_)
+                completed = bool((nxt == tok.eot).all())
+            cur = len(seqs[0])
+            if completed or cur > n_ctx:
+                break
+            if i + 1 == setup.sample_len:
+                break
+            # ---- device state follows the host: caches of the source hypotheses, new token rows, next logits
+            if source != list(range(G)):
+                src = torch.as_tensor(source, dtype=torch.long, device=dev)
+                for li in range(L):
+                    for name in ("sk", "sv"):
+                        t = st8[name][li]
+                        t[:G, :, :cur - 1] = t[src, :, :cur - 1]
+            th = np.zeros((G, n_ctx + 1), dtype=np.int32)
+            for r, s_ in enumerate(seqs):
+                th[r, :cur] = s_
+            ses["tokens"][:G].copy_(torch.from_numpy(th))
+            ses["n_tokens"][:G].fill_(cur)
+            self._step_logits(ses)
+        ph.__exit__()
+        # ---- finalize + rank (upstream BeamSearchDecoder.finalize / GreedyDecoder.finalize, MaximumLikelihoodRanker)
+        if beam:
+            if len(finished) < beam:
+                for j in list(np.argsort(sum_lp.numpy()))[::-1]:
+                    finished[tuple(seqs[j] + [tok.eot])] = sum_lp[j].item()
+                    if len(finished) >= beam:
+                        break
+            cands = [list(k) for k in finished.keys()]
+            cand_lp = list(finished.values())
+        else:
+            cands = [s_ + [tok.eot] for s_ in seqs]
+            cand_lp = sum_lp.tolist()
+        cut = []
+        for c in cands:
+            body = c[P:]
+            cut.append(body[:body.index(tok.eot)])
+        lp_len = [len(c) for c in cut]
+        if setup.length_penalty is None:
+            score = [lp / n if n else (float("-inf") if lp < 0 else float("inf")) for lp, n in zip(cand_lp, lp_len)]
+        else:
+            score = [lp / (((5 + n) / 6) ** setup.length_penalty) for lp, n in zip(cand_lp, lp_len)]
+        best = int(np.argmax(score))
+        torch.cuda.synchronize(dev)
+        return WindowRecord(seek=job["seek"], segment_size=job["segment_size"], prompt=prompt, tokens=cut[best], logprobs=None,
+                            ended_by_eot=True, no_speech_prob=float(no_speech.cpu()[0]), qk_window=-1, temperature=T,
+                            language=tok.language, sum_logprob=float(cand_lp[best]))
 
     def _final_logits_static(self, x_rows, n_rows, logits, st8, active=None):
         d, w = self.dims, self.w

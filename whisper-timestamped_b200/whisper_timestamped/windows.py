@@ -255,6 +255,15 @@ def plan_window_alignment(rec: WindowRecord, setup: DecodeSetup, next_prompt: Op
             plans.append(final_plan)
         else:
             final_plan = None
+    for plan in plans:
+        # T.py:529-538: the reference re-estimates an end timestamp that is not after the start one from the full last
+        # log-prob row.  With greedy decoding under ApplyTimestampRules a closing timestamp is strictly greater than the
+        # opening one, so this cannot happen on the built paths; if it ever does (new sampling rules, a fallback token
+        # taken from the next prompt), fail loudly instead of silently diverging from the reference.
+        if len(plan.tokens) >= 2 and plan.tokens[0] >= ts0 and plan.tokens[-1] >= ts0 and plan.tokens[-1] <= plan.tokens[0]:
+            raise NotImplementedError(
+                f"segment ends with timestamp {plan.tokens[-1]} <= its start {plan.tokens[0]}: the reference re-estimates "
+                "the end from the last log-prob row (T.py:529-538), which this drop-in does not keep per row")
     info = dict(n_fed=n_fed, reached=reached, last_chunk_token=last_chunk_token,
                 final_unfinished=bool(final_plan and final_plan.unfinished))
     return plans, info
