@@ -265,7 +265,7 @@ typedef struct WtsDecodeSteps {
     float *logprobs, *full, *last_full, *qk_buf;                     /* full / last_full optional */
     const uint8_t *suppress, *blank;
     float *x, *qkv, *att, *q, *mid, *logits;                         /* scratch: [cap, D], [cap, 3D], [cap, D], [cap, D], [cap, 4D], [cap, V] */
-    uint32_t* sync;                                                  /* [512]: [1] error flag, [2] steps completed, [64 + c] barrier generation published by CTA c */
+    uint32_t* sync;                                                  /* [64] (two 128-byte lines): [0] barrier arrivals, [1] error flag, [2] steps completed, [32] barrier generation */
     uint64_t* prof;                                                  /* optional: %globaltimer of CTA 0 after every grid barrier */
     WtsDecodeCfg cfg;
     int32_t n_layer, D, H, n_ctx, n_audio_ctx, n_slots, cap, lp_ld, qk_rows, n_steps, max_rows, prof_cap;

@@ -45,11 +45,11 @@ __device__ __forceinline__ float4 ldg_stream4(const float* p)
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// ---- grid-wide barrier, flag array: every CTA publishes the barrier generation in ITS OWN word (one release store,
-// nothing to wait for), then warp 0 polls all gridDim.x words (32 per coalesced acquire load) until none is behind.
-// No atomics and no second hop through a "last arriver": measured on the B200, a counter barrier (atomic add + polling,
-// with or without a separate generation word) costs ~5-6 us per barrier with 148 CTAs across the two dies.
-// sync[1] = error flag, sync[2] = steps completed, sync[64 + c] = generation published by CTA c.
+// ---- grid-wide barrier.  Arrivals are one release-add per CTA on a counter; the LAST arriver publishes the new
+// generation on a different 128-byte line, which is the only thing the other CTAs poll (acquire loads with a short
+// back-off) — polls never contend with the arriving atomics (measured: polling the counter itself cost ~6 us per
+// barrier with 148 CTAs; a flag-array barrier — every CTA publishes its generation, warp 0 polls all 148 words — was
+// slower still: ~8 us).  sync[0] = arrivals, sync[1] = error flag, sync[2] = steps completed, sync[32] = generation.
 // A spin limit turns a would-be hang (a bug, or a grid that is not co-resident) into an error flag the host reports.
 __device__ __forceinline__ void grid_sync(uint32_t* sync, uint32_t& gen, MgShared& sh)
 {
@@ -57,26 +57,25 @@ __device__ __forceinline__ void grid_sync(uint32_t* sync, uint32_t& gen, MgShare
     gen += 1;
     if (threadIdx.x == 0 && !sh.abort_flag) {
         __threadfence();
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(sync + 64 + blockIdx.x), "r"(gen) : "memory");
-    }
-    if (threadIdx.x < 32 && !sh.abort_flag) {
-        const int lane = threadIdx.x;
-        int spins = 0;
-        while (true) {
-            bool behind = false;
-            for (int c = lane; c < (int)gridDim.x; c += 32) {
-                uint32_t g;
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g) : "l"(sync + 64 + c) : "memory");
-                behind |= (int32_t)(g - gen) < 0;
-            }
-            if (!__any_sync(FULL_MASK, behind)) break;
-            if ((++spins & 255) == 0) {
-                uint32_t e = 0;
-                if (lane == 0) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(e) : "l"(sync + 1) : "memory");
-                e = __shfl_sync(FULL_MASK, e, 0);
-                if (e != 0 || spins > (1 << 20)) {           // ~1 s of polling: a bug, or a grid that is not co-resident
-                    if (lane == 0) { atomicExch(sync + 1, 1u); sh.abort_flag = 1; }
-                    break;
+        uint32_t old;
+        asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(sync) : "memory");
+        if (old + 1 == gen * gridDim.x) {
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(sync + 32), "r"(gen) : "memory");
+        } else {
+            uint32_t g;
+            int spins = 0;
+            while (true) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g) : "l"(sync + 32) : "memory");
+                if (g >= gen) break;
+                __nanosleep(20);
+                if ((++spins & 1023) == 0) {
+                    uint32_t e;
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(e) : "l"(sync + 1) : "memory");
+                    if (e != 0 || spins > (1 << 22)) {       // ~1 s of polling: a bug, or a grid that is not co-resident
+                        atomicExch(sync + 1, 1u);
+                        sh.abort_flag = 1;
+                        break;
+                    }
                 }
             }
         }
@@ -734,7 +733,7 @@ extern "C" int wts_decode_steps(const WtsDecodeSteps* p, void* stream)
         WTS_CUDA_CHECK(cudaFuncSetAttribute(decode_steps_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
-    WTS_CUDA_CHECK(cudaMemsetAsync(P.sync, 0, 512 * sizeof(uint32_t), st));
+    WTS_CUDA_CHECK(cudaMemsetAsync(P.sync, 0, 64 * sizeof(uint32_t), st));
     void* args[] = {const_cast<WtsDecodeSteps*>(p)};
     const void* fn = P.max_rows <= 4 ? (const void*)decode_steps_kernel<4>
                    : P.max_rows <= 8 ? (const void*)decode_steps_kernel<8> : (const void*)decode_steps_kernel<16>;

@@ -350,7 +350,19 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-template <int TC, int LA, bool DIRS_SMEM>
+// float32 -> float64 widening on the INTEGER pipe (exact for zeros and normal numbers; `ok` = false for denormals, inf and
+// nan, which the caller widens with the fp64-pipe conversion instead).  Experiment WTS_DTW_VARIANT=5: takes one of the four
+// fp64-pipe instructions of an anti-diagonal step (3 DADD + 1 F2F) off that pipe.
+__device__ __forceinline__ double widen_f32_int(uint32_t u, bool& ok)
+{
+    const uint32_t mag = u & 0x7fffffffu;
+    const uint32_t e = mag >> 23;
+    ok = (e != 255u) && (e != 0u || mag == 0u);
+    const uint32_t hi = (mag == 0u ? 0u : (mag >> 3) + 0x38000000u) | (u & 0x80000000u);
+    return __hiloint2double((int)hi, (int)(u << 29));
+}
+
+template <int TC, int LA, bool DIRS_SMEM, bool INTW = false>
 __global__ void __launch_bounds__(32)
 dtw_small_kernel(const float* __restrict__ cost, const WtsSegDesc* __restrict__ segs, const int nseg,
                  uint32_t* __restrict__ dir_ws, int32_t* __restrict__ jumps_out, const int l2_prefetch)
@@ -369,10 +381,9 @@ dtw_small_kernel(const float* __restrict__ cost, const WtsSegDesc* __restrict__ 
 
     const int T = sd.T, F = sd.F, P = (F + 3) & ~3;
     const float* C = cost + sd.cost_off;
-    // The tile copies below fetch 64..128-byte pieces 4 P bytes apart: measured, HBM serves that pattern at ~1.5 TB/s
-    // whatever the occupancy or the instruction count (four ring geometries, 11..22 warps per SM, all at 0.32 ms for
-    // 16384 matrices).  One bulk L2 prefetch of the whole contiguous matrix (T x P float32, <= 44 KB) turns the DRAM
-    // side into a sequential stream; the tile copies then hit L2.
+    // Optional (WTS_DTW_L2PF=1): one bulk L2 prefetch of the whole contiguous matrix (T x P float32, <= 44 KB), so that
+    // the 64..128-byte tile copies hit L2.  Measured: no effect (0.329 vs 0.323 ms for 16384 matrices) — the kernel is
+    // not bound by the DRAM access pattern.
     if (lane == 0 && l2_prefetch)
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(C), "r"((uint32_t)(T * P * 4)) : "memory");
     // zero the row buffers once: cells read before their tile arrives (j < 0), rows beyond T and the virtual row 0
@@ -425,7 +436,15 @@ dtw_small_kernel(const float* __restrict__ cost, const WtsSegDesc* __restrict__ 
         if (s0 == 0) acc = 0;
 #pragma unroll
         for (int k = 0; k < TC; ++k) {
-            const double l = (double)lds<float>(rd + 4 * k);
+            double l;
+            if (INTW) {
+                const float lf = lds<float>(rd + 4 * k);
+                bool ok;
+                l = widen_f32_int(__float_as_uint(lf), ok);
+                if (__any_sync(FULL_MASK, !ok)) l = (double)lf;      // denormal / non-finite somewhere in the warp: rare
+            } else {
+                l = (double)lds<float>(rd + 4 * k);
+            }
             const double up = __shfl_up_sync(FULL_MASK, cur, 1);
             const double c1 = upprev + l, c2 = cur + l, c3 = up + l;
             upprev = up;
@@ -516,21 +535,22 @@ extern "C" int wts_dtw_batch(const void* d_cost, int32_t cost_is_f64, const WtsS
         if (use_small) {
             // geometry variants (WTS_DTW_VARIANT, default 0): <columns per tile, tiles in flight, directions in shared memory>
             static const int variant = [] { const char* e = getenv("WTS_DTW_VARIANT"); return e ? atoi(e) : 0; }();
-            static const int l2pf = [] { const char* e = getenv("WTS_DTW_L2PF"); return e ? atoi(e) : 1; }();
-#define WTS_LAUNCH_SMALL(TC_, LA_, DS_)                                                                                   \
+            static const int l2pf = [] { const char* e = getenv("WTS_DTW_L2PF"); return e ? atoi(e) : 0; }();   // measured: no effect
+#define WTS_LAUNCH_SMALL(TC_, LA_, DS_, IW_)                                                                              \
             do {                                                                                                          \
                 const size_t smem_s = SmGeo<TC_, LA_>::warp_bytes(DS_);                                                   \
-                WTS_CUDA_CHECK(cudaFuncSetAttribute(dtw_small_kernel<TC_, LA_, DS_>,                                      \
+                WTS_CUDA_CHECK(cudaFuncSetAttribute(dtw_small_kernel<TC_, LA_, DS_, IW_>,                                 \
                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));          \
-                dtw_small_kernel<TC_, LA_, DS_><<<nseg, 32, smem_s, st>>>((const float*)d_cost, d_segs, nseg, d_dir_ws,  \
-                                                                         d_jumps, l2pf);                                 \
+                dtw_small_kernel<TC_, LA_, DS_, IW_><<<nseg, 32, smem_s, st>>>((const float*)d_cost, d_segs, nseg,       \
+                                                                              d_dir_ws, d_jumps, l2pf);                  \
             } while (0)
             switch (variant) {
-                case 1: WTS_LAUNCH_SMALL(16, 1, false); break;
-                case 2: WTS_LAUNCH_SMALL(8, 3, true); break;
-                case 3: WTS_LAUNCH_SMALL(8, 3, false); break;
-                case 4: WTS_LAUNCH_SMALL(32, 1, true); break;
-                default: WTS_LAUNCH_SMALL(16, 1, true); break;
+                case 1: WTS_LAUNCH_SMALL(16, 1, false, false); break;
+                case 2: WTS_LAUNCH_SMALL(8, 3, true, false); break;
+                case 3: WTS_LAUNCH_SMALL(8, 3, false, false); break;
+                case 4: WTS_LAUNCH_SMALL(32, 1, true, false); break;
+                case 5: WTS_LAUNCH_SMALL(16, 1, false, true); break;
+                default: WTS_LAUNCH_SMALL(16, 1, true, false); break;
             }
 #undef WTS_LAUNCH_SMALL
             WTS_LAUNCH_CHECK();

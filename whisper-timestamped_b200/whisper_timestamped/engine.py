@@ -412,7 +412,7 @@ class CudaEngine:
         f32 = dict(dtype=torch.float32, device=dev)
         keep = dict(layers=torch.from_numpy(raw).to(dev), x=torch.zeros((cap, D), **f32), qkv=torch.zeros((cap, 3 * D), **f32),
                     att=torch.zeros((cap, D), **f32), q=torch.zeros((cap, D), **f32), mid=torch.zeros((cap, 4 * D), **f32),
-                    sync=torch.zeros(512, dtype=torch.int32, device=dev))
+                    sync=torch.zeros(64, dtype=torch.int32, device=dev))
         p = nat.DecodeSteps()
         p.layers = keep["layers"].data_ptr()
         p.emb, p.pos, p.ln_g, p.ln_b = w.emb.data_ptr(), w.dec_pos.data_ptr(), w.ln_g.data_ptr(), w.ln_b.data_ptr()
