@@ -272,9 +272,9 @@ __device__ __noinline__ void gemv_phase(const float* __restrict__ W, int N, int 
     const int ntasks = (N + MG_G - 1) / MG_G;
     const int rounds = (ntasks + total_warps - 1) / total_warps;
     const int npass = (nA + RB - 1) / RB;
-    // Either every active row with all K columns fits the staging buffer (always when K == D): staged ONCE for all
+    // Either every pass's RB rows with all K columns fit the staging buffer (always when K == D): staged ONCE for all
     // rounds and passes.  Or (FC2 with more than 8 active rows) each pass stages its own rows in chunks of Kc columns.
-    const bool once = nA * K <= MG_STAGE_FLOATS;
+    const bool once = npass * RB * K <= MG_STAGE_FLOATS;     // a pass reads RB rows of the buffer whatever nA is
     const int Kc = once ? K : (MG_STAGE_FLOATS / (RB * D)) * D;
     const int nchunks = (K + Kc - 1) / Kc;
     if (once) stage_rows<LN>(src, lds, 0, K, 0, nA, gam, bet, sh, xs);
