@@ -721,7 +721,7 @@ extern "C" int wts_decode_steps(const WtsDecodeSteps* p, void* stream)
         WTS_CUDA_CHECK(cudaGetDevice(&dev));
         WTS_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     }
-    const size_t stage = (size_t)MG_MAXROWS * P.D * sizeof(float);
+    const size_t stage = (size_t)MG_STAGE_FLOATS * sizeof(float);             // gemv_phase sizes its chunks for this capacity
     size_t smem = stage > sizeof(CaScratch) ? stage : sizeof(CaScratch);
     const size_t sa = (size_t)MG_WARPS * P.n_ctx * sizeof(float);             // self-attention score scratch
     if (sa > smem) smem = sa;

@@ -302,8 +302,9 @@ dtw_warp_kernel(const TIn* __restrict__ cost, const WtsSegDesc* __restrict__ seg
 // padded to 16 bytes) gets its own kernel, built to spend as few issue slots per anti-diagonal as the bit-exact fp64
 // recurrence allows (the general kernel above is ISSUE-bound: ~40 warp instructions per step of which the recurrence
 // needs ~17, profiles/r1c_dtw_summary.md):
-//  * staging is ONE predicated instruction per 16-column tile: every lane L (1..T) issues a 64-byte 1-D bulk copy
-//    (cp.async.bulk, TMA) of its own row's tile, two tiles ahead; completion is counted by mbarriers (three, rotating);
+//  * staging is 16-byte cp.async (LDGSTS.128): one warp instruction moves 8 rows x 16 columns of a tile, i.e. four
+//    instructions per tile of up to 31 rows, one tile ahead, completion by cp.async groups (rows are padded to 16 bytes
+//    so every chunk is aligned);
 //  * the row buffers are NOT skewed: a ring of five tiles (t-2 .. t being read — the 31 lanes of skew span two
 //    tiles back —, t+1 and t+2 in flight) plus a mirror of slot 0 behind the ring, so lane L reads
 //    `row_base + 4 p_L + 4 k` at step k of a tile — an immediate offset with no wrap inside the tile
@@ -326,29 +327,6 @@ template <int TC, int LA> struct SmGeo {
     static_assert(16 % TC == 0 || TC % 16 == 0, "tile must divide or be a multiple of a direction word");
     static constexpr int warp_bytes(bool dirs_smem) { return TILE_BYTES + (dirs_smem ? DS_WORDS * 32 * 4 : 0) + 64; }
 };
-
-__device__ __forceinline__ void mbar_init1(uint32_t bar) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar)); }
-__device__ __forceinline__ void mbar_arrive_expect(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "DTW_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DTW_DONE;\n\t"
-        "bra DTW_WAIT;\n\t"
-        "DTW_DONE:\n\t"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
 
 // float32 -> float64 widening on the INTEGER pipe (exact for zeros and normal numbers; `ok` = false for denormals, inf and
 // nan, which the caller widens with the fp64-pipe conversion instead).  Experiment WTS_DTW_VARIANT=5: takes one of the four
@@ -377,7 +355,6 @@ dtw_small_kernel(const float* __restrict__ cost, const WtsSegDesc* __restrict__ 
     unsigned char* my = smem_raw;
     const uint32_t tile_a = smem_u32(my);
     uint32_t* dirs = DIRS_SMEM ? reinterpret_cast<uint32_t*>(my + G::TILE_BYTES) : dir_ws + sd.dir_off;
-    const uint32_t bar0 = tile_a + G::TILE_BYTES + (DIRS_SMEM ? DS_WORDS * 32 * 4 : 0);
 
     const int T = sd.T, F = sd.F, P = (F + 3) & ~3;
     const float* C = cost + sd.cost_off;
@@ -392,32 +369,38 @@ dtw_small_kernel(const float* __restrict__ cost, const WtsSegDesc* __restrict__ 
         float4* z = reinterpret_cast<float4*>(my);
         for (int k = lane; k < G::TILE_BYTES / 16; k += 32) z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < G::NB; ++i) mbar_init1(bar0 + 8u * i);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy zeros ordered before async-proxy writes
     __syncwarp();
 
     const int niter = dtw_niter(F);                          // 32-step tiles of the wavefront (direction layout: 2 words each)
     const int nit = niter * (32 / TC);                       // TC-step iterations
     const int ntile = (P + TC - 1) / TC;                     // column tiles of the matrix
-    const bool owner = lane >= 1 && lane <= T;
-    const char* myrow = reinterpret_cast<const char*>(C + (int64_t)(lane - 1) * P);
-    const uint32_t myrow_a = tile_a + lane * (G::PITCH * 4);
+    // Staging: 16-byte cp.async (LDGSTS.128).  A lane owns chunk `cq` (4 columns) of the rows rq, rq + RPI, ... of every
+    // tile: one warp instruction moves 32 chunks = RPI rows x TC columns, so a tile of T <= 31 rows costs
+    // ceil(T / RPI) instructions (twice that when its ring slot is mirrored) plus their address arithmetic.
+    // (A per-lane cp.async.bulk looked like "one instruction for all rows" in PTX, but SASS serialises it: ELECT + R2UR +
+    // UBLKCP + branch per active lane, ~10 issue slots per copy — 17 of the 39 instructions per step in the ncu capture.)
+    constexpr int CPR = TC / 4;                              // 16-byte chunks per row and tile
+    constexpr int RPI = 32 / CPR;                            // rows per warp instruction
+    constexpr int NG = (31 + RPI - 1) / RPI;                 // instructions per tile
+    const int cq = lane % CPR, rq = lane / CPR;
+    const float* src_lane = C + (int64_t)rq * P + 4 * cq;
+    const uint32_t dst_lane = tile_a + (uint32_t)(rq + 1) * (G::PITCH * 4) + 16u * cq;
 
     auto issue_tile = [&](int u) {                           // columns [TC u, TC u + TC) of every row -> ring slot u % NT
-        const int ncol = min(TC, P - TC * u);
-        const uint32_t bytes = (uint32_t)ncol * 4u;
-        const int slot = u % G::NT;
-        const uint32_t bar = bar0 + 8u * (u % G::NB);
-        if (lane == 0) mbar_arrive_expect(bar, bytes * (uint32_t)T * (slot == 0 ? 2u : 1u));
-        if (owner) {
-            const char* src = myrow + (size_t)u * TC * 4;
-            bulk_g2s(myrow_a + slot * TC * 4, src, bytes, bar);
-            if (slot == 0) bulk_g2s(myrow_a + G::RING * 4, src, bytes, bar);   // mirror behind the ring
+        if (u < ntile) {
+            const int slot = u % G::NT;
+            const bool col_ok = TC * u + 4 * cq < P;
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                if (col_ok && rq + RPI * g < T) {
+                    const float* src = src_lane + (int64_t)(RPI * g) * P + TC * u;
+                    const uint32_t dst = dst_lane + (uint32_t)(RPI * g) * (G::PITCH * 4) + (uint32_t)(slot * TC * 4);
+                    cp_async<16>(dst, src);
+                    if (slot == 0) cp_async<16>(dst + G::RING * 4, src);      // mirror behind the ring
+                }
+            }
         }
+        cp_async_commit();                                   // one group per tile, also when nothing was issued
     };
 
     const double INF = dinf();
@@ -425,12 +408,13 @@ dtw_small_kernel(const float* __restrict__ cost, const WtsSegDesc* __restrict__ 
     if (lane == 1) upprev = 0.0;                             // seeds cm[0,0] = 0 + lm[0,0]
     uint32_t pb = (uint32_t)((G::RING - lane + 1) % G::RING) * 4u;   // 4 * ((TC t - L + 1) mod RING), t = 0
     uint32_t acc = 0;
+    const uint32_t myrow_a = tile_a + lane * (G::PITCH * 4);
 #pragma unroll
-    for (int u = 0; u < LA; ++u)
-        if (u < ntile) issue_tile(u);
+    for (int u = 0; u < LA; ++u) issue_tile(u);
     for (int t = 0; t < nit; ++t) {
-        if (t < ntile) mbar_wait_parity(bar0 + 8u * (t % G::NB), (uint32_t)((t / G::NB) & 1));
-        if (t + LA < ntile) issue_tile(t + LA);              // its ring slot held a tile last read in iteration t - 1
+        cp_async_wait<LA - 1>();                             // all but the newest LA - 1 groups have landed: tile t is in
+        __syncwarp();
+        issue_tile(t + LA);                                  // its ring slot held a tile last read in iteration t - 1
         const uint32_t rd = myrow_a + pb;
         const int s0 = (t * TC) & 15;                        // position of this tile inside its direction word
         if (s0 == 0) acc = 0;
@@ -467,6 +451,7 @@ dtw_small_kernel(const float* __restrict__ cost, const WtsSegDesc* __restrict__ 
         pb += TC * 4;
         if (pb >= (uint32_t)(G::RING * 4)) pb -= G::RING * 4;
     }
+    cp_async_wait<0>();
     if (!DIRS_SMEM) __threadfence_block();
     __syncwarp();
     dtw_backtrack_jumps(dirs, 2 * niter, T, F, jumps_out + sd.jumps_off, lane);
