@@ -221,7 +221,13 @@ def cpu_baseline_align(args):
 # synthetic large-v3 behaves like speech — ~80 % of the windows end with <|endoftext|>, ~75 sampled tokens and
 # 3-4 closed segments per window (the zoo defaults were tuned on the tiny model and leave most large-v3 windows
 # running into the 224-token limit).
-SYNTH_KW = {"ts_offset": 4.5, "eot_logit": 14.5}
+RECIPES = {
+    "default": {"ts_offset": 4.5, "eot_logit": 14.5},
+    # denser text (the reference's own goldens hold ~115 tokens per 30-s window, the default recipe ~45):
+    # picked with tools/recipe_scan.py; reported as a second line (`--recipe dense`), never instead of the default
+    "dense": {"ts_offset": 3.5, "eot_logit": 16.5},
+}
+SYNTH_KW = dict(RECIPES["default"])
 
 
 def _dist_setup():
@@ -452,7 +458,10 @@ def reference_chunks(args, timed, warm):
         pass
     step = int(args.chunk_seconds * 16000)
     need = max(list(timed) + list(warm)) + 1
-    audio = make_audio(min(args.audio_seconds, need * args.chunk_seconds))
+    # the SAME audio as the GPU arm: make_audio() draws it in 300-s pieces, so whole pieces are generated and then cut
+    # (a shorter request would consume the generator differently and give different audio)
+    whole = min(args.audio_seconds, 300.0 * np.ceil(need * args.chunk_seconds / 300.0))
+    audio = make_audio(whole)[: need * step]
     ref = _load_reference()
     if ref is not None:
         kind = "reference"
@@ -541,10 +550,13 @@ def main():
     ap.add_argument("--align-batch", type=int, default=16384)
     ap.add_argument("--align-T", type=int, default=24)
     ap.add_argument("--align-F", type=int, default=300)
+    ap.add_argument("--recipe", default="default", choices=sorted(RECIPES))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    SYNTH_KW.clear()
+    SYNTH_KW.update(RECIPES[args.recipe])
     rank, world, local = _dist_setup()
 
     workload_name = (f"{args.model}, {args.audio_seconds:.0f} s synthetic 16 kHz audio in independent "
