@@ -94,6 +94,14 @@ int wts_dtw_batch(const void* d_cost, int32_t cost_is_f64,
                   int32_t* d_jumps, int32_t* d_path, const int64_t* d_path_off,
                   int32_t* d_path_len, int32_t* d_status, void* stream);
 
+/* Same, with the largest T / F of the batch as sizing hints for the single-strip fast path's shared-memory buffers
+ * (0 = unknown).  Segments above the hints still run — in the general kernel. */
+int wts_dtw_batch_sized(const void* d_cost, int32_t cost_is_f64,
+                  const WtsSegDesc* d_segs, int32_t nseg,
+                  uint32_t* d_dir_ws, double* d_bnd_ws,
+                  int32_t* d_jumps, int32_t* d_path, const int64_t* d_path_off,
+                  int32_t* d_path_len, int32_t* d_status, int32_t max_T, int32_t max_F, void* stream);
+
 /* detect_disfluencies (T.py:1656-1683): for every token t of every segment, d_out[jumps_off + t] = -1, or — when
  * scipy.signal.find_peaks(-cost[t, jumps[t]:jumps[t+1]], width=3, prominence=0.02) finds more than one peak —
  * round(left_ips[-1]), the offset (from jumps[t]) at which the token really starts.  d_cost / d_segs / d_jumps are

@@ -227,7 +227,8 @@ dtw_warp_kernel(const TIn* __restrict__ cost, const WtsSegDesc* __restrict__ seg
     if (seg >= nseg) return;
 
     const WtsSegDesc sd = segs[seg];
-    if (skip_small && dtw_small_eligible(sd)) return;        // owned by dtw_small_kernel
+    if (skip_small && dtw_small_eligible(sd) && sd.T + 1 <= (skip_small >> 8) && dtw_wpr(sd.F) <= (skip_small & 255))
+        return;                                              // owned by dtw_small_kernel (skip_small = rows << 8 | dir words)
     const int T = sd.T, F = sd.F, P = seg_pitch(sd);
     const TIn* C = cost + sd.cost_off;
     // directions live in shared memory when the whole matrix fits one strip and DS_WORDS words per row
@@ -343,18 +344,22 @@ __device__ __forceinline__ double widen_f32_int(uint32_t u, bool& ok)
 template <int TC, int LA, bool DIRS_SMEM, bool INTW = false>
 __global__ void __launch_bounds__(32)
 dtw_small_kernel(const float* __restrict__ cost, const WtsSegDesc* __restrict__ segs, const int nseg,
-                 uint32_t* __restrict__ dir_ws, int32_t* __restrict__ jumps_out, const int l2_prefetch)
+                 uint32_t* __restrict__ dir_ws, int32_t* __restrict__ jumps_out, const int l2_prefetch, const int n_rows,
+                 const int n_dir_words)
 {
+    // n_rows: row buffers in shared memory (1 + the largest T of the batch, <= 32); n_dir_words: direction words per lane
+    // (for the largest F of the batch, <= DS_WORDS) — sized per launch so that more warps fit an SM
     using G = SmGeo<TC, LA>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int lane = threadIdx.x;
     const int seg = blockIdx.x;                              // one warp (= one CTA) per matrix
     if (seg >= nseg) return;
     const WtsSegDesc sd = segs[seg];
-    if (!dtw_small_eligible(sd)) return;                     // the general kernel owns this segment
+    if (!dtw_small_eligible(sd) || sd.T + 1 > n_rows || dtw_wpr(sd.F) > n_dir_words) return;   // the general kernel owns it
     unsigned char* my = smem_raw;
     const uint32_t tile_a = smem_u32(my);
-    uint32_t* dirs = DIRS_SMEM ? reinterpret_cast<uint32_t*>(my + G::TILE_BYTES) : dir_ws + sd.dir_off;
+    const int tile_bytes = n_rows * G::PITCH * 4;
+    uint32_t* dirs = DIRS_SMEM ? reinterpret_cast<uint32_t*>(my + tile_bytes) : dir_ws + sd.dir_off;
 
     const int T = sd.T, F = sd.F, P = (F + 3) & ~3;
     const float* C = cost + sd.cost_off;
@@ -367,7 +372,7 @@ dtw_small_kernel(const float* __restrict__ cost, const WtsSegDesc* __restrict__ 
     // must hold finite values (INF + 0 stays INF; they never feed a cell of the matrix)
     {
         float4* z = reinterpret_cast<float4*>(my);
-        for (int k = lane; k < G::TILE_BYTES / 16; k += 32) z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = lane; k < tile_bytes / 16; k += 32) z[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncwarp();
 
@@ -408,7 +413,7 @@ dtw_small_kernel(const float* __restrict__ cost, const WtsSegDesc* __restrict__ 
     if (lane == 1) upprev = 0.0;                             // seeds cm[0,0] = 0 + lm[0,0]
     uint32_t pb = (uint32_t)((G::RING - lane + 1) % G::RING) * 4u;   // 4 * ((TC t - L + 1) mod RING), t = 0
     uint32_t acc = 0;
-    const uint32_t myrow_a = tile_a + lane * (G::PITCH * 4);
+    const uint32_t myrow_a = tile_a + min(lane, n_rows - 1) * (G::PITCH * 4);   // lanes beyond the buffers re-read the last row
 #pragma unroll
     for (int u = 0; u < LA; ++u) issue_tile(u);
     for (int t = 0; t < nit; ++t) {
@@ -490,11 +495,29 @@ extern "C" int64_t wts_dtw_bnd_doubles(int32_t T, int32_t F)
     return ((int64_t)F + 3) & ~3LL;
 }
 
+extern "C" int wts_dtw_batch_sized(const void* d_cost, int32_t cost_is_f64, const WtsSegDesc* d_segs,
+                                   int32_t nseg, uint32_t* d_dir_ws, double* d_bnd_ws, int32_t* d_jumps,
+                                   int32_t* d_path, const int64_t* d_path_off, int32_t* d_path_len,
+                                   int32_t* d_status, int32_t max_T, int32_t max_F, void* stream);
+
 extern "C" int wts_dtw_batch(const void* d_cost, int32_t cost_is_f64, const WtsSegDesc* d_segs,
                              int32_t nseg, uint32_t* d_dir_ws, double* d_bnd_ws, int32_t* d_jumps,
                              int32_t* d_path, const int64_t* d_path_off, int32_t* d_path_len,
                              int32_t* d_status, void* stream)
 {
+    return wts_dtw_batch_sized(d_cost, cost_is_f64, d_segs, nseg, d_dir_ws, d_bnd_ws, d_jumps, d_path, d_path_off, d_path_len,
+                               d_status, 0, 0, stream);
+}
+
+extern "C" int wts_dtw_batch_sized(const void* d_cost, int32_t cost_is_f64, const WtsSegDesc* d_segs,
+                                   int32_t nseg, uint32_t* d_dir_ws, double* d_bnd_ws, int32_t* d_jumps,
+                                   int32_t* d_path, const int64_t* d_path_off, int32_t* d_path_len,
+                                   int32_t* d_status, int32_t max_T, int32_t max_F, void* stream)
+{
+    // max_T / max_F: largest T / F of the batch when the caller knows them (0 = unknown): they size the shared-memory
+    // buffers of the single-strip fast path (fewer rows / direction words -> more resident warps)
+    const int n_rows = (max_T > 0 && max_T < RS) ? max_T + 1 : RS + 1;
+    const int n_dir_words = (max_F > 0 && dtw_wpr(max_F) < DS_WORDS) ? dtw_wpr(max_F) : DS_WORDS;
     if (nseg <= 0) return 0;
     if (!d_cost || !d_segs || !d_dir_ws || !d_jumps) { set_error("wts_dtw_batch: null pointer"); return -2; }
     if (d_path && (!d_path_off || !d_path_len)) { set_error("wts_dtw_batch: d_path needs d_path_off and d_path_len"); return -2; }
@@ -515,19 +538,21 @@ extern "C" int wts_dtw_batch(const void* d_cost, int32_t cost_is_f64, const WtsS
         const size_t smem = (size_t)DTW_WARPS * (TILE_WORDS * sizeof(float) + DS_WORDS * 32 * sizeof(uint32_t));
         WTS_CUDA_CHECK(cudaFuncSetAttribute(dtw_warp_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dtw_warp_kernel<float><<<grid, DTW_WARPS * 32, smem, st>>>(
-            (const float*)d_cost, d_segs, nseg, d_dir_ws, d_bnd_ws, d_jumps, d_path, d_path_off, d_path_len, use_small);
+            (const float*)d_cost, d_segs, nseg, d_dir_ws, d_bnd_ws, d_jumps, d_path, d_path_off, d_path_len,
+            use_small ? ((n_rows << 8) | n_dir_words) : 0);
         WTS_LAUNCH_CHECK();
         if (use_small) {
             // geometry variants (WTS_DTW_VARIANT, default 0): <columns per tile, tiles in flight, directions in shared memory>
-            static const int variant = [] { const char* e = getenv("WTS_DTW_VARIANT"); return e ? atoi(e) : 0; }();
+            static const int variant = [] { const char* e = getenv("WTS_DTW_VARIANT"); return e ? atoi(e) : 4; }();
             static const int l2pf = [] { const char* e = getenv("WTS_DTW_L2PF"); return e ? atoi(e) : 0; }();   // measured: no effect
 #define WTS_LAUNCH_SMALL(TC_, LA_, DS_, IW_)                                                                              \
             do {                                                                                                          \
-                const size_t smem_s = SmGeo<TC_, LA_>::warp_bytes(DS_);                                                   \
+                const size_t smem_s = (size_t)n_rows * SmGeo<TC_, LA_>::PITCH * 4 + (DS_ ? n_dir_words * 32 * 4 : 0) + 64;      \
                 WTS_CUDA_CHECK(cudaFuncSetAttribute(dtw_small_kernel<TC_, LA_, DS_, IW_>,                                 \
                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));          \
                 dtw_small_kernel<TC_, LA_, DS_, IW_><<<nseg, 32, smem_s, st>>>((const float*)d_cost, d_segs, nseg,       \
-                                                                              d_dir_ws, d_jumps, l2pf);                  \
+                                                                              d_dir_ws, d_jumps, l2pf, n_rows,           \
+                                                                              n_dir_words);                              \
             } while (0)
             switch (variant) {
                 case 1: WTS_LAUNCH_SMALL(16, 1, false, false); break;
@@ -535,7 +560,8 @@ extern "C" int wts_dtw_batch(const void* d_cost, int32_t cost_is_f64, const WtsS
                 case 3: WTS_LAUNCH_SMALL(8, 3, false, false); break;
                 case 4: WTS_LAUNCH_SMALL(32, 1, true, false); break;
                 case 5: WTS_LAUNCH_SMALL(16, 1, false, true); break;
-                default: WTS_LAUNCH_SMALL(16, 1, true, false); break;
+                case 0: WTS_LAUNCH_SMALL(16, 1, true, false); break;
+                default: WTS_LAUNCH_SMALL(32, 1, true, false); break;        // measured best
             }
 #undef WTS_LAUNCH_SMALL
             WTS_LAUNCH_CHECK();

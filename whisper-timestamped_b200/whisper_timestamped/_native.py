@@ -96,6 +96,8 @@ def _load():
     lib.wts_attn_prep_batch.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32, vp, vp]
     lib.wts_dtw_batch.restype = ctypes.c_int
     lib.wts_dtw_batch.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.wts_dtw_batch_sized.restype = ctypes.c_int
+    lib.wts_dtw_batch_sized.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]
     lib.wts_disfluency_starts.restype = ctypes.c_int
     lib.wts_disfluency_starts.argtypes = [vp, vp, i32, vp, vp, vp]
     i64, f32p = ctypes.c_int64, vp
@@ -140,7 +142,7 @@ lib = _load()
 
 EXPORTED_SYMBOLS = [
     "wts_version", "wts_last_error", "wts_dtw_dir_words", "wts_dtw_bnd_doubles",
-    "wts_attn_prep_batch", "wts_dtw_batch", "wts_disfluency_starts", "wts_gemm", "wts_to_sb16", "wts_layernorm", "wts_softmax_rows",
+    "wts_attn_prep_batch", "wts_dtw_batch", "wts_dtw_batch_sized", "wts_disfluency_starts", "wts_gemm", "wts_to_sb16", "wts_layernorm", "wts_softmax_rows",
     "wts_frames", "wts_power", "wts_logmel_max", "wts_logmel_finish", "wts_window_gather", "wts_embed",
     "wts_gather_rows", "wts_decoder_attention", "wts_kv_append", "wts_decode_select", "wts_filtered_logprobs", "wts_decode_steps", "wts_decode_step_kernels", "wts_step_inputs",
     "wts_softmax_pick", "wts_logprob_gather", "wts_cross_kv_pack", "wts_cross_attention_f16", "wts_enc_attention",

@@ -144,10 +144,11 @@ def dtw(cost: torch.Tensor, plan: AlignPlan, want_path=False, want_status=False,
     if want_status:
         d_status = torch.zeros(plan.nseg, dtype=torch.int32, device=dev)
         out.update(status=d_status, status_order=plan.dtw_order)
-    rc = nat.lib.wts_dtw_batch(nat.ptr(cost), 1 if cost.dtype == torch.float64 else 0, nat.ptr(d_segs),
-                               plan.nseg, nat.ptr(d_dir), nat.ptr(d_bnd), nat.ptr(jumps), nat.ptr(d_path),
-                               nat.ptr(d_poff), nat.ptr(d_plen), nat.ptr(d_status), nat.stream_ptr(dev))
-    nat.check(rc, "wts_dtw_batch")
+    rc = nat.lib.wts_dtw_batch_sized(nat.ptr(cost), 1 if cost.dtype == torch.float64 else 0, nat.ptr(d_segs),
+                                     plan.nseg, nat.ptr(d_dir), nat.ptr(d_bnd), nat.ptr(jumps), nat.ptr(d_path),
+                                     nat.ptr(d_poff), nat.ptr(d_plen), nat.ptr(d_status), plan.max_T, plan.max_F,
+                                     nat.stream_ptr(dev))
+    nat.check(rc, "wts_dtw_batch_sized")
     return out
 
 
