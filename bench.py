@@ -225,7 +225,7 @@ RECIPES = {
     "default": {"ts_offset": 4.5, "eot_logit": 14.5},
     # denser text (the reference's own goldens hold ~115 tokens per 30-s window, the default recipe ~45):
     # picked with tools/recipe_scan.py; reported as a second line (`--recipe dense`), never instead of the default
-    "dense": {"ts_offset": 3.5, "eot_logit": 16.5},
+    "dense": {"ts_offset": 6.0, "eot_logit": 13.0},       # ~116 decoded tokens per window, 71 % end with <|endoftext|>
 }
 SYNTH_KW = dict(RECIPES["default"])
 

@@ -262,6 +262,10 @@ typedef struct WtsDecLayer {
     const void *cross_k16, *cross_v16;                               /* [cap, H, n_audio_ctx, 64] fp16 */
     const float* cross_k_align;                                      /* [cap, n_slots, n_audio_ctx, 64] float32 */
     const int32_t* head_slot;                                        /* [H]: alignment slot of each head or -1 */
+    /* the same six matrices as split-bf16 (SB16) planes [2][out][in] (hi plane at the pointer, lo plane `pl_*` ELEMENTS
+     * further), row pitch = in: operands of the mma.sync variant of the lean kernels (use_mma) */
+    const void *sb_qkv, *sb_o, *sb_cq, *sb_co, *sb_fc1, *sb_fc2;
+    int64_t pl_qkv, pl_o, pl_cq, pl_co, pl_fc1, pl_fc2;
 } WtsDecLayer;
 
 typedef struct WtsDecodeSteps {
@@ -275,6 +279,9 @@ typedef struct WtsDecodeSteps {
     float *x, *qkv, *att, *q, *mid, *logits;                         /* scratch: [cap, D], [cap, 3D], [cap, D], [cap, D], [cap, 4D], [cap, V] */
     uint32_t* sync;                                                  /* [64] (two 128-byte lines): [0] barrier arrivals, [1] error flag, [2] steps completed, [32] barrier generation */
     uint64_t* prof;                                                  /* optional: %globaltimer of CTA 0 after every grid barrier */
+    const void* emb_sb;                                              /* token embedding as SB16 planes (logits of the mma variant) */
+    int64_t emb_plane;
+    int64_t use_mma;                                                 /* wts_decode_step_kernels: tensor-core matrix-vector phases */
     WtsDecodeCfg cfg;
     int32_t n_layer, D, H, n_ctx, n_audio_ctx, n_slots, cap, lp_ld, qk_rows, n_steps, max_rows, prof_cap;
 } WtsDecodeSteps;

@@ -241,3 +241,55 @@ def model_dtw_small(cost, late=False, TC=16, LA=1):
         j = jj - 1 if (not is_up and jj > 0) else jj
         i -= 1
     return jumps
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Index model of lean_mma_kernel (decode_steps.cu): small-batch matrix-vector products on mma.sync.m16n8k16 with a
+# PERMUTED k order, so that a thread's weight fragment for two MMAs is one 16-byte load of 8 consecutive k.
+# Inside every block of 32 k, word w = 4 s + q of the staged activations (two bf16) holds actual k = 8 q + 2 s + {0, 1}.
+def mma_model(x, w):
+    """x [16, K] float, w [8, K] float -> D [16, 8] through the fragment definitions of mma.m16n8k16 (PTX ISA):
+    A: a0 (row g, k 2t..2t+1), a1 (row g+8, same k), a2 (row g, k 8+2t..), a3 (row g+8, k 8+2t..);  B: b0 (k 2t..2t+1, n g),
+    b1 (k 8+2t.., n g);  D: d0,d1 (row g, n 2t..2t+1), d2,d3 (row g+8, ...) with g = lane >> 2, t = lane & 3."""
+    x = np.asarray(x, dtype=np.float64)
+    w = np.asarray(w, dtype=np.float64)
+    K = x.shape[1]
+    assert K % 32 == 0
+    # staging: permuted activation words, xs_perm[row, kb, word, e]
+    xp = np.zeros((16, K // 32, 16, 2))
+    for kb in range(K // 32):
+        for q in range(4):
+            for s in range(4):
+                for e in range(2):
+                    xp[:, kb, 4 * s + q, e] = x[:, 32 * kb + 8 * q + 2 * s + e]
+    D = np.zeros((16, 8))
+    for kb in range(K // 32):
+        for lane in range(32):
+            g, t = lane >> 2, lane & 3
+            wl = w[g, 32 * kb + 8 * t: 32 * kb + 8 * t + 8]          # the thread's 16-byte load: 8 consecutive k of feature g
+            words = wl.reshape(4, 2)                                   # four 32-bit words of two bf16
+            for m, (sa, sb) in enumerate(((0, 1), (2, 3))):            # two MMAs per block
+                b0, b1 = words[2 * m], words[2 * m + 1]
+                a0, a1 = xp[g, kb, 4 * sa + t], xp[g + 8, kb, 4 * sa + t]
+                a2, a3 = xp[g, kb, 4 * sb + t], xp[g + 8, kb, 4 * sb + t]
+                # what the tensor core computes for the k-slots this thread contributes to: slot pair 2t..2t+1 (a0/a1 x b0)
+                # and 8+2t.. (a2/a3 x b1), for output column n = g of B.  Accumulate into D[row, n = g].
+                D[g, g] += 0  # (placeholder to keep the structure obvious)
+                for row, (lo, hi) in ((g, (a0, a2)), (g + 8, (a1, a3))):
+                    pass
+        # The MMA contracts over k-slots across the four threads of a group for A (rows) and across groups for B (n):
+        # emulate it exactly: build the 16x16 A tile and 16x8 B tile from the fragments and multiply.
+        for m, (sa, sb) in enumerate(((0, 1), (2, 3))):
+            A = np.zeros((16, 16))
+            B = np.zeros((16, 8))
+            for lane in range(32):
+                g, t = lane >> 2, lane & 3
+                A[g, 2 * t: 2 * t + 2] = xp[g, kb, 4 * sa + t]
+                A[g + 8, 2 * t: 2 * t + 2] = xp[g + 8, kb, 4 * sa + t]
+                A[g, 8 + 2 * t: 8 + 2 * t + 2] = xp[g, kb, 4 * sb + t]
+                A[g + 8, 8 + 2 * t: 8 + 2 * t + 2] = xp[g + 8, kb, 4 * sb + t]
+                words = w[g, 32 * kb + 8 * t: 32 * kb + 8 * t + 8].reshape(4, 2)
+                B[2 * t: 2 * t + 2, g] = words[2 * m]
+                B[8 + 2 * t: 8 + 2 * t + 2, g] = words[2 * m + 1]
+            D += A @ B
+    return D

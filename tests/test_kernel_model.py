@@ -54,3 +54,15 @@ def test_small_kernel_model_matches_oracle(late, geo):
             c = -rng.integers(1, 4, (T, F)).astype(np.float32)
         _, _, jumps, _ = oracle.dtw_symmetric1(c.astype(np.float64))
         assert np.array_equal(jumps, model_dtw_small(c, late=late, TC=geo[0], LA=geo[1])), (T, F, late, geo)
+
+
+def test_mma_k_permutation_model():
+    """The permuted-k staging of lean_mma_kernel: with activations stored as word 4 s + q <- k 8 q + 2 s + {0, 1} per
+    32-k block and every thread's weight fragment taken from ONE 16-byte load of 8 consecutive k, the two MMAs of a
+    block contract exactly the 32 products of that block."""
+    from dtw_kernel_model import mma_model
+    rng = np.random.default_rng(3)
+    for K in (32, 96, 384, 1280):
+        x = rng.standard_normal((16, K))
+        w = rng.standard_normal((8, K))
+        assert np.allclose(mma_model(x, w), x @ w.T, rtol=1e-12, atol=1e-9), K

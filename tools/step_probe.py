@@ -25,7 +25,7 @@ def main():
     ap.add_argument("--active", type=str, default="128,32,16,8,4,1")
     ap.add_argument("--steps", type=int, default=24)
     ap.add_argument("--eager", action="store_true")
-    ap.add_argument("--only", default="graph,lean,steps")
+    ap.add_argument("--only", default="graph,lean_mma,lean,steps")
     args = ap.parse_args()
     import whisper_timestamped as wt
     from whisper_timestamped.engine import CudaEngine
@@ -33,7 +33,7 @@ def main():
     from whisper_timestamped.windows import make_decode_setup
 
     m = wt.load_model(args.model, device="cuda")
-    eng = CudaEngine(m, max_batch=args.cap)
+    eng = CudaEngine(m, max_batch=args.cap, small_batch_rows=32)
     tok = get_tokenizer(m.is_multilingual, num_languages=m.num_languages, language="en", task="transcribe")
     setup = make_decode_setup(tok, m.dims.n_text_ctx)
     ses = eng._decoder_session(setup, args.cap)
@@ -81,17 +81,19 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             res["graph_ms_per_step"] = round(e0.elapsed_time(e1) / args.steps, 3)
-        if "lean" in args.only and ses["steps"] is not None and n_active <= eng.small_batch_rows:
-            reset(n_active)
-            graph = eng._lean_graph(ses, n_active)
-            for _ in range(3):
-                graph.replay()
-            e0.record()
-            for _ in range(args.steps):
-                graph.replay()
-            e1.record()
-            torch.cuda.synchronize()
-            res["lean_ms_per_step"] = round(e0.elapsed_time(e1) / args.steps, 3)
+        for name, mma in (("lean_mma", True), ("lean", False)):
+            if name in args.only.split(",") and ses["steps"] is not None and n_active <= eng.small_batch_rows:
+                reset(n_active)
+                eng.small_batch_mma = mma
+                graph = eng._lean_graph(ses, n_active)
+                for _ in range(3):
+                    graph.replay()
+                e0.record()
+                for _ in range(args.steps):
+                    graph.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                res[name + "_ms_per_step"] = round(e0.elapsed_time(e1) / args.steps, 3)
         if "steps" in args.only and ses["steps"] is not None and n_active <= eng.small_batch_rows:
             reset(n_active)
             eng._run_steps(ses, 3, n_active)

@@ -66,7 +66,9 @@ class DecLayer(ctypes.Structure):
         "ln1_g", "ln1_b", "w_qkv", "b_qkv", "w_o", "b_o",
         "ln2_g", "ln2_b", "w_cq", "b_cq", "w_co", "b_co",
         "ln3_g", "ln3_b", "w_fc1", "b_fc1", "w_fc2", "b_fc2",
-        "self_k", "self_v", "cross_k16", "cross_v16", "cross_k_align", "head_slot")]
+        "self_k", "self_v", "cross_k16", "cross_v16", "cross_k_align", "head_slot",
+        "sb_qkv", "sb_o", "sb_cq", "sb_co", "sb_fc1", "sb_fc2")] + [(n, ctypes.c_int64) for n in (
+        "pl_qkv", "pl_o", "pl_cq", "pl_co", "pl_fc1", "pl_fc2")]
 
 
 class DecodeSteps(ctypes.Structure):
@@ -74,7 +76,8 @@ class DecodeSteps(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in (
         "layers", "emb", "pos", "ln_g", "ln_b", "tokens", "n_tokens", "n_prompt", "done",
         "logprobs", "full", "last_full", "qk_buf", "suppress", "blank",
-        "x", "qkv", "att", "q", "mid", "logits", "sync", "prof")] + [("cfg", DecodeCfg)] + [(n, ctypes.c_int32) for n in (
+        "x", "qkv", "att", "q", "mid", "logits", "sync", "prof", "emb_sb")] + [("emb_plane", ctypes.c_int64),
+                                                                              ("use_mma", ctypes.c_int64), ("cfg", DecodeCfg)] + [(n, ctypes.c_int32) for n in (
         "n_layer", "D", "H", "n_ctx", "n_audio_ctx", "n_slots", "cap", "lp_ld", "qk_rows", "n_steps", "max_rows",
         "prof_cap")]
 

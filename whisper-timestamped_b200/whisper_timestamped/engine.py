@@ -58,6 +58,8 @@ class CudaEngine:
         # how the small-batch steps run: "lean" = chain of per-phase kernels replayed as a CUDA graph (default),
         # "persistent" = one cooperative kernel with software grid barriers (measured slower on B200: ~5 us per barrier)
         self.small_batch_mode = os.environ.get("WTS_SMALL_BATCH_MODE", "lean")
+        # matrix-vector phases of the lean kernels on mma.sync tensor cores (split-bf16, 3 terms) instead of FP32 FMAs
+        self.small_batch_mma = os.environ.get("WTS_SMALL_BATCH_MMA", "1") != "0"
         self._graphs = {}
         self.profile = False            # when set, phases are bracketed with CUDA events (stage_ms())
         self._events = []
@@ -410,6 +412,10 @@ class CudaEngine:
             y.self_k, y.self_v = st8["sk"][li].data_ptr(), st8["sv"][li].data_ptr()
             y.cross_k16, y.cross_v16 = st8["ck"][li].data_ptr(), st8["cv"][li].data_ptr()
             y.cross_k_align, y.head_slot = st8["ckal"][li].data_ptr(), w.head_slot[li].data_ptr()
+            for name, sb in (("qkv", a.qkv), ("o", a.out), ("cq", c.q), ("co", c.out), ("fc1", blk.fc1), ("fc2", blk.fc2)):
+                assert sb.ld == sb.cols
+                setattr(y, "sb_" + name, sb.ptr)
+                setattr(y, "pl_" + name, sb.plane)
         raw = np.frombuffer(bytes(layers), dtype=np.uint8).copy()
         f32 = dict(dtype=torch.float32, device=dev)
         keep = dict(layers=torch.from_numpy(raw).to(dev), x=torch.zeros((cap, D), **f32), qkv=torch.zeros((cap, 3 * D), **f32),
@@ -425,6 +431,8 @@ class CudaEngine:
         p.suppress, p.blank = ses["suppress"].data_ptr(), ses["blank"].data_ptr()
         p.x, p.qkv, p.att, p.q, p.mid = (keep[k].data_ptr() for k in ("x", "qkv", "att", "q", "mid"))
         p.logits, p.sync = ses["logits"].data_ptr(), keep["sync"].data_ptr()
+        p.emb_sb, p.emb_plane = w.emb_sb.ptr, w.emb_sb.plane
+        p.use_mma = 1 if self.small_batch_mma else 0
         p.cfg = ses["cfg"]
         p.n_layer, p.D, p.H, p.n_ctx, p.n_audio_ctx = L, D, H, d.n_text_ctx, N_CTX_AUDIO
         p.n_slots, p.cap, p.lp_ld, p.qk_rows = max(1, len(self.m.heads)), cap, ses["qk_rows"], ses["qk_rows"]
@@ -435,13 +443,14 @@ class CudaEngine:
         rows-per-pass variant that fits `n_active` (4 / 8 / 16 / 32 rows); captured on first use."""
         sd = ses["steps"]
         rows = 4 if n_active <= 4 else 8 if n_active <= 8 else 16 if n_active <= 16 else 32
-        if rows in sd["graphs"]:
-            return sd["graphs"][rows]
+        key = (rows, bool(self.small_batch_mma))
+        if key in sd["graphs"]:
+            return sd["graphs"][key]
         dev = self.dev
         p = sd["args"]
 
         def launch():
-            p.max_rows, p.n_steps = rows, 1
+            p.max_rows, p.n_steps, p.use_mma = rows, 1, int(key[1])
             nat.check(nat.lib.wts_decode_step_kernels(ctypes.byref(p), ctypes.byref(sd["host_layers"]), self._st()),
                       "wts_decode_step_kernels")
         saved = {k: ses[k].clone() for k in ("tokens", "n_tokens", "done", "logprobs")}
@@ -456,7 +465,7 @@ class CudaEngine:
             with torch.cuda.graph(graph, stream=cap_stream):
                 launch()
         torch.cuda.current_stream(dev).wait_stream(cap_stream)
-        sd["graphs"][rows] = graph
+        sd["graphs"][key] = graph
         return graph
 
     def _step_graph(self, ses):
