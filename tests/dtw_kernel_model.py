@@ -264,19 +264,6 @@ def mma_model(x, w):
                     xp[:, kb, 4 * s + q, e] = x[:, 32 * kb + 8 * q + 2 * s + e]
     D = np.zeros((16, 8))
     for kb in range(K // 32):
-        for lane in range(32):
-            g, t = lane >> 2, lane & 3
-            wl = w[g, 32 * kb + 8 * t: 32 * kb + 8 * t + 8]          # the thread's 16-byte load: 8 consecutive k of feature g
-            words = wl.reshape(4, 2)                                   # four 32-bit words of two bf16
-            for m, (sa, sb) in enumerate(((0, 1), (2, 3))):            # two MMAs per block
-                b0, b1 = words[2 * m], words[2 * m + 1]
-                a0, a1 = xp[g, kb, 4 * sa + t], xp[g + 8, kb, 4 * sa + t]
-                a2, a3 = xp[g, kb, 4 * sb + t], xp[g + 8, kb, 4 * sb + t]
-                # what the tensor core computes for the k-slots this thread contributes to: slot pair 2t..2t+1 (a0/a1 x b0)
-                # and 8+2t.. (a2/a3 x b1), for output column n = g of B.  Accumulate into D[row, n = g].
-                D[g, g] += 0  # (placeholder to keep the structure obvious)
-                for row, (lo, hi) in ((g, (a0, a2)), (g + 8, (a1, a3))):
-                    pass
         # The MMA contracts over k-slots across the four threads of a group for A (rows) and across groups for B (n):
         # emulate it exactly: build the 16x16 A tile and 16x8 B tile from the fragments and multiply.
         for m, (sa, sb) in enumerate(((0, 1), (2, 3))):

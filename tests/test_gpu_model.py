@@ -377,3 +377,25 @@ def test_chunks_mode_equals_reference_on_every_cut(path, backend):
     ref, warns = stitch_cuts(g)
     compare(res, ref, conf_tol=2e-3, time_tol=1e-6, prob_tol=1e-3)
     assert norm_warnings(cap.messages) == norm_warnings(warns)
+
+
+def test_continuous_batching_equals_rounds():
+    """decode_stream (a stream's next window joins the running batch as soon as its previous one finishes) gives exactly
+    what the round-based loop gives: chunk mode with follow-up windows, more streams than decode slots, and the
+    sequential (single-stream) mode with prompt carry-over."""
+    import whisper_timestamped as wt
+    from whisper_timestamped.engine import CudaEngine
+    from whisper_timestamped.synthetic_audio import synthetic_speech
+    gm = wt.load_model("synthetic:tiny", device="cuda:0")
+    audio = synthetic_speech(200.0, seed=51)
+    for kw, max_batch in ((dict(language="en", chunks=30.0), 64), (dict(language="en", chunks=20.0), 4), (dict(language="en"), 64)):
+        a = wt.transcribe(gm, audio, engine=CudaEngine(gm, max_batch=max_batch), continuous_batching=True, **kw)
+        b = wt.transcribe(gm, audio, engine=CudaEngine(gm, max_batch=max_batch), continuous_batching=False, **kw)
+        assert a["text"] == b["text"]
+        assert len(a["segments"]) == len(b["segments"]) > 3
+        for x, y in zip(a["segments"], b["segments"]):
+            assert x["tokens"] == y["tokens"] and x["seek"] == y["seek"]
+            assert abs(x["avg_logprob"] - y["avg_logprob"]) <= 1e-5
+            wx, wy = x.get("words", []), y.get("words", [])
+            assert [(w_["text"], w_["start"], w_["end"]) for w_ in wx] == [(w_["text"], w_["start"], w_["end"]) for w_ in wy]
+            assert all(abs(p["confidence"] - q["confidence"]) <= 2e-3 for p, q in zip(wx, wy))

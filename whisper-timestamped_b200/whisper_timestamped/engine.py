@@ -685,6 +685,182 @@ class CudaEngine:
                                         language=tok.language, last_row_logprobs=last_lp))
         return records
 
+    # ------------------------------------------------------------------ continuous batching
+    @torch.no_grad()
+    def decode_stream(self, jobs, setup, feed):
+        """Greedy decoding with CONTINUOUS batching: decode `jobs`; as soon as a window finishes its record goes to
+        `feed(job, record)`, which may return the next window of that audio stream (upstream's seek loop: the follow-up
+        window of a 30-s cut, or the next window of a long file) — it is encoded, prefilled and admitted into the freed
+        slot while the other windows keep decoding.  The round-based `decode_windows` makes every round wait for its
+        slowest window (a stuck one runs to the 224-token limit) before the follow-up windows even start.
+        Same kernels, same per-window arithmetic as `decode_windows`; only the grouping of windows into steps differs."""
+        d, dev, st, w = self.dims, self.dev, self._st(), self.w
+        tok = setup.tokenizer
+        assert not self.keep_full_logprobs, "decode_stream keeps no per-row log-prob tables"
+        D, V, n_ctx = d.n_text_state, d.n_vocab, d.n_text_ctx
+        queue = list(jobs)
+        if not queue:
+            return
+        ses = self._decoder_session(setup, min(self.max_batch, len(queue)))
+        cap, st8, qk_buf = ses["cap"], ses["st8"], ses["qk_buf"]
+        f32 = dict(dtype=torch.float32, device=dev)
+        ses["done"].fill_(1)
+        ses["suppress"].zero_()
+        ses["suppress"][torch.as_tensor(list(setup.suppress_tokens), dtype=torch.long, device=dev)] = 1
+        ses["blank"].zero_()
+        if setup.blank_tokens:
+            ses["blank"][torch.as_tensor(list(setup.blank_tokens), dtype=torch.long, device=dev)] = 1
+        slot_job = [None] * cap               # job decoded in each slot
+        slot_info = [None] * cap              # (prompt, no_speech_prob)
+        free = list(range(cap))
+        max_steps = setup.sample_len - 1
+
+        def admit(batch):
+            """batch: list of (slot, job).  Encoder + cross K/V + prompt prefill + first token of the new windows."""
+            n = len(batch)
+            slots = [b for b, _ in batch]
+            d_slots = torch.as_tensor(slots, dtype=torch.long, device=dev)
+            with self.phase("encoder"):
+                xa = self.encode([j for _, j in batch])
+            with self.phase("cross_kv"):
+                if slots == list(range(n)):            # first admission: the windows land in slots 0 .. n-1 directly
+                    self._cross_kv(xa, st8, n)
+                else:
+                    tmp = self._alloc_cross_state(n)
+                    self._cross_kv(xa, tmp, n)
+                    for li in range(d.n_text_layer):
+                        for name in ("ck", "cv", "ckal"):
+                            st8[name][li].index_copy_(0, d_slots, tmp[name][li])
+                    del tmp
+                del xa
+            prompts = [list(j["prompt"]) for _, j in batch]
+            P = [len(p) for p in prompts]
+            R0 = sum(P)
+            th = np.zeros((n, n_ctx + 1), dtype=np.int32)
+            for k, p in enumerate(prompts):
+                th[k, :len(p)] = p
+            ses["tokens"].index_copy_(0, d_slots, torch.from_numpy(th).to(dev))
+            nt = torch.as_tensor(P, dtype=torch.int32, device=dev)
+            ses["n_tokens"].index_copy_(0, d_slots, nt)
+            ses["n_prompt"].index_copy_(0, d_slots, nt)
+            ses["logprobs"].index_fill_(0, d_slots, 0.0)
+            with self.phase("prefill"):
+                row_seq = _i32([b for b, p in zip(slots, prompts) for _ in p], dev)
+                row_pos = _i32([i for p in prompts for i in range(len(p))], dev)
+                row_tok = _i32([t for p in prompts for t in p], dev)
+                qk_row = _i32([0 if i == len(p) - 1 else -1 for p in prompts for i in range(len(p))], dev)
+                pre = dict(st8)
+                pre.update(hs=SB16(R0, D, dev), att=SB16(R0, D, dev), mid=SB16(R0, 4 * D, dev),
+                           qkv=torch.empty((R0, 3 * D), **f32), q=torch.empty((R0, D), **f32))
+                x = torch.empty((R0, D), **f32)
+                nat.check(nat.lib.wts_embed(row_tok.data_ptr(), row_pos.data_ptr(), w.emb.data_ptr(), w.dec_pos.data_ptr(), R0, D,
+                                            x.data_ptr(), st), "wts_embed")
+                self._decoder_rows(pre, x, R0, row_seq, row_pos, qk_row, qk_buf)
+                ends = np.cumsum(P) - 1
+                sot_rows = [int(ends[k] - P[k] + 1 + prompts[k].index(tok.sot)) for k in range(n)]
+                sel = _i32(list(ends) + sot_rows, dev)
+                xr = torch.empty((2 * n, D), **f32)
+                nat.check(nat.lib.wts_gather_rows(x.data_ptr(), D, sel.data_ptr(), 2 * n, D, xr.data_ptr(), st), "wts_gather_rows")
+                logits2 = torch.empty((2 * n, V), **f32)
+                self._final_logits(xr, 2 * n, logits2)
+                no_speech = torch.zeros(n, **f32)
+                if tok.no_speech is not None:
+                    nat.check(nat.lib.wts_softmax_pick(logits2.data_ptr() + 4 * n * V, V, V, tok.no_speech, no_speech.data_ptr(), n, st),
+                              "wts_softmax_pick")
+                # first token of the new windows only: the select kernel works slot-wise, so the other slots are parked
+                ses["logits"].index_copy_(0, d_slots, logits2[:n])
+                saved = ses["done"].clone()
+                ses["done"].fill_(1)
+                ses["done"].index_fill_(0, d_slots, 0)
+                self._select(ses, ses["logits"], cap)
+                mask = torch.zeros(cap, dtype=torch.bool, device=dev)
+                mask[d_slots] = True
+                ses["done"].copy_(torch.where(mask, ses["done"], saved))
+                self.launches += 4
+            ns = no_speech.cpu().numpy()
+            for k, (b, job) in enumerate(batch):
+                slot_job[b] = job
+                slot_info[b] = (prompts[k], float(ns[k]))
+
+        def collect(finished, done_h):
+            """Records of the finished slots (their alignment rows are copied out: the slot is about to be reused)."""
+            d_f = torch.as_tensor(finished, dtype=torch.long, device=dev)
+            tokens_h = ses["tokens"].index_select(0, d_f).cpu().numpy()
+            n_tok_h = ses["n_tokens"].index_select(0, d_f).cpu().numpy()
+            lp_h = ses["logprobs"].index_select(0, d_f).cpu().numpy()
+            limit = [k for k, b in enumerate(finished) if int(done_h[b]) == 2]
+            last_rows = {}
+            if limit:
+                lf = ses["last_full"].index_select(0, d_f[torch.as_tensor(limit, device=dev)]).cpu()
+                last_rows = {k: lf[i] for i, k in enumerate(limit)}
+            out = []
+            n_rows = [int(n_tok_h[k]) - len(slot_info[b][0]) + (1 if int(done_h[b]) == 1 else 0) for k, b in enumerate(finished)]
+            buf_idx = len(self.qk_buffers)                   # one alignment buffer per collection (rows up to its longest window)
+            self.qk_buffers.append(qk_buf.index_select(0, d_f)[:, :, :max(1, max(n_rows))].contiguous())
+            for k, b in enumerate(finished):
+                prompt, ns = slot_info[b]
+                job = slot_job[b]
+                n = int(n_tok_h[k]) - len(prompt)
+                ended = int(done_h[b]) == 1
+                rows = n + 1 if ended else n
+                gid = len(self.window_index)
+                self.window_index.append((buf_idx, k))
+                last_lp = (lambda t, row=last_rows[k]: float(row[t])) if k in last_rows else None
+                out.append((job, WindowRecord(seek=job["seek"], segment_size=job["segment_size"], prompt=prompt,
+                                              tokens=tokens_h[k, len(prompt):len(prompt) + n].tolist(), logprobs=lp_h[k, :rows].copy(),
+                                              ended_by_eot=ended, no_speech_prob=ns, qk_window=gid, temperature=0.0,
+                                              language=tok.language, last_row_logprobs=last_lp)))
+                slot_job[b] = slot_info[b] = None
+            return out
+
+        done = ses["done"]
+        while queue or any(j is not None for j in slot_job):
+            if queue and free:
+                batch = []
+                while queue and free:
+                    batch.append((free.pop(0), queue.pop(0)))
+                admit(batch)
+            ph = self.phase("decode_steps")
+            ph.__enter__()
+            n_active = int((done == 0).sum().item())
+            if n_active > 0:
+                chunk = 8
+                if ses["steps"] is not None and n_active <= self.small_batch_rows and self.small_batch_mode == "lean":
+                    graph = self._lean_graph(ses, n_active)
+                    for _ in range(chunk):
+                        graph.replay()
+                    self.launches += chunk * (8 * d.n_text_layer + 3)
+                    self.small_batch_steps += chunk
+                else:
+                    graph = self._step_graph(ses) if (self.use_graph and max_steps > 4) else None
+                    for _ in range(chunk):
+                        if graph is not None:
+                            graph.replay()
+                            self.launches += ses["per_step"]
+                        else:
+                            self._step(ses)
+                self.decode_steps_run = getattr(self, "decode_steps_run", 0) + chunk
+            ph.__exit__()
+            done_h = done.cpu().numpy()
+            finished = [b for b in range(cap) if slot_job[b] is not None and int(done_h[b]) != 0]
+            if finished:
+                for job, rec in collect(finished, done_h):
+                    nxt = feed(job, rec)
+                    if nxt is not None:
+                        queue.append(nxt)
+                free.extend(finished)
+                free.sort()
+
+    def _alloc_cross_state(self, B):
+        """Cross-attention K/V buffers for B windows (the layout of the session's, used as a staging area)."""
+        d, dev = self.dims, self.dev
+        H, L = d.n_text_head, d.n_text_layer
+        return dict(
+            ck=[torch.empty((B, H, N_CTX_AUDIO, 64), dtype=torch.float16, device=dev) for _ in range(L)],
+            cv=[torch.empty((B, H, N_CTX_AUDIO, 64), dtype=torch.float16, device=dev) for _ in range(L)],
+            ckal=[torch.empty((B, max(1, len(self.m.heads)), N_CTX_AUDIO, 64), dtype=torch.float32, device=dev) for _ in range(L)],
+            kvtmp=torch.empty((B, H, N_CTX_AUDIO, 64), dtype=torch.float32, device=dev))
+
     # ------------------------------------------------------------------ beam search / sampling (upstream strategies)
     @torch.no_grad()
     def _decode_strategy(self, job, setup):
@@ -955,6 +1131,7 @@ class CudaEngine:
         for i, it in enumerate(items):
             buf, b = self.window_index[it["window"]]
             groups.setdefault(buf, []).append((i, b, it))
+        queued = []
         for buf, lst in groups.items():
             plan = plan_segments([(b, it["row0"], it["last_row"], it["T"], it["f0"], it["F"], it["max_dur"])
                                   for (_, b, it) in lst], nonpositive=True)
@@ -963,15 +1140,19 @@ class CudaEngine:
                 cost = attn_prep(qk, plan)
             with self.phase("align_dtw"):
                 res = dtw(cost, plan)
-            jumps = split_jumps(res["jumps"].cpu().numpy(), plan)
             self.launches += 3
-            for (i, _, _), j in zip(lst, jumps):
-                out[i] = j
+            dl = None
             if disfluencies:
                 from .alignment import disfluency_starts
-                dl = split_jumps(disfluency_starts(cost, plan, res["jumps"]).cpu().numpy(), plan)
+                dl = disfluency_starts(cost, plan, res["jumps"])
                 self.launches += 1
-                for (i, _, _), l_ in zip(lst, dl):
+            queued.append((lst, plan, res["jumps"], dl))
+        for lst, plan, d_jumps, dl in queued:                # all launches are queued: the device->host copies come last
+            jumps = split_jumps(d_jumps.cpu().numpy(), plan)
+            for (i, _, _), j in zip(lst, jumps):
+                out[i] = j
+            if dl is not None:
+                for (i, _, _), l_ in zip(lst, split_jumps(dl.cpu().numpy(), plan)):
                     lefts[i] = l_[:-1]
         return (out, lefts) if disfluencies else out
 

@@ -148,6 +148,7 @@ def transcribe_timestamped(
     *,
     chunks=None,
     engine=None,
+    continuous_batching=True,
 ):
     """Drop-in for whisper_timestamped.transcribe (reference T.py:79-357).
 
@@ -157,6 +158,8 @@ def transcribe_timestamped(
               file (condition_on_previous_text is forced off across cuts); all cuts are decoded in the
               same GPU batches.  This is the data-parallel mode BASELINE.json's north_star names.
       engine: inject a decode/alignment engine (tests); default = the model's CUDA engine.
+      continuous_batching: let the engine admit a stream's next window while other windows are still decoding
+              (default; False = decode in rounds, every round waiting for its slowest window).  Same results.
     """
     # ---- option checks, as T.py:223-261
     assert refine_whisper_precision >= 0 and refine_whisper_precision / AUDIO_TIME_PER_TOKEN == round(
@@ -244,18 +247,28 @@ def transcribe_timestamped(
         content_frames = eng.mel_frames(mel) - N_FRAMES
         streams.append(_Stream(i, mel, content_frames, s / SAMPLE_RATE, initial_prompt_tokens))
 
-    # ---- decode rounds: the next window of every active stream in one GPU batch
-    while True:
-        jobs = [st.next_job(setup) for st in streams if st.active]
-        if not jobs:
-            break
-        records = decode_with_fallback(eng, jobs, setup, temperatures, tokenizer, compression_ratio_threshold,
-                                       logprob_threshold, no_speech_threshold)
-        for job, rec in zip(jobs, records):
-            if language_detected and job["stream"] == 0 and not streams[0].records:
-                rec.mel_from_language_detection = True        # first window of the file, see WindowRecord.max_duration
-            streams[job["stream"]].consume(rec, tokenizer, no_speech_threshold, logprob_threshold,
-                                           condition_on_previous_text)
+    # ---- decode: the next window of every active stream in one GPU batch
+    def consume(job, rec):
+        st = streams[job["stream"]]
+        if language_detected and job["stream"] == 0 and not st.records:
+            rec.mel_from_language_detection = True        # first window of the file, see WindowRecord.max_duration
+        st.consume(rec, tokenizer, no_speech_threshold, logprob_threshold, condition_on_previous_text)
+        return st.next_job(setup) if st.active else None
+
+    plain_greedy = len(temperatures) == 1 and temperatures[0] == 0 and setup.beam_size is None
+    if plain_greedy and hasattr(eng, "decode_stream") and continuous_batching:
+        # continuous batching: a stream's next window is admitted into the decode batch as soon as its previous one
+        # finishes (no round barrier); per stream the windows are still decoded strictly in upstream's order
+        eng.decode_stream([st.next_job(setup) for st in streams if st.active], setup, consume)
+    else:
+        while True:
+            jobs = [st.next_job(setup) for st in streams if st.active]
+            if not jobs:
+                break
+            records = decode_with_fallback(eng, jobs, setup, temperatures, tokenizer, compression_ratio_threshold,
+                                           logprob_threshold, no_speech_threshold)
+            for job, rec in zip(jobs, records):
+                consume(job, rec)
 
     use_space = should_use_space(language)
     if naive_approach:
