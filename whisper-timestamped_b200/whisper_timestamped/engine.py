@@ -50,9 +50,9 @@ class CudaEngine:
         self.launches = 0
         self.use_graph = os.environ.get("WTS_CUDA_GRAPH", "1") != "0"
         # at most this many sequences still decoding -> the small-batch kernels take over (0 = never, at most 32).
-        # Default 4: measured on large-v3 (tools/step_probe.py) the lean kernels beat the tensor-core
-        # graph up to 4 active windows (3.48 / 3.51 ms vs 3.57 / 3.68) and lose from 8 on (3.88 vs 3.78)
-        self.small_batch_rows = min(32, int(os.environ.get("WTS_SMALL_BATCH_ROWS", "4")) if small_batch_rows is None
+        # Default 8: measured on large-v3 (tools/step_probe.py) the lean kernels with mma.sync phases beat
+        # the tcgen05 graph up to 8 active windows (3.44 / 3.49 / 3.54 ms vs 3.57 / 3.67 / 3.78) and lose at 16 (4.62 vs 3.98)
+        self.small_batch_rows = min(32, int(os.environ.get("WTS_SMALL_BATCH_ROWS", "8")) if small_batch_rows is None
                                     else int(small_batch_rows))
         self.small_batch_steps = 0
         # how the small-batch steps run: "lean" = chain of per-phase kernels replayed as a CUDA graph (default),
