@@ -644,7 +644,8 @@ lean_cross_attn_kernel(const WtsDecodeSteps P, const WtsDecLayer* Lr)
     cross_attention_phase(P, *Lr, sh, xs);
 }
 
-__global__ void __launch_bounds__(MG_THREADS)
+constexpr int LEAN_SELECT_THREADS = 1024;    // one CTA per row walks 51866 logits: 4x the threads of the other lean kernels
+__global__ void __launch_bounds__(LEAN_SELECT_THREADS)
 lean_select_kernel(const WtsDecodeSteps P)
 {
     __shared__ SelectScratch S;
@@ -947,7 +948,7 @@ static int launch_lean_step_mma(const WtsDecodeSteps& P, const WtsDecLayer* h_la
     }
     WTS_CUDA_CHECK(launch_pdl(lean_mma_kernel<MT>, g_gemv, blk, sm_mma, st, P, (BF)P.emb_sb, (int64_t)P.emb_plane, V, D, nof,
                               (const float*)P.x, (int64_t)D, P.ln_g, P.ln_b, P.logits, (int64_t)V, (int)EPI_STORE, 1));
-    WTS_CUDA_CHECK(launch_pdl(lean_select_kernel, dim3(P.cap), blk, 0, st, P));
+    WTS_CUDA_CHECK(launch_pdl(lean_select_kernel, dim3(P.cap), dim3(LEAN_SELECT_THREADS), 0, st, P));
     return 0;
 }
 
@@ -988,7 +989,7 @@ static int launch_lean_step(const WtsDecodeSteps& P, const WtsDecLayer* h_layers
     }
     WTS_CUDA_CHECK(launch_pdl(lean_gemv_kernel<RB, true>, g_gemv, blk, stage, st, P, P.emb, V, D, nof, (const float*)P.x, (int64_t)D,
                               P.ln_g, P.ln_b, P.logits, (int64_t)V, (int)EPI_STORE));
-    WTS_CUDA_CHECK(launch_pdl(lean_select_kernel, dim3(P.cap), blk, 0, st, P));
+    WTS_CUDA_CHECK(launch_pdl(lean_select_kernel, dim3(P.cap), dim3(LEAN_SELECT_THREADS), 0, st, P));
     return 0;
 }
 

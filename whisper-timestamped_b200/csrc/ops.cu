@@ -372,7 +372,7 @@ __global__ void kv_append_kernel(const float* k, const float* v, int64_t ld,
 
 // ------------------------------------------------------------------------------------ decode select
 // one CTA per sequence: decode_common.cuh select_row
-constexpr int DS_THREADS = 512;
+constexpr int DS_THREADS = 1024;
 __global__ void __launch_bounds__(DS_THREADS)
 decode_select_kernel(float* logits, int64_t ldl, const WtsDecodeCfg cfg,
                      const uint8_t* suppress, const uint8_t* blank,
