@@ -121,6 +121,14 @@ def bytes_prep(N, T, F):
     return 4 * N * T * F + 4 * T * F
 
 
+def dtw_kernel_name(nseg, T):
+    """Which DTW kernel wts_dtw_batch_sized picks for a batch of nseg single-strip matrices (csrc/dtw.cu)."""
+    lane_min = int(os.environ.get("WTS_DTW_LANE_MIN", "8192"))
+    if lane_min > 0 and nseg >= lane_min and T <= 32:
+        return "dtw_lane_kernel<%d>" % (8 if T <= 8 else 16 if T <= 16 else 24 if T <= 24 else 32)
+    return "dtw_small_kernel<32,1>" if T <= 31 else "dtw_warp_kernel<float>"
+
+
 def run_align(args, rank, world):
     import torch
     from whisper_timestamped.alignment import plan_segments, attn_prep, dtw, dtw_descriptors, _segs_to_device
@@ -628,8 +636,8 @@ def main():
                     al = run_align(args, rank, world)
                     line["dtw_roofline"] = {
                         "bound": "hbm", "achieved": al["dtw_gbs"], "peak": al["peaks"]["hbm_gbs"], "unit": "GB/s",
-                        "frac": al["dtw_gbs"] / al["peaks"]["hbm_gbs"], "traffic": None, "kernel": "dtw_warp_kernel<float>",
-                        "ms": al["ms_dtw"], "prep_gbs": al["prep_gbs"], "prep_ms": al["ms_prep"],
+                        "frac": al["dtw_gbs"] / al["peaks"]["hbm_gbs"], "traffic": None,
+                        "kernel": dtw_kernel_name(args.align_batch, args.align_T), "ms": al["ms_dtw"], "prep_gbs": al["prep_gbs"], "prep_ms": al["ms_prep"],
                         "workload": f"{args.align_batch} segments, T={args.align_T}, F={args.align_F}, N=10 heads"}
                 except Exception as err:                                   # noqa: BLE001
                     line["dtw_roofline"] = {"error": f"{type(err).__name__}: {err}"[:200]}
@@ -662,7 +670,7 @@ def main():
                            "l2": "inputs (qk %.1f GB) larger than L2" % (args.align_batch * 10 * args.align_T * 1500 * 4 / 1e9)},
                 "roofline": {"bound": "hbm", "achieved": res["dtw_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
                              "frac": res["dtw_gbs"] / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
-                             "kernel": "dtw_warp_kernel<float>", "ms": res["ms_dtw"]},
+                             "kernel": dtw_kernel_name(args.align_batch, args.align_T), "ms": res["ms_dtw"]},
                 "prep": {"gbs": res["prep_gbs"], "ms": res["ms_prep"]},
                 "e2e": {"value": res["e2e_segments_per_s"], "unit": "segments/s", "h2d_bytes_per_step": res["h2d"],
                         "d2h_bytes_per_step": res["d2h"]},

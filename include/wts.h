@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define WTS_VERSION 101
+#define WTS_VERSION 102
 #define WTS_SEG_NONPOSITIVE 1
 #define WTS_SEG_PITCH16 2
 
@@ -94,13 +94,17 @@ int wts_dtw_batch(const void* d_cost, int32_t cost_is_f64,
                   int32_t* d_jumps, int32_t* d_path, const int64_t* d_path_off,
                   int32_t* d_path_len, int32_t* d_status, void* stream);
 
-/* Same, with the largest T / F of the batch as sizing hints for the single-strip fast path's shared-memory buffers
- * (0 = unknown).  Segments above the hints still run — in the general kernel. */
+/* Same, with hints about the batch: the largest T / F (0 = unknown; they size the fast paths' shared-memory buffers and
+ * row unrolling — segments above the hints still run, in the general kernel) and all_flags = the bitwise AND of
+ * WtsSegDesc.flags over the batch (0 = unknown; when every segment is known to belong to a fast path the general kernel
+ * is not launched).  Batches of WTS_DTW_LANE_MIN (environment, default 8192) matrices or more use the lane-per-matrix
+ * kernel (T <= 32, any F), smaller ones the warp-per-matrix wavefront kernels; results are identical. */
 int wts_dtw_batch_sized(const void* d_cost, int32_t cost_is_f64,
                   const WtsSegDesc* d_segs, int32_t nseg,
                   uint32_t* d_dir_ws, double* d_bnd_ws,
                   int32_t* d_jumps, int32_t* d_path, const int64_t* d_path_off,
-                  int32_t* d_path_len, int32_t* d_status, int32_t max_T, int32_t max_F, void* stream);
+                  int32_t* d_path_len, int32_t* d_status, int32_t max_T, int32_t max_F, int32_t all_flags,
+                  void* stream);
 
 /* detect_disfluencies (T.py:1656-1683): for every token t of every segment, d_out[jumps_off + t] = -1, or — when
  * scipy.signal.find_peaks(-cost[t, jumps[t]:jumps[t+1]], width=3, prominence=0.02) finds more than one peak —

@@ -280,3 +280,134 @@ def mma_model(x, w):
                 B[8 + 2 * t: 8 + 2 * t + 2, g] = words[2 * m + 1]
             D += A @ B
     return D
+
+
+def model_dtw_lane(cost, TR=24, stale=None, NC=2, G=2):
+    """dtw_lane_kernel<TR, NC, G> for the G lanes of ONE matrix: band b owns rows [b RL, (b + 1) RL) in a register
+    column D[RL] and runs b column groups behind band b - 1, whose last row it gets by shuffle once per group; NC columns
+    advance together, skewed by one row each (chain c sits on cell (s - c, j + c) in step s and takes `left` / `diag` from
+    what chain c - 1 produced one / two steps earlier); direction words [16-column group][row], flushed per 16 columns;
+    clz backtrack by the first band's lane.  Cells outside the matrix (rows >= T, columns >= the padded pitch) read
+    `stale` values, as the kernel reads never-written shared memory there.  cost: float32 [T, F], all <= 0 with
+    cost[0, 0] < 0."""
+    cost = np.asarray(cost, np.float32)
+    T, F = cost.shape
+    assert 1 <= T <= TR <= 32 and TR % 8 == 0 and NC in (2, 4) and G in (1, 2, 4) and G - 1 < 8 // NC
+    RL, GPT = TR // G, 8 // NC
+    P = (F + 3) & ~3
+    rng = np.random.default_rng(1234)
+    ntile = (F + 7) >> 3
+    ncols = (ntile + 2) * 8
+    stage = (-rng.random((TR, ncols)).astype(np.float32) * 7) if stale is None else np.full((TR, ncols), stale, np.float32)
+    stage[:T, :F] = cost
+    stage[:T, F:P] = 0                                   # padding columns hold zeros
+
+    def less(a, b):                                      # the integer compare on strictly negative doubles / +inf
+        ua = np.array([a], np.float64).view(np.uint64)[0]
+        ub = np.array([b], np.float64).view(np.uint64)[0]
+        return bool(ua > ub)
+
+    INF = np.float64(np.inf)
+    ngroups = (F + 15) >> 4
+    dirs = np.zeros((ngroups + 1) * TR, np.uint32)
+
+    def cell(diag, left, up, l):
+        l = np.float64(l)
+        with np.errstate(invalid="ignore"):
+            c1, c2, c3 = diag + l, left + l, up + l
+        p2 = less(c2, c1)
+        m = c2 if p2 else c1
+        p3 = less(c3, m)
+        return (c3 if p3 else m), p2, p3
+
+    class Lane:
+        pass
+
+    lanes = []
+    for b in range(G):
+        ln = Lane()
+        ln.D, ln.acc, ln.last, ln.plast = [INF] * RL, [0] * RL, [INF] * NC, INF
+        lanes.append(ln)
+
+    def cols(ln, rows0, j, diag0, bnd, one, two):
+        up, h1, h2 = list(bnd), [INF] * NC, [INF] * NC
+        h1[0] = bnd[0]
+        diagA = diag0
+        for s in range(RL + NC - 1):
+            out = [INF] * NC
+            for c in range(NC):
+                r = s - c
+                if r < 0 or r >= RL:
+                    out[c] = bnd[c] if r == -1 else INF
+                    continue
+                left = ln.D[r] if c == 0 else h1[c - 1]
+                diag = diagA if c == 0 else h2[c - 1]
+                cur, p2, p3 = cell(diag, left, up[c], stage[rows0 + r, j + c])
+                if p2:
+                    ln.acc[r] |= one << (2 * c)
+                if p3:
+                    ln.acc[r] |= two << (2 * c)
+                up[c] = cur
+                out[c] = cur
+                if c == 0:
+                    diagA = left
+                if c == NC - 1:
+                    ln.D[r] = cur
+                if r == RL - 1:
+                    ln.last[c] = cur
+            h2, h1 = h1, out
+
+    nsteps = ntile * GPT + (G - 1)
+    for gs in range(nsteps):
+        shuffled = [(list(lanes[b - 1].last), lanes[b - 1].plast) if b > 0 else None for b in range(G)]   # before anyone moves
+        for b, ln in enumerate(lanes):
+            mg = gs - b
+            if b == 0:
+                bnd, diag0 = [INF] * NC, (np.float64(0.0) if mg == 0 else INF)
+            else:
+                bnd, diag0 = shuffled[b]
+            mgc = max(mg, 0)
+            j = NC * mgc
+            sh = 2 * (j & 15)
+            ln.plast = ln.last[NC - 1]
+            cols(ln, b * RL, j, diag0, bnd, 1 << sh, 2 << sh)
+            if mg < 0:
+                ln.D, ln.acc, ln.last, ln.plast = [INF] * RL, [0] * RL, [INF] * NC, INF
+            if mg >= 0 and ((j + NC) & 15) == 0:
+                g16 = j >> 4
+                if g16 < ngroups:
+                    dirs[g16 * TR + b * RL: g16 * TR + (b + 1) * RL] = np.array(ln.acc, np.uint64).astype(np.uint32)
+                ln.acc = [0] * RL
+    for b, ln in enumerate(lanes):
+        jend = NC * (nsteps - b)
+        if jend & 15:
+            g16 = jend >> 4
+            if g16 < ngroups:
+                dirs[g16 * TR + b * RL: g16 * TR + (b + 1) * RL] = np.array(ln.acc, np.uint64).astype(np.uint32)
+
+    def nonleft(x):
+        lo, hi = x & 0x55555555, (x >> 1) & 0x55555555
+        return 0x55555555 & ~(lo & ~hi) & 0xffffffff
+
+    jumps = np.zeros(T + 1, np.int64)
+    jumps[T] = F - 1
+    i, j = T - 1, F - 1
+    while i > 0:
+        g, pos = j >> 4, j & 15
+        while True:
+            x = int(dirs[g * TR + i])
+            msk = nonleft(x) & (0xffffffff >> (30 - 2 * pos))
+            if msk:
+                kf = (msk.bit_length() - 1) >> 1
+                break
+            if g == 0:
+                kf = 0
+                break
+            g, pos = g - 1, 15
+        jj = g * 16 + kf
+        is_up = (x >> (2 * kf + 1)) & 1
+        jumps[i] = jj
+        j = jj - 1 if (not is_up and jj > 0) else jj
+        i -= 1
+    jumps[0] = 0
+    return jumps

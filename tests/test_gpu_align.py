@@ -156,6 +156,60 @@ def test_dtw_nonpositive_fast_path_vs_oracle():
         assert np.array_equal(jl[n], j), (n, m.shape)
 
 
+@pytest.mark.parametrize("chains,bands", [(4, 2), (2, 4), (2, 2), (2, 1), (4, 1)])
+@pytest.mark.parametrize("max_rows", [8, 16, 24, 32, 70])
+def test_dtw_lane_kernel_vs_oracle(max_rows, chains, bands, monkeypatch):
+    """The lane-per-matrix kernel (large batches; forced here with WTS_DTW_LANE_MIN=1) on ragged batches: every row
+    unrolling (8/16/24/32), matrices above 32 rows falling back to the general kernel in the same call, heavy ties."""
+    from whisper_timestamped.alignment import plan_segments, dtw, split_jumps, put_cost_matrix
+    monkeypatch.setenv("WTS_DTW_LANE_MIN", "1")
+    monkeypatch.setenv("WTS_DTW_LANE_NC", str(chains))
+    monkeypatch.setenv("WTS_DTW_LANE_G", str(bands))
+    rng = np.random.default_rng(100 + max_rows)
+    shapes = [(1, 1), (1, 2), (2, 2), (min(max_rows, 32), 7), (min(max_rows, 32), 8), (min(max_rows, 32), 9), (3, 16), (3, 17),
+              (min(max_rows, 24), 300), (min(max_rows, 31), 354), (min(max_rows, 32), 1500), (5, 1499)]
+    shapes += [(int(rng.integers(1, max_rows + 1)), int(rng.integers(1, 420))) for _ in range(150)]
+    mats = []
+    for n, (T, F) in enumerate(shapes):
+        if n % 3 == 0:
+            c = -(rng.random((T, F), dtype=np.float32) + 1e-3)
+        elif n % 3 == 1:
+            c = -np.ones((T, F), np.float32)
+        else:
+            c = -(rng.integers(1, 4, (T, F)).astype(np.float32))
+        mats.append(c)
+    plan = plan_segments([(0, 0, None, m.shape[0], 0, m.shape[1], 0) for m in mats], nonpositive=True)
+    host = np.zeros(plan.cost_elems, dtype=np.float32)
+    for s, m in zip(plan.segs, mats):
+        put_cost_matrix(host, s, m)
+    out = dtw(torch.from_numpy(host).to(_dev()), plan)
+    torch.cuda.synchronize()
+    jl = split_jumps(out["jumps"].cpu().numpy(), plan)
+    for n, m in enumerate(mats):
+        _, _, j, _ = oracle.dtw_symmetric1(m.astype(np.float64))
+        assert np.array_equal(jl[n], j), (n, m.shape)
+
+
+def test_dtw_lane_kernel_equals_wavefront_kernel_at_full_size(monkeypatch):
+    """BASELINE-size batch (16384 x 24 x 300, what bench.py --workload align times): both kernels, identical jumps."""
+    from whisper_timestamped.alignment import plan_segments, dtw, put_cost_matrix
+    rng = np.random.default_rng(8)
+    base = [-(rng.random((24, 300), dtype=np.float32) + 1e-3) for _ in range(256)]
+    plan = plan_segments([(0, 0, None, 24, 0, 300, 0)] * 16384, nonpositive=True)
+    host = np.zeros(plan.cost_elems, dtype=np.float32)
+    for k, s in enumerate(plan.segs):
+        put_cost_matrix(host, s, base[k % 256])
+    cost = torch.from_numpy(host).to(_dev())
+    monkeypatch.setenv("WTS_DTW_LANE_MIN", "0")
+    a = dtw(cost, plan)["jumps"].cpu().numpy()
+    monkeypatch.setenv("WTS_DTW_LANE_MIN", "1")
+    b = dtw(cost, plan)["jumps"].cpu().numpy()
+    assert np.array_equal(a, b)
+    for n in range(0, 256, 37):
+        _, _, j, _ = oracle.dtw_symmetric1(base[n].astype(np.float64))
+        assert np.array_equal(b[plan.segs[n]["jumps_off"]: plan.segs[n]["jumps_off"] + 25], j)
+
+
 def test_dtw_status_flags_non_finite():
     a = -np.ones((4, 9), np.float32)
     b = a.copy()

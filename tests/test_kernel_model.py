@@ -66,3 +66,26 @@ def test_mma_k_permutation_model():
         x = rng.standard_normal((16, K))
         w = rng.standard_normal((8, K))
         assert np.allclose(mma_model(x, w), x @ w.T, rtol=1e-12, atol=1e-9), K
+
+
+@pytest.mark.parametrize("NC,G", [(2, 1), (4, 1), (2, 2), (4, 2), (2, 4)])
+@pytest.mark.parametrize("TR", [8, 16, 24, 32])
+def test_lane_kernel_model_matches_oracle(TR, NC, G):
+    """Recurrence order of dtw_lane_kernel (NC columns skewed by one row each in one lane's registers, G row bands per
+    matrix running one column group apart and handing their last row down), its direction-word layout and backtrack, with garbage in the cells outside the matrix — on negative costs incl. heavy ties."""
+    from dtw_kernel_model import model_dtw_lane
+    rng = np.random.default_rng(11 + TR)
+    shapes = [(1, 1), (1, 2), (1, 17), (2, 2), (2, 3), (TR, 16), (TR, 17), (TR, 31), (TR, 32), (TR, 33), (TR - 1, 48),
+              (min(TR, 24), 300), (3, 8), (3, 9), (TR, 7), (TR, 8)]
+    shapes += [(int(rng.integers(1, TR + 1)), int(rng.integers(1, 120))) for _ in range(12)]
+    for n, (T, F) in enumerate(shapes):
+        if n % 3 == 0:
+            c = -(rng.random((T, F)).astype(np.float32) + np.float32(1e-3))
+        elif n % 3 == 1:
+            c = -np.ones((T, F), np.float32)
+        else:
+            c = -rng.integers(1, 4, (T, F)).astype(np.float32)
+        _, _, jumps, _ = oracle.dtw_symmetric1(c.astype(np.float64))
+        assert np.array_equal(jumps, model_dtw_lane(c, TR=TR, NC=NC, G=G)), (T, F, TR, NC, G)
+        if n % 4 == 0:
+            assert np.array_equal(jumps, model_dtw_lane(c, TR=TR, NC=NC, G=G, stale=np.float32("nan"))), (T, F, TR, NC, G, "nan")

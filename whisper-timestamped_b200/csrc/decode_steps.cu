@@ -696,65 +696,52 @@ __device__ __forceinline__ void mma_stage(const float* src, int64_t ld, int col0
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NI = kc >> 7;
-    // a warp takes rows warp, warp + 8, ...: two rows per trip, so that their loads share one memory round trip
-    for (int i0 = warp; i0 < sh.n_active; i0 += 2 * MG_WARPS) {
-        float4 v[2][MG_MAXNI];
+    for (int i = warp; i < sh.n_active; i += MG_WARPS) {
+        const float* r = src + (int64_t)sh.list[i] * ld + col0;
+        float4 v[MG_MAXNI];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int i = i0 + h * MG_WARPS;
-            if (i < sh.n_active) {
-                const float* r = src + (int64_t)sh.list[i] * ld + col0;
+        for (int k = 0; k < MG_MAXNI; ++k)
+            if (k < NI) v[k] = ldcg4(r + 4 * (lane + 32 * k));
+        if (LN) {
+            float s = 0.f;
 #pragma unroll
-                for (int k = 0; k < MG_MAXNI; ++k)
-                    if (k < NI) v[h][k] = ldcg4(r + 4 * (lane + 32 * k));
-            }
-        }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int i = i0 + h * MG_WARPS;
-            if (i >= sh.n_active) break;
-            if (LN) {
-                float s = 0.f;
-#pragma unroll
-                for (int k = 0; k < MG_MAXNI; ++k)
-                    if (k < NI) s += (v[h][k].x + v[h][k].y) + (v[h][k].z + v[h][k].w);
-                const float mean = warp_sum(s) / (float)kc;
-                float q = 0.f;
-#pragma unroll
-                for (int k = 0; k < MG_MAXNI; ++k)
-                    if (k < NI) {
-                        const float a = v[h][k].x - mean, b = v[h][k].y - mean, c = v[h][k].z - mean, d = v[h][k].w - mean;
-                        q += (a * a + b * b) + (c * c + d * d);
-                    }
-                const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)kc + 1e-5f);
-#pragma unroll
-                for (int k = 0; k < MG_MAXNI; ++k)
-                    if (k < NI) {
-                        const float4 g = __ldg(reinterpret_cast<const float4*>(gam) + lane + 32 * k);
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(bet) + lane + 32 * k);
-                        v[h][k].x = (v[h][k].x - mean) * rstd * g.x + b.x;
-                        v[h][k].y = (v[h][k].y - mean) * rstd * g.y + b.y;
-                        v[h][k].z = (v[h][k].z - mean) * rstd * g.z + b.z;
-                        v[h][k].w = (v[h][k].w - mean) * rstd * g.w + b.w;
-                    }
-            }
-            uint32_t* ah = Ah + (int64_t)i * pitchW;
-            uint32_t* al = Al + (int64_t)i * pitchW;
+            for (int k = 0; k < MG_MAXNI; ++k)
+                if (k < NI) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+            const float mean = warp_sum(s) / (float)kc;
+            float q = 0.f;
 #pragma unroll
             for (int k = 0; k < MG_MAXNI; ++k)
                 if (k < NI) {
-                    const int f = lane + 32 * k;             // float4 index: actual k = 4 f .. 4 f + 3
-                    const int kb = f >> 3, j = f & 7;
-                    const int w0 = kb * 16 + ((j & 1) * 2) * 4 + (j >> 1);     // word of (k, k+1): s = 2 (j & 1), q = j >> 1
-                    const float4 x = v[h][k];
-                    const float hx = __bfloat162float(__float2bfloat16_rn(x.x)), hy = __bfloat162float(__float2bfloat16_rn(x.y));
-                    const float hz = __bfloat162float(__float2bfloat16_rn(x.z)), hw = __bfloat162float(__float2bfloat16_rn(x.w));
-                    ah[w0] = pack_bf16x2(hx, hy);
-                    ah[w0 + 4] = pack_bf16x2(hz, hw);        // (k+2, k+3): s + 1
-                    al[w0] = pack_bf16x2(x.x - hx, x.y - hy);
-                    al[w0 + 4] = pack_bf16x2(x.z - hz, x.w - hw);
+                    const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+                    q += (a * a + b * b) + (c * c + d * d);
+                }
+            const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)kc + 1e-5f);
+#pragma unroll
+            for (int k = 0; k < MG_MAXNI; ++k)
+                if (k < NI) {
+                    const float4 g = __ldg(reinterpret_cast<const float4*>(gam) + lane + 32 * k);
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(bet) + lane + 32 * k);
+                    v[k].x = (v[k].x - mean) * rstd * g.x + b.x;
+                    v[k].y = (v[k].y - mean) * rstd * g.y + b.y;
+                    v[k].z = (v[k].z - mean) * rstd * g.z + b.z;
+                    v[k].w = (v[k].w - mean) * rstd * g.w + b.w;
                 }
         }
+#pragma unroll
+        for (int k = 0; k < MG_MAXNI; ++k)
+            if (k < NI) {
+                const int f = lane + 32 * k;                 // float4 index: actual k = 4 f .. 4 f + 3
+                const int kb = f >> 3, j = f & 7;
+                const int w0 = kb * 16 + ((j & 1) * 2) * 4 + (j >> 1);     // word of (k, k+1): s = 2 (j & 1), q = j >> 1
+                const float hx = __bfloat162float(__float2bfloat16_rn(v[k].x)), hy = __bfloat162float(__float2bfloat16_rn(v[k].y));
+                const float hz = __bfloat162float(__float2bfloat16_rn(v[k].z)), hw = __bfloat162float(__float2bfloat16_rn(v[k].w));
+                uint32_t* ah = Ah + (int64_t)i * pitchW;
+                uint32_t* al = Al + (int64_t)i * pitchW;
+                ah[w0] = pack_bf16x2(hx, hy);
+                ah[w0 + 4] = pack_bf16x2(hz, hw);            // (k+2, k+3): s + 1
+                al[w0] = pack_bf16x2(v[k].x - hx, v[k].y - hy);
+                al[w0 + 4] = pack_bf16x2(v[k].z - hz, v[k].w - hw);
+            }
     }
 }
 

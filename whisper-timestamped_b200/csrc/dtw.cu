@@ -47,6 +47,13 @@ __host__ __device__ inline bool dtw_small_eligible(const WtsSegDesc& sd)
            sd.T >= 1 && sd.T <= RS && sd.F >= 1 && dtw_wpr(sd.F) <= DS_WORDS;
 }
 
+// segments the lane-per-matrix path (dtw_lane_kernel<TR>, below) owns when a call uses it
+__host__ __device__ inline bool dtw_lane_eligible(const WtsSegDesc& sd, int TR)
+{
+    return (sd.flags & (WTS_SEG_NONPOSITIVE | WTS_SEG_PITCH16)) == (WTS_SEG_NONPOSITIVE | WTS_SEG_PITCH16) &&
+           sd.T >= 1 && sd.T <= TR && sd.F >= 1;
+}
+
 __device__ __forceinline__ double dinf() { return __longlong_as_double(0x7ff0000000000000LL); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -227,8 +234,12 @@ dtw_warp_kernel(const TIn* __restrict__ cost, const WtsSegDesc* __restrict__ seg
     if (seg >= nseg) return;
 
     const WtsSegDesc sd = segs[seg];
-    if (skip_small && dtw_small_eligible(sd) && sd.T + 1 <= (skip_small >> 8) && dtw_wpr(sd.F) <= (skip_small & 255))
-        return;                                              // owned by dtw_small_kernel (skip_small = rows << 8 | dir words)
+    // skip_small = lane-path rows << 16 | fast-path rows << 8 | fast-path dir words: segments another kernel of this call owns
+    if ((skip_small >> 16) & 255) {
+        if (dtw_lane_eligible(sd, (skip_small >> 16) & 255)) return;                   // dtw_lane_kernel
+    } else if (skip_small && dtw_small_eligible(sd) && sd.T + 1 <= ((skip_small >> 8) & 255) && dtw_wpr(sd.F) <= (skip_small & 255)) {
+        return;                                                                         // dtw_small_kernel
+    }
     const int T = sd.T, F = sd.F, P = seg_pitch(sd);
     const TIn* C = cost + sd.cost_off;
     // directions live in shared memory when the whole matrix fits one strip and DS_WORDS words per row
@@ -462,6 +473,304 @@ dtw_small_kernel(const float* __restrict__ cost, const WtsSegDesc* __restrict__ 
     dtw_backtrack_jumps(dirs, 2 * niter, T, F, jumps_out + sd.jumps_off, lane);
 }
 
+// ------------------------------------------------------------------------------------ lane-per-matrix path (large batches)
+// With thousands of matrices in one call the wavefront kernels above are bound by their dependent chain, and that chain
+// carries a shuffle per cell (lane = row: `up` comes from the neighbouring lane).  Here a LANE owns a whole matrix
+// (T <= TR <= 32 rows, any F) and a warp walks 32 matrices column by column: the column of accumulated costs lives in
+// registers (D[TR], statically indexed), `up` is the value the same lane produced one cell earlier, `left` / `diag` are
+// the previous column's registers — no shuffle, no shared memory in the recurrence.  Two columns advance together,
+// skewed by one row (cell (s, j) and cell (s-1, j+1) in step s), which gives every lane two independent chains to
+// interleave.  Same three fp64 sums, same strict compares, same tie-breaks as the kernels above (bit-identical).
+//  * staging: the warp copies the next tile (8 columns = one 32-byte sector of every row of its 32 matrices) with
+//    16-byte cp.async while it computes the current one: two lanes per sector, 8 rows x 2 matrices per instruction,
+//    `.L2::128B` so that DRAM sees 128-byte requests and the following three tiles hit L2.  Shared layout
+//    [slot][row][half][matrix] x 16 bytes: a lane's LDS.64 of (row, column pair) is base + immediate.
+//  * directions: 2 bits per cell, one word per (16 columns, row), TR words of a column group contiguous per matrix
+//    (128-bit stores every 16 columns); the backtrack runs per lane on its own matrix (one step per token row, clz
+//    over the packed words), reading back what the same thread wrote.
+// Throughput kernel: its latency is that of one matrix walked serially (T F cells), so it only pays when the batch
+// fills the machine (wts_dtw_batch_sized picks it from WTS_DTW_LANE_MIN matrices on).
+
+__device__ __forceinline__ void cp_async_cg16_l2(uint32_t dst, const void* src)
+{
+    asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ float2 lds_f2(uint32_t addr)
+{
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ bool neg_less(double a, double b)   // a < b for strictly negative doubles or +inf
+{
+    return (unsigned long long)__double_as_longlong(a) > (unsigned long long)__double_as_longlong(b);
+}
+
+// one cell: the first strict minimum of (diag, left, up) sums wins; direction bits ORed into the row's word by two
+// predicated instructions (written in PTX: the compiler's own choice was SEL + SEL + LOP3)
+__device__ __forceinline__ double dtw_lane_cell(const double c1, const double c2, const double c3, uint32_t& acc,
+                                                const uint32_t one, const uint32_t two)
+{
+    unsigned long long cur;
+    asm("{\n\t.reg .pred p2, p3;\n\t.reg .b64 m;\n\t"
+        "setp.gt.u64 p2, %3, %2;\n\t"          // c2 < c1  (strictly negative doubles or +inf: a < b <=> bits(a) >u bits(b))
+        "selp.b64 m, %3, %2, p2;\n\t"
+        "setp.gt.u64 p3, %4, m;\n\t"           // c3 < min(c1, c2)
+        "selp.b64 %0, %4, m, p3;\n\t"
+        "@p2 or.b32 %1, %1, %5;\n\t"
+        "@p3 or.b32 %1, %1, %6;\n\t}"
+        : "=l"(cur), "+r"(acc)
+        : "l"((unsigned long long)__double_as_longlong(c1)), "l"((unsigned long long)__double_as_longlong(c2)),
+          "l"((unsigned long long)__double_as_longlong(c3)), "r"(one), "r"(two));
+    return __longlong_as_double((long long)cur);
+}
+
+template <int TR, int G> struct LaneGeo {
+    static constexpr int MPW = 32 / G;                       // matrices per warp
+    static constexpr int RL = TR / G;                        // rows per lane (one band of the matrix)
+    static constexpr int CHUNK_BYTES = MPW * 16;             // [matrix] x 16 bytes (4 columns)
+    static constexpr int ROW_BYTES = 2 * CHUNK_BYTES;        // [half][matrix] x 16 bytes
+    static constexpr int SLOT_BYTES = TR * ROW_BYTES;
+    static constexpr int TABLE_BYTES = 32 * 16;
+    static constexpr int SMEM = TABLE_BYTES + 2 * SLOT_BYTES;
+};
+
+// NC adjacent columns j .. j + NC - 1 of one band (RL rows) of every lane's matrix, skewed by one row: in step s chain c
+// sits on cell (s - c, j + c), so a lane has NC independent dependent chains to interleave.  Chain c's `left` / `diag`
+// are what chain c - 1 produced one / two steps earlier; chain 0 reads the previous column from D, the last chain
+// writes D back.  bnd[c]: the accumulated cost just above the band in column j + c (+inf for the first band), diag0:
+// the same for column j - 1 (0 for the very first cell); last[c] returns the band's last row.
+// D: column j - 1 on entry, column j + NC - 1 on exit.  ld_addr: this lane's 16-byte chunk of its row 0 (4 columns).
+template <int RL, int NC, int ROW_BYTES>
+__device__ __forceinline__ void dtw_lane_cols(double (&D)[RL], uint32_t (&acc)[RL], const uint32_t ld_addr, const double diag0,
+                                              const double (&bnd)[NC], double (&last)[NC], const uint32_t one, const uint32_t two)
+{
+    static_assert(NC == 2 || NC == 4, "two or four columns per group");
+    const double INF = dinf();
+    double up[NC], h1[NC], h2[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) { up[c] = bnd[c]; h1[c] = INF; h2[c] = INF; }
+    h1[0] = bnd[0];                                          // chain 0 "at row -1" one step before the first
+    double diagA = diag0;
+    float lv[RL][NC];
+#pragma unroll
+    for (int i = 0; i < RL; ++i) {
+        if (NC == 4) {
+            const float4 v = lds_f4(ld_addr + i * ROW_BYTES);
+            lv[i][0] = v.x; lv[i][1] = v.y; lv[i][NC - 2] = v.z; lv[i][NC - 1] = v.w;
+        } else {
+            const float2 v = lds_f2(ld_addr + i * ROW_BYTES);
+            lv[i][0] = v.x; lv[i][1] = v.y;
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < RL + NC - 1; ++s) {
+        double out[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const int r = s - c;
+            if (r < 0 || r >= RL) { out[c] = (r == -1) ? bnd[c] : INF; continue; }
+            const double l = (double)lv[r][c];
+            const double left = (c == 0) ? D[r] : h1[c > 0 ? c - 1 : 0];
+            const double diag = (c == 0) ? diagA : h2[c > 0 ? c - 1 : 0];
+            const double cur = dtw_lane_cell(diag + l, left + l, up[c] + l, acc[r], one << (2 * c), two << (2 * c));
+            up[c] = cur;
+            out[c] = cur;
+            if (c == 0) diagA = left;
+            if (c == NC - 1) D[r] = cur;
+            if (r == RL - 1) last[c] = cur;
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) { h2[c] = h1[c]; h1[c] = out[c]; }
+    }
+}
+
+// G lanes per matrix: lane = band * MPW + matrix, band b owns rows [b RL, (b + 1) RL) and runs b column groups behind
+// band b - 1, whose last row it receives by shuffle once per group (not per cell).
+template <int TR, int NC, int G>
+__global__ void __launch_bounds__(32)
+dtw_lane_kernel(const float* __restrict__ cost, const WtsSegDesc* __restrict__ segs, const int nseg,
+                uint32_t* __restrict__ dir_ws, int32_t* __restrict__ jumps_out)
+{
+    using Geo = LaneGeo<TR, G>;
+    constexpr int MPW = Geo::MPW, RL = Geo::RL, GPT = 8 / NC;   // GPT: column groups per tile
+    static_assert(TR % 8 == 0 && TR <= 32 && (G == 1 || G == 2 || G == 4) && TR % G == 0, "rows per matrix: 8, 16, 24 or 32; 1, 2 or 4 bands");
+    static_assert(G - 1 < GPT, "the last band must leave a tile before the tile after next is issued into its slot");
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int lane = threadIdx.x;
+    const int band = lane / MPW, mi = lane % MPW;
+    const int seg = blockIdx.x * MPW + mi;                   // one warp (= one CTA) per MPW matrices
+    WtsSegDesc sd;
+    bool mine = false;
+    if (seg < nseg) { sd = segs[seg]; mine = dtw_lane_eligible(sd, TR); }
+    const int T = mine ? sd.T : 0, F = mine ? sd.F : 0, P = mine ? ((sd.F + 3) & ~3) : 0;
+    const float* C = mine ? cost + sd.cost_off : cost;
+    uint4* table = reinterpret_cast<uint4*>(smem_raw);       // per matrix: source pointer, row pitch, rows
+    if (band == 0) {
+        const unsigned long long a = (unsigned long long)(uintptr_t)C;
+        table[mi] = make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)P, (uint32_t)T);
+    }
+    const uint32_t stage_a = smem_u32(smem_raw + Geo::TABLE_BYTES);
+    int Fmax = F;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) Fmax = max(Fmax, __shfl_xor_sync(FULL_MASK, Fmax, o));
+    if (Fmax == 0) return;                                   // nothing here for this path (the general kernel owns them)
+    __syncwarp();
+    const int ntile = (Fmax + 7) >> 3;
+
+    // Staging roles: two lanes per 32-byte sector, 8 rows x 2 matrices per warp instruction.  What a lane needs to
+    // know about the MPW / 2 matrices it copies for (source of its row / half-sector, pitch, rows) stays in registers,
+    // so that issuing a tile is straight-line code with no loads in front of the address arithmetic.
+    const int half = lane & 1, rr = (lane >> 1) & 7, mm = lane >> 4;
+    const float* sp[MPW / 2];                                // (matrix 2 k + mm, row rr, column 4 half)
+    uint32_t sq[MPW / 2];                                    // rows << 16 | pitch
+#pragma unroll
+    for (int k = 0; k < MPW / 2; ++k) {
+        const uint4 d = table[2 * k + mm];
+        sp[k] = reinterpret_cast<const float*>((uintptr_t)(((unsigned long long)d.y << 32) | d.x)) + (int64_t)rr * (int)d.z + 4 * half;
+        sq[k] = (d.w << 16) | d.z;
+    }
+    const uint32_t dst_lane = stage_a + (uint32_t)rr * Geo::ROW_BYTES + (uint32_t)half * Geo::CHUNK_BYTES + (uint32_t)mm * 16;
+    auto issue_tile = [&](int t) {
+        if (t < ntile) {
+            const int col = 8 * t + 4 * half;
+            const uint32_t dst0 = dst_lane + (uint32_t)(t & 1) * Geo::SLOT_BYTES;
+#pragma unroll
+            for (int k = 0; k < MPW / 2; ++k) {
+                const int Pm = (int)(sq[k] & 0xffffu), Tm = (int)(sq[k] >> 16);
+                const bool col_ok = col < Pm;
+                const float* src = sp[k] + 8 * t;
+#pragma unroll
+                for (int rb = 0; rb < TR / 8; ++rb)
+                    if (col_ok && rr + 8 * rb < Tm)
+                        cp_async_cg16_l2(dst0 + (uint32_t)k * 32 + (uint32_t)rb * 8 * Geo::ROW_BYTES, src + (int64_t)(rb * 8) * Pm);
+            }
+        }
+        cp_async_commit();                                   // one group per tile, also when nothing was issued
+    };
+
+    double D[RL];
+    uint32_t acc[RL];
+    const double INF = dinf();
+#pragma unroll
+    for (int i = 0; i < RL; ++i) { D[i] = INF; acc[i] = 0; }
+    uint32_t* dirs = dir_ws + (mine ? sd.dir_off : 0) + band * RL;   // word of (16-column group g, row i): [g * TR + i]
+    const int ngroups16 = (F + 15) >> 4;
+    const uint32_t row_a = stage_a + (uint32_t)(band * RL) * Geo::ROW_BYTES + (uint32_t)mi * 16;
+    double last[NC], plast = INF;                            // this band's last row: previous group, and its last column before
+#pragma unroll
+    for (int c = 0; c < NC; ++c) last[c] = INF;
+
+    const int nsteps = ntile * GPT + (G - 1);                // band b handles column group (step - b)
+    issue_tile(0);
+#pragma unroll 1
+    for (int gs = 0; gs < nsteps; ++gs) {
+        const int t = gs / GPT, p = gs % GPT;
+        if (p == 0 && t < ntile) {
+            cp_async_wait<0>();                              // tile t has landed (this lane's copies)
+            __syncwarp();                                    // ... and everybody's
+        }
+        if (p == G - 1) {
+            // the slot of tile t + 1 held tile t - 1, which the last band read until the previous step
+            if (G > 1) __syncwarp();
+            issue_tile(t + 1);
+        }
+        // what the band above produced in its previous step = this band's boundary for the group it handles now
+        double bnd[NC], diag0;
+        if (G > 1) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) bnd[c] = __shfl_up_sync(FULL_MASK, last[c], MPW);
+            diag0 = __shfl_up_sync(FULL_MASK, plast, MPW);
+        }
+        const int mg = gs - band;                            // this lane's column group
+        if (G == 1 || band == 0) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) bnd[c] = INF;
+            diag0 = (mg == 0) ? 0.0 : INF;
+        }
+        const int mgc = max(mg, 0);
+        const int j = NC * mgc;
+        const int tm = mgc / GPT, pm = mgc % GPT;
+        const uint32_t sh = 2u * (uint32_t)(j & 15);
+        const uint32_t ld = row_a + (uint32_t)(tm & 1) * Geo::SLOT_BYTES + (uint32_t)((NC * pm) >> 2) * Geo::CHUNK_BYTES +
+                            (uint32_t)((NC * pm) & 3) * 4;
+        plast = last[NC - 1];
+        dtw_lane_cols<RL, NC, Geo::ROW_BYTES>(D, acc, ld, diag0, bnd, last, 1u << sh, 2u << sh);
+        if (G > 1 && mg < 0) {                               // a band that has not started yet: undo the step
+#pragma unroll
+            for (int i = 0; i < RL; ++i) { D[i] = INF; acc[i] = 0; }
+#pragma unroll
+            for (int c = 0; c < NC; ++c) last[c] = INF;
+            plast = INF;
+        }
+        if (mg >= 0 && ((j + NC) & 15) == 0) {               // a 16-column direction group is complete
+            const int g16 = j >> 4;
+            if (g16 < ngroups16) {
+                uint32_t* dst = dirs + (int64_t)g16 * TR;
+                if (RL % 4 == 0) {
+#pragma unroll
+                    for (int q = 0; q < RL / 4; ++q)
+                        reinterpret_cast<uint4*>(dst)[q] = make_uint4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < RL; ++q) dst[q] = acc[q];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < RL; ++i) acc[i] = 0;
+        }
+    }
+    {   // the last, incomplete direction group
+        const int jend = NC * (nsteps - band);               // first column this lane has not processed
+        if ((jend & 15) != 0) {
+            const int g16 = jend >> 4;
+            if (g16 < ngroups16) {
+                uint32_t* dst = dirs + (int64_t)g16 * TR;
+#pragma unroll
+                for (int q = 0; q < RL; ++q) dst[q] = acc[q];
+            }
+        }
+    }
+    cp_async_wait<0>();
+    __syncwarp();                                            // direction words of all bands are visible to band 0
+    if (!mine || band != 0) return;
+
+    // backtrack on this lane's matrix: one step per token row (T.py:1648-1652)
+    const uint32_t* dm = dir_ws + sd.dir_off;
+    int32_t* jumps = jumps_out + sd.jumps_off;
+    int i = T - 1, j = F - 1;
+    jumps[T] = F - 1;
+    uint4 cw = make_uint4(0, 0, 0, 0);                       // the words of four consecutive rows of one column group: one
+    int cg = -1, cq = -1;                                    // 16-byte load serves the moves up inside the group
+    while (i > 0) {
+        int g = j >> 4, pos = j & 15, kf = 0;
+        uint32_t x = 0;
+        while (true) {
+            if (g != cg || (i >> 2) != cq) {
+                cg = g; cq = i >> 2;
+                cw = __ldcg(reinterpret_cast<const uint4*>(dm + (int64_t)g * TR + 4 * cq));
+            }
+            x = (i & 2) ? ((i & 1) ? cw.w : cw.z) : ((i & 1) ? cw.y : cw.x);
+            const uint32_t msk = dtw_nonleft_mask(x) & (0xffffffffu >> (30 - 2 * pos));
+            if (msk) { kf = (31 - __clz(msk)) >> 1; break; }
+            if (g == 0) { kf = 0; break; }
+            --g; pos = 15;
+        }
+        const int jj = g * 16 + kf;
+        const bool is_up = (x >> (2 * kf + 1)) & 1u;
+        jumps[i] = jj;
+        j = (!is_up && jj > 0) ? jj - 1 : jj;
+        --i;
+    }
+    jumps[0] = 0;
+}
+
 // status: 1 when the segment's local-cost matrix holds a non-finite value (the situation in which
 // the reference's dtw() can end with "No warping path found").
 template <typename TIn>
@@ -498,7 +807,7 @@ extern "C" int64_t wts_dtw_bnd_doubles(int32_t T, int32_t F)
 extern "C" int wts_dtw_batch_sized(const void* d_cost, int32_t cost_is_f64, const WtsSegDesc* d_segs,
                                    int32_t nseg, uint32_t* d_dir_ws, double* d_bnd_ws, int32_t* d_jumps,
                                    int32_t* d_path, const int64_t* d_path_off, int32_t* d_path_len,
-                                   int32_t* d_status, int32_t max_T, int32_t max_F, void* stream);
+                                   int32_t* d_status, int32_t max_T, int32_t max_F, int32_t all_flags, void* stream);
 
 extern "C" int wts_dtw_batch(const void* d_cost, int32_t cost_is_f64, const WtsSegDesc* d_segs,
                              int32_t nseg, uint32_t* d_dir_ws, double* d_bnd_ws, int32_t* d_jumps,
@@ -506,13 +815,13 @@ extern "C" int wts_dtw_batch(const void* d_cost, int32_t cost_is_f64, const WtsS
                              int32_t* d_status, void* stream)
 {
     return wts_dtw_batch_sized(d_cost, cost_is_f64, d_segs, nseg, d_dir_ws, d_bnd_ws, d_jumps, d_path, d_path_off, d_path_len,
-                               d_status, 0, 0, stream);
+                               d_status, 0, 0, 0, stream);
 }
 
 extern "C" int wts_dtw_batch_sized(const void* d_cost, int32_t cost_is_f64, const WtsSegDesc* d_segs,
                                    int32_t nseg, uint32_t* d_dir_ws, double* d_bnd_ws, int32_t* d_jumps,
                                    int32_t* d_path, const int64_t* d_path_off, int32_t* d_path_len,
-                                   int32_t* d_status, int32_t max_T, int32_t max_F, void* stream)
+                                   int32_t* d_status, int32_t max_T, int32_t max_F, int32_t all_flags, void* stream)
 {
     // max_T / max_F: largest T / F of the batch when the caller knows them (0 = unknown): they size the shared-memory
     // buffers of the single-strip fast path (fewer rows / direction words -> more resident warps)
@@ -533,14 +842,53 @@ extern "C" int wts_dtw_batch_sized(const void* d_cost, int32_t cost_is_f64, cons
     } else {
         // single-strip fast path (dtw_small_kernel) for the segments that qualify; it produces jumps only, so a
         // request for full paths keeps everything in the general kernel.  WTS_DTW_SMALL=0 turns it off.
+        // From WTS_DTW_LANE_MIN matrices on (default 8192; 0 = never) the lane-per-matrix kernel takes them instead.
         static const int small_on = [] { const char* e = getenv("WTS_DTW_SMALL"); return e ? atoi(e) : 1; }();
-        const int use_small = small_on && d_path == nullptr;
-        const size_t smem = (size_t)DTW_WARPS * (TILE_WORDS * sizeof(float) + DS_WORDS * 32 * sizeof(uint32_t));
-        WTS_CUDA_CHECK(cudaFuncSetAttribute(dtw_warp_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dtw_warp_kernel<float><<<grid, DTW_WARPS * 32, smem, st>>>(
-            (const float*)d_cost, d_segs, nseg, d_dir_ws, d_bnd_ws, d_jumps, d_path, d_path_off, d_path_len,
-            use_small ? ((n_rows << 8) | n_dir_words) : 0);
-        WTS_LAUNCH_CHECK();
+        const char* lane_env = getenv("WTS_DTW_LANE_MIN");  // read per call: tests and benchmarks switch paths at run time
+        const int lane_min = lane_env ? atoi(lane_env) : 8192;
+        const int use_lane = d_path == nullptr && lane_min > 0 && nseg >= lane_min;
+        const int use_small = !use_lane && small_on && d_path == nullptr;
+        const int lane_rows = (max_T <= 0 || max_T > 24) ? 32 : max_T > 16 ? 24 : max_T > 8 ? 16 : 8;
+        // all_flags (AND of the batch's WtsSegDesc.flags, 0 = unknown) together with the size hints tells when every
+        // segment belongs to the fast kernel: the general kernel (whose warps would all exit) is then not launched
+        const bool uniform = (all_flags & (WTS_SEG_NONPOSITIVE | WTS_SEG_PITCH16)) == (WTS_SEG_NONPOSITIVE | WTS_SEG_PITCH16) && max_T > 0;
+        const bool general_idle = uniform && ((use_lane && max_T <= 32) ||
+                                              (use_small && max_T <= RS && max_F > 0 && dtw_wpr(max_F) <= DS_WORDS));
+        if (!general_idle) {
+            const size_t smem = (size_t)DTW_WARPS * (TILE_WORDS * sizeof(float) + DS_WORDS * 32 * sizeof(uint32_t));
+            WTS_CUDA_CHECK(cudaFuncSetAttribute(dtw_warp_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            dtw_warp_kernel<float><<<grid, DTW_WARPS * 32, smem, st>>>(
+                (const float*)d_cost, d_segs, nseg, d_dir_ws, d_bnd_ws, d_jumps, d_path, d_path_off, d_path_len,
+                use_lane ? (lane_rows << 16) : use_small ? ((n_rows << 8) | n_dir_words) : 0);
+            WTS_LAUNCH_CHECK();
+        }
+        if (use_lane) {
+#define WTS_LAUNCH_LANE(TR_, NC_, G_)                                                                                     \
+            do {                                                                                                          \
+                constexpr int mpw = LaneGeo<TR_, G_>::MPW;                                                                \
+                WTS_CUDA_CHECK(cudaFuncSetAttribute(dtw_lane_kernel<TR_, NC_, G_>,                                        \
+                                                    cudaFuncAttributeMaxDynamicSharedMemorySize,                         \
+                                                    (int)LaneGeo<TR_, G_>::SMEM));                                        \
+                dtw_lane_kernel<TR_, NC_, G_><<<(nseg + mpw - 1) / mpw, 32, LaneGeo<TR_, G_>::SMEM, st>>>(                \
+                    (const float*)d_cost, d_segs, nseg, d_dir_ws, d_jumps);                                               \
+            } while (0)
+            // WTS_DTW_LANE_NC: columns advanced together per lane (2 or 4 independent chains); WTS_DTW_LANE_G: lanes
+            // (row bands) per matrix, 1, 2 or 4 — more bands = more warps per scheduler for the same work
+            const char* nc_env = getenv("WTS_DTW_LANE_NC");
+            const char* g_env = getenv("WTS_DTW_LANE_G");
+            const int lane_g = g_env ? atoi(g_env) : 2;
+            const int lane_nc = lane_g == 4 ? 2 : (nc_env && atoi(nc_env) == 2) ? 2 : 4;      // measured: 4 chains with 2 bands
+#define WTS_LANE_CASE(TR_)                                                                                                \
+            if (lane_rows == TR_) {                                                                                       \
+                if (lane_g == 1)      { if (lane_nc == 2) WTS_LAUNCH_LANE(TR_, 2, 1); else WTS_LAUNCH_LANE(TR_, 4, 1); }  \
+                else if (lane_g == 4) { WTS_LAUNCH_LANE(TR_, 2, 4); }                                                     \
+                else                  { if (lane_nc == 2) WTS_LAUNCH_LANE(TR_, 2, 2); else WTS_LAUNCH_LANE(TR_, 4, 2); }  \
+            }
+            WTS_LANE_CASE(8) WTS_LANE_CASE(16) WTS_LANE_CASE(24) WTS_LANE_CASE(32)
+#undef WTS_LANE_CASE
+#undef WTS_LAUNCH_LANE
+            WTS_LAUNCH_CHECK();
+        }
         if (use_small) {
             // geometry variants (WTS_DTW_VARIANT, default 0): <columns per tile, tiles in flight, directions in shared memory>
             static const int variant = [] { const char* e = getenv("WTS_DTW_VARIANT"); return e ? atoi(e) : 4; }();

@@ -100,7 +100,7 @@ def _load():
     lib.wts_dtw_batch.restype = ctypes.c_int
     lib.wts_dtw_batch.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.wts_dtw_batch_sized.restype = ctypes.c_int
-    lib.wts_dtw_batch_sized.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]
+    lib.wts_dtw_batch_sized.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
     lib.wts_disfluency_starts.restype = ctypes.c_int
     lib.wts_disfluency_starts.argtypes = [vp, vp, i32, vp, vp, vp]
     i64, f32p = ctypes.c_int64, vp

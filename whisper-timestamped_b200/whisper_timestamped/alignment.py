@@ -147,6 +147,7 @@ def dtw(cost: torch.Tensor, plan: AlignPlan, want_path=False, want_status=False,
     rc = nat.lib.wts_dtw_batch_sized(nat.ptr(cost), 1 if cost.dtype == torch.float64 else 0, nat.ptr(d_segs),
                                      plan.nseg, nat.ptr(d_dir), nat.ptr(d_bnd), nat.ptr(jumps), nat.ptr(d_path),
                                      nat.ptr(d_poff), nat.ptr(d_plen), nat.ptr(d_status), plan.max_T, plan.max_F,
+                                     int(np.bitwise_and.reduce(plan.segs["flags"])) if plan.nseg else 0,
                                      nat.stream_ptr(dev))
     nat.check(rc, "wts_dtw_batch_sized")
     return out
