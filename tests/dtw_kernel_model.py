@@ -309,7 +309,10 @@ def model_dtw_lane(cost, TR=24, stale=None, NC=2, G=2):
 
     INF = np.float64(np.inf)
     ngroups = (F + 15) >> 4
-    dirs = np.zeros((ngroups + 1) * TR, np.uint32)
+    dirs = np.zeros((ngroups + 2) * TR, np.uint32)
+
+    def didx(g16, row):                                  # dtw_lane_dir_index: blocks of 2 column groups x 4 rows
+        return (((g16 >> 1) * (TR // 4) + (row >> 2)) << 3) + ((g16 & 1) << 2) + (row & 3)
 
     def cell(diag, left, up, l):
         l = np.float64(l)
@@ -376,14 +379,16 @@ def model_dtw_lane(cost, TR=24, stale=None, NC=2, G=2):
             if mg >= 0 and ((j + NC) & 15) == 0:
                 g16 = j >> 4
                 if g16 < ngroups:
-                    dirs[g16 * TR + b * RL: g16 * TR + (b + 1) * RL] = np.array(ln.acc, np.uint64).astype(np.uint32)
+                    for q in range(RL):
+                        dirs[didx(g16, b * RL + q)] = ln.acc[q] & 0xffffffff
                 ln.acc = [0] * RL
     for b, ln in enumerate(lanes):
         jend = NC * (nsteps - b)
         if jend & 15:
             g16 = jend >> 4
             if g16 < ngroups:
-                dirs[g16 * TR + b * RL: g16 * TR + (b + 1) * RL] = np.array(ln.acc, np.uint64).astype(np.uint32)
+                for q in range(RL):
+                    dirs[didx(g16, b * RL + q)] = ln.acc[q] & 0xffffffff
 
     def nonleft(x):
         lo, hi = x & 0x55555555, (x >> 1) & 0x55555555
@@ -395,7 +400,7 @@ def model_dtw_lane(cost, TR=24, stale=None, NC=2, G=2):
     while i > 0:
         g, pos = j >> 4, j & 15
         while True:
-            x = int(dirs[g * TR + i])
+            x = int(dirs[didx(g, i)])
             msk = nonleft(x) & (0xffffffff >> (30 - 2 * pos))
             if msk:
                 kf = (msk.bit_length() - 1) >> 1

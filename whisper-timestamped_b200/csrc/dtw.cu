@@ -546,19 +546,10 @@ template <int TR, int G> struct LaneGeo {
 // are what chain c - 1 produced one / two steps earlier; chain 0 reads the previous column from D, the last chain
 // writes D back.  bnd[c]: the accumulated cost just above the band in column j + c (+inf for the first band), diag0:
 // the same for column j - 1 (0 for the very first cell); last[c] returns the band's last row.
-// D: column j - 1 on entry, column j + NC - 1 on exit.  ld_addr: this lane's 16-byte chunk of its row 0 (4 columns).
+// D: column j - 1 on entry, column j + NC - 1 on exit.  lv: the band's local costs of the group (dtw_lane_load).
 template <int RL, int NC, int ROW_BYTES>
-__device__ __forceinline__ void dtw_lane_cols(double (&D)[RL], uint32_t (&acc)[RL], const uint32_t ld_addr, const double diag0,
-                                              const double (&bnd)[NC], double (&last)[NC], const uint32_t one, const uint32_t two)
+__device__ __forceinline__ void dtw_lane_load(float (&lv)[RL][NC], const uint32_t ld_addr)
 {
-    static_assert(NC == 2 || NC == 4, "two or four columns per group");
-    const double INF = dinf();
-    double up[NC], h1[NC], h2[NC];
-#pragma unroll
-    for (int c = 0; c < NC; ++c) { up[c] = bnd[c]; h1[c] = INF; h2[c] = INF; }
-    h1[0] = bnd[0];                                          // chain 0 "at row -1" one step before the first
-    double diagA = diag0;
-    float lv[RL][NC];
 #pragma unroll
     for (int i = 0; i < RL; ++i) {
         if (NC == 4) {
@@ -569,6 +560,19 @@ __device__ __forceinline__ void dtw_lane_cols(double (&D)[RL], uint32_t (&acc)[R
             lv[i][0] = v.x; lv[i][1] = v.y;
         }
     }
+}
+
+template <int RL, int NC>
+__device__ __forceinline__ void dtw_lane_cols(double (&D)[RL], uint32_t (&acc)[RL], const float (&lv)[RL][NC], const double diag0,
+                                              const double (&bnd)[NC], double (&last)[NC], const uint32_t one, const uint32_t two)
+{
+    static_assert(NC == 2 || NC == 4, "two or four columns per group");
+    const double INF = dinf();
+    double up[NC], h1[NC], h2[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) { up[c] = bnd[c]; h1[c] = INF; h2[c] = INF; }
+    h1[0] = bnd[0];                                          // chain 0 "at row -1" one step before the first
+    double diagA = diag0;
 #pragma unroll
     for (int s = 0; s < RL + NC - 1; ++s) {
         double out[NC];
@@ -591,13 +595,23 @@ __device__ __forceinline__ void dtw_lane_cols(double (&D)[RL], uint32_t (&acc)[R
     }
 }
 
+// Direction words of the lane path: one word = 16 columns x 2 bits of one row.  They are stored in blocks of
+// (2 column groups x 4 rows) = 32 bytes, so that the backtrack — a chain of dependent L2 reads that walks up and to the
+// left — finds the neighbouring rows and the previous column group of its position in the sector it already holds.
+template <int TR>
+__host__ __device__ __forceinline__ int64_t dtw_lane_dir_index(int g16, int row)
+{
+    return (((int64_t)(g16 >> 1) * (TR / 4) + (row >> 2)) << 3) + ((g16 & 1) << 2) + (row & 3);
+}
+
 // G lanes per matrix: lane = band * MPW + matrix, band b owns rows [b RL, (b + 1) RL) and runs b column groups behind
 // band b - 1, whose last row it receives by shuffle once per group (not per cell).
 template <int TR, int NC, int G>
 __global__ void __launch_bounds__(32)
 dtw_lane_kernel(const float* __restrict__ cost, const WtsSegDesc* __restrict__ segs, const int nseg,
-                uint32_t* __restrict__ dir_ws, int32_t* __restrict__ jumps_out)
+                uint32_t* dir_ws, int32_t* __restrict__ jumps_out, const int bt_bytes)
 {
+    // bt_bytes: shared-memory bytes per matrix for the backtrack's copy of the direction words (0 = walk them in L2)
     using Geo = LaneGeo<TR, G>;
     constexpr int MPW = Geo::MPW, RL = Geo::RL, GPT = 8 / NC;   // GPT: column groups per tile
     static_assert(TR % 8 == 0 && TR <= 32 && (G == 1 || G == 2 || G == 4) && TR % G == 0, "rows per matrix: 8, 16, 24 or 32; 1, 2 or 4 bands");
@@ -660,7 +674,7 @@ dtw_lane_kernel(const float* __restrict__ cost, const WtsSegDesc* __restrict__ s
     const double INF = dinf();
 #pragma unroll
     for (int i = 0; i < RL; ++i) { D[i] = INF; acc[i] = 0; }
-    uint32_t* dirs = dir_ws + (mine ? sd.dir_off : 0) + band * RL;   // word of (16-column group g, row i): [g * TR + i]
+    uint32_t* dirs = dir_ws + (mine ? sd.dir_off : 0);       // word of (16-column group g, row i): dtw_lane_dir_index
     const int ngroups16 = (F + 15) >> 4;
     const uint32_t row_a = stage_a + (uint32_t)(band * RL) * Geo::ROW_BYTES + (uint32_t)mi * 16;
     double last[NC], plast = INF;                            // this band's last row: previous group, and its last column before
@@ -668,6 +682,9 @@ dtw_lane_kernel(const float* __restrict__ cost, const WtsSegDesc* __restrict__ s
     for (int c = 0; c < NC; ++c) last[c] = INF;
 
     const int nsteps = ntile * GPT + (G - 1);                // band b handles column group (step - b)
+    double nb[NC], nd = INF;                                 // the band above's last row, shuffled at the end of the previous step
+#pragma unroll
+    for (int c = 0; c < NC; ++c) nb[c] = INF;
     issue_tile(0);
 #pragma unroll 1
     for (int gs = 0; gs < nsteps; ++gs) {
@@ -676,32 +693,25 @@ dtw_lane_kernel(const float* __restrict__ cost, const WtsSegDesc* __restrict__ s
             cp_async_wait<0>();                              // tile t has landed (this lane's copies)
             __syncwarp();                                    // ... and everybody's
         }
+        const int mg = gs - band;                            // this lane's column group
+        const int mgc = max(mg, 0);
+        const int j = NC * mgc;
+        const int tm = mgc / GPT, pm = mgc % GPT;
+        const uint32_t sh = 2u * (uint32_t)(j & 15);
+        float lv[RL][NC];                                    // local costs of the group: loaded first, consumed after the copies below
+        dtw_lane_load<RL, NC, Geo::ROW_BYTES>(lv, row_a + (uint32_t)(tm & 1) * Geo::SLOT_BYTES +
+                                                      (uint32_t)((NC * pm) >> 2) * Geo::CHUNK_BYTES + (uint32_t)((NC * pm) & 3) * 4);
         if (p == G - 1) {
             // the slot of tile t + 1 held tile t - 1, which the last band read until the previous step
             if (G > 1) __syncwarp();
             issue_tile(t + 1);
         }
-        // what the band above produced in its previous step = this band's boundary for the group it handles now
         double bnd[NC], diag0;
-        if (G > 1) {
 #pragma unroll
-            for (int c = 0; c < NC; ++c) bnd[c] = __shfl_up_sync(FULL_MASK, last[c], MPW);
-            diag0 = __shfl_up_sync(FULL_MASK, plast, MPW);
-        }
-        const int mg = gs - band;                            // this lane's column group
-        if (G == 1 || band == 0) {
-#pragma unroll
-            for (int c = 0; c < NC; ++c) bnd[c] = INF;
-            diag0 = (mg == 0) ? 0.0 : INF;
-        }
-        const int mgc = max(mg, 0);
-        const int j = NC * mgc;
-        const int tm = mgc / GPT, pm = mgc % GPT;
-        const uint32_t sh = 2u * (uint32_t)(j & 15);
-        const uint32_t ld = row_a + (uint32_t)(tm & 1) * Geo::SLOT_BYTES + (uint32_t)((NC * pm) >> 2) * Geo::CHUNK_BYTES +
-                            (uint32_t)((NC * pm) & 3) * 4;
+        for (int c = 0; c < NC; ++c) bnd[c] = (G == 1 || band == 0) ? INF : nb[c];
+        diag0 = (G == 1 || band == 0) ? ((mg == 0) ? 0.0 : INF) : nd;
         plast = last[NC - 1];
-        dtw_lane_cols<RL, NC, Geo::ROW_BYTES>(D, acc, ld, diag0, bnd, last, 1u << sh, 2u << sh);
+        dtw_lane_cols<RL, NC>(D, acc, lv, diag0, bnd, last, 1u << sh, 2u << sh);
         if (G > 1 && mg < 0) {                               // a band that has not started yet: undo the step
 #pragma unroll
             for (int i = 0; i < RL; ++i) { D[i] = INF; acc[i] = 0; }
@@ -709,17 +719,22 @@ dtw_lane_kernel(const float* __restrict__ cost, const WtsSegDesc* __restrict__ s
             for (int c = 0; c < NC; ++c) last[c] = INF;
             plast = INF;
         }
+        if (G > 1) {                                         // hand the last row down for the next step (off its critical path)
+#pragma unroll
+            for (int c = 0; c < NC; ++c) nb[c] = __shfl_up_sync(FULL_MASK, last[c], MPW);
+            nd = __shfl_up_sync(FULL_MASK, plast, MPW);
+        }
         if (mg >= 0 && ((j + NC) & 15) == 0) {               // a 16-column direction group is complete
             const int g16 = j >> 4;
             if (g16 < ngroups16) {
-                uint32_t* dst = dirs + (int64_t)g16 * TR;
                 if (RL % 4 == 0) {
 #pragma unroll
                     for (int q = 0; q < RL / 4; ++q)
-                        reinterpret_cast<uint4*>(dst)[q] = make_uint4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+                        *reinterpret_cast<uint4*>(dirs + dtw_lane_dir_index<TR>(g16, band * RL + 4 * q)) =
+                            make_uint4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
                 } else {
 #pragma unroll
-                    for (int q = 0; q < RL; ++q) dst[q] = acc[q];
+                    for (int q = 0; q < RL; ++q) dirs[dtw_lane_dir_index<TR>(g16, band * RL + q)] = acc[q];
                 }
             }
 #pragma unroll
@@ -731,31 +746,51 @@ dtw_lane_kernel(const float* __restrict__ cost, const WtsSegDesc* __restrict__ s
         if ((jend & 15) != 0) {
             const int g16 = jend >> 4;
             if (g16 < ngroups16) {
-                uint32_t* dst = dirs + (int64_t)g16 * TR;
 #pragma unroll
-                for (int q = 0; q < RL; ++q) dst[q] = acc[q];
+                for (int q = 0; q < RL; ++q) dirs[dtw_lane_dir_index<TR>(g16, band * RL + q)] = acc[q];
             }
         }
     }
     cp_async_wait<0>();
-    __syncwarp();                                            // direction words of all bands are visible to band 0
+    __syncwarp();                                            // direction words of all bands are visible to the whole warp
+
+    // The backtrack is a chain of dependent reads.  When the batch's direction words fit the (now idle) staging
+    // buffers, the warp first copies them back from L2 in one pipelined sweep and walks them in shared memory.
+    const int dir_bytes = ((ngroups16 + 1) >> 1) * (TR / 4) * 32;
+    const bool in_smem = bt_bytes > 0 && __all_sync(FULL_MASK, !mine || dir_bytes <= bt_bytes);
+    if (in_smem) {
+#pragma unroll 1
+        for (int m = 0; m < MPW; ++m) {                      // lane m = band 0 of matrix m
+            const unsigned long long src = __shfl_sync(FULL_MASK, (unsigned long long)(uintptr_t)dirs, m);
+            const int nch = __shfl_sync(FULL_MASK, mine ? dir_bytes >> 4 : 0, m);
+            for (int c = lane; c < nch; c += 32)
+                cp_async_cg16_l2(stage_a + (uint32_t)(m * bt_bytes + 16 * c), reinterpret_cast<const char*>((uintptr_t)src) + 16 * c);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
+    }
     if (!mine || band != 0) return;
 
     // backtrack on this lane's matrix: one step per token row (T.py:1648-1652)
-    const uint32_t* dm = dir_ws + sd.dir_off;
+    const uint32_t* dm = in_smem ? reinterpret_cast<const uint32_t*>(smem_raw + Geo::TABLE_BYTES + mi * bt_bytes) : dirs;
     int32_t* jumps = jumps_out + sd.jumps_off;
     int i = T - 1, j = F - 1;
     jumps[T] = F - 1;
-    uint4 cw = make_uint4(0, 0, 0, 0);                       // the words of four consecutive rows of one column group: one
-    int cg = -1, cq = -1;                                    // 16-byte load serves the moves up inside the group
+    uint4 ce = make_uint4(0, 0, 0, 0), co = ce;              // the 32-byte block (2 column groups x 4 rows) the walk is in
+    int ck = -1;
     while (i > 0) {
         int g = j >> 4, pos = j & 15, kf = 0;
         uint32_t x = 0;
         while (true) {
-            if (g != cg || (i >> 2) != cq) {
-                cg = g; cq = i >> 2;
-                cw = __ldcg(reinterpret_cast<const uint4*>(dm + (int64_t)g * TR + 4 * cq));
+            const int key = (g >> 1) * (TR / 4) + (i >> 2);
+            if (key != ck) {
+                ck = key;
+                const uint4* blk = reinterpret_cast<const uint4*>(dm + ((int64_t)key << 3));
+                if (in_smem) { ce = blk[0]; co = blk[1]; }
+                else { ce = __ldcg(blk); co = __ldcg(blk + 1); }
             }
+            const uint4 cw = (g & 1) ? co : ce;
             x = (i & 2) ? ((i & 1) ? cw.w : cw.z) : ((i & 1) ? cw.y : cw.x);
             const uint32_t msk = dtw_nonleft_mask(x) & (0xffffffffu >> (30 - 2 * pos));
             if (msk) { kf = (31 - __clz(msk)) >> 1; break; }
@@ -866,12 +901,28 @@ extern "C" int wts_dtw_batch_sized(const void* d_cost, int32_t cost_is_f64, cons
 #define WTS_LAUNCH_LANE(TR_, NC_, G_)                                                                                     \
             do {                                                                                                          \
                 constexpr int mpw = LaneGeo<TR_, G_>::MPW;                                                                \
+                const int warps = (nseg + mpw - 1) / mpw, per_sm = (warps + n_sm - 1) / n_sm;                             \
+                /* shared memory a warp may take without lowering the number of resident warps the batch needs */        \
+                const int room = per_sm > 0 ? ((232448 / per_sm - 1024) & ~127) : 0;                                      \
+                int smem_l = (int)LaneGeo<TR_, G_>::SMEM, bt = 0;                                                         \
+                if (max_F > 0 && bt_smem) {                                                                               \
+                    const int need = (((max_F + 15) / 16 + 1) / 2) * (TR_ / 4) * 32;                                      \
+                    const int tot = (int)LaneGeo<TR_, G_>::TABLE_BYTES + mpw * need;                                      \
+                    if (tot <= 232448 - 1024 && (tot <= smem_l || tot <= room)) { bt = need; if (tot > smem_l) smem_l = tot; } \
+                }                                                                                                         \
                 WTS_CUDA_CHECK(cudaFuncSetAttribute(dtw_lane_kernel<TR_, NC_, G_>,                                        \
-                                                    cudaFuncAttributeMaxDynamicSharedMemorySize,                         \
-                                                    (int)LaneGeo<TR_, G_>::SMEM));                                        \
-                dtw_lane_kernel<TR_, NC_, G_><<<(nseg + mpw - 1) / mpw, 32, LaneGeo<TR_, G_>::SMEM, st>>>(                \
-                    (const float*)d_cost, d_segs, nseg, d_dir_ws, d_jumps);                                               \
+                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, smem_l));                \
+                dtw_lane_kernel<TR_, NC_, G_><<<warps, 32, smem_l, st>>>((const float*)d_cost, d_segs, nseg, d_dir_ws,    \
+                                                                         d_jumps, bt);                                    \
             } while (0)
+            static int n_sm = 0;
+            if (n_sm == 0) {
+                int dev = 0;
+                WTS_CUDA_CHECK(cudaGetDevice(&dev));
+                WTS_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+            }
+            const char* bt_env = getenv("WTS_DTW_LANE_BT_SMEM");   // 0: the backtrack walks the direction words in L2
+            const int bt_smem = bt_env ? atoi(bt_env) : 1;
             // WTS_DTW_LANE_NC: columns advanced together per lane (2 or 4 independent chains); WTS_DTW_LANE_G: lanes
             // (row bands) per matrix, 1, 2 or 4 — more bands = more warps per scheduler for the same work
             const char* nc_env = getenv("WTS_DTW_LANE_NC");
