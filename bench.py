@@ -121,11 +121,22 @@ def bytes_prep(N, T, F):
     return 4 * N * T * F + 4 * T * F
 
 
+def dtw_traffic(kernel):
+    """dram read + write bytes of one launch from the committed ncu capture (profiles/roofline_traffic.json), or None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))[kernel]
+        return int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
+    except Exception:                                          # noqa: BLE001
+        return None
+
+
 def dtw_kernel_name(nseg, T):
     """Which DTW kernel wts_dtw_batch_sized picks for a batch of nseg single-strip matrices (csrc/dtw.cu)."""
     lane_min = int(os.environ.get("WTS_DTW_LANE_MIN", "8192"))
     if lane_min > 0 and nseg >= lane_min and T <= 32:
-        return "dtw_lane_kernel<%d>" % (8 if T <= 8 else 16 if T <= 16 else 24 if T <= 24 else 32)
+        g = int(os.environ.get("WTS_DTW_LANE_G", "2"))
+        nc = 2 if g == 4 else int(os.environ.get("WTS_DTW_LANE_NC", "4"))
+        return "dtw_lane_kernel<%d,%d,%d>" % (8 if T <= 8 else 16 if T <= 16 else 24 if T <= 24 else 32, nc, g)
     return "dtw_small_kernel<32,1>" if T <= 31 else "dtw_warp_kernel<float>"
 
 
@@ -636,7 +647,8 @@ def main():
                     al = run_align(args, rank, world)
                     line["dtw_roofline"] = {
                         "bound": "hbm", "achieved": al["dtw_gbs"], "peak": al["peaks"]["hbm_gbs"], "unit": "GB/s",
-                        "frac": al["dtw_gbs"] / al["peaks"]["hbm_gbs"], "traffic": None,
+                        "frac": al["dtw_gbs"] / al["peaks"]["hbm_gbs"], "traffic": dtw_traffic(dtw_kernel_name(args.align_batch, args.align_T))
+                        if (args.align_batch, args.align_T, args.align_F) == (16384, 24, 300) else None,
                         "kernel": dtw_kernel_name(args.align_batch, args.align_T), "ms": al["ms_dtw"], "prep_gbs": al["prep_gbs"], "prep_ms": al["ms_prep"],
                         "workload": f"{args.align_batch} segments, T={args.align_T}, F={args.align_F}, N=10 heads"}
                 except Exception as err:                                   # noqa: BLE001
@@ -669,7 +681,10 @@ def main():
                 "config": {"workload": f"align: {args.align_batch} segments/GPU, T={args.align_T}, F={args.align_F}, N=10 heads",
                            "l2": "inputs (qk %.1f GB) larger than L2" % (args.align_batch * 10 * args.align_T * 1500 * 4 / 1e9)},
                 "roofline": {"bound": "hbm", "achieved": res["dtw_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                             "frac": res["dtw_gbs"] / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                             "frac": res["dtw_gbs"] / peaks["hbm_gbs"],
+                             "traffic": dtw_traffic(dtw_kernel_name(args.align_batch, args.align_T))
+                             if (args.align_batch, args.align_T, args.align_F) == (16384, 24, 300) else None,
+                             "peak_source": peaks["source"],
                              "kernel": dtw_kernel_name(args.align_batch, args.align_T), "ms": res["ms_dtw"]},
                 "prep": {"gbs": res["prep_gbs"], "ms": res["ms_prep"]},
                 "e2e": {"value": res["e2e_segments_per_s"], "unit": "segments/s", "h2d_bytes_per_step": res["h2d"],
