@@ -562,13 +562,10 @@ __device__ __forceinline__ void dtw_lane_load(float (&lv)[RL][NC], const uint32_
     }
 }
 
-template <int RL, int NC, typename Hook>
+template <int RL, int NC>
 __device__ __forceinline__ void dtw_lane_cols(double (&D)[RL], uint32_t (&acc)[RL], const float (&lv)[RL][NC], const double diag0,
-                                              const double (&bnd)[NC], double (&last)[NC], const uint32_t one, const uint32_t two,
-                                              Hook&& hook)
+                                              const double (&bnd)[NC], double (&last)[NC], const uint32_t one, const uint32_t two)
 {
-    // hook(s): called once per skew step with the (compile-time) step index — the kernel spreads the next tile's copies
-    // over the steps, so that their address arithmetic and LSU-queue waits sit between chain instructions
     static_assert(NC == 2 || NC == 4, "two or four columns per group");
     const double INF = dinf();
     double up[NC], h1[NC], h2[NC];
@@ -595,7 +592,6 @@ __device__ __forceinline__ void dtw_lane_cols(double (&D)[RL], uint32_t (&acc)[R
         }
 #pragma unroll
         for (int c = 0; c < NC; ++c) { h2[c] = h1[c]; h1[c] = out[c]; }
-        hook(s);
     }
 }
 
@@ -613,10 +609,9 @@ __host__ __device__ __forceinline__ int64_t dtw_lane_dir_index(int g16, int row)
 template <int TR, int NC, int G>
 __global__ void __launch_bounds__(32)
 dtw_lane_kernel(const float* __restrict__ cost, const WtsSegDesc* __restrict__ segs, const int nseg,
-                uint32_t* dir_ws, int32_t* __restrict__ jumps_out, const int bt_bytes, const int spread)
+                uint32_t* dir_ws, int32_t* __restrict__ jumps_out, const int bt_bytes)
 {
     // bt_bytes: shared-memory bytes per matrix for the backtrack's copy of the direction words (0 = walk them in L2)
-    // spread: issue a tile's copies between the chain steps instead of back to back
     using Geo = LaneGeo<TR, G>;
     constexpr int MPW = Geo::MPW, RL = Geo::RL, GPT = 8 / NC;   // GPT: column groups per tile
     static_assert(TR % 8 == 0 && TR <= 32 && (G == 1 || G == 2 || G == 4) && TR % G == 0, "rows per matrix: 8, 16, 24 or 32; 1, 2 or 4 bands");
@@ -706,39 +701,17 @@ dtw_lane_kernel(const float* __restrict__ cost, const WtsSegDesc* __restrict__ s
         float lv[RL][NC];                                    // local costs of the group: loaded first, consumed after the copies below
         dtw_lane_load<RL, NC, Geo::ROW_BYTES>(lv, row_a + (uint32_t)(tm & 1) * Geo::SLOT_BYTES +
                                                       (uint32_t)((NC * pm) >> 2) * Geo::CHUNK_BYTES + (uint32_t)((NC * pm) & 3) * 4);
-        // The step with p == G - 1 also copies tile t + 1 (its slot held tile t - 1, which the last band read until the
-        // previous step): COPIES_PER_STEP copies after every skew step of the chains (WTS_DTW_LANE_SPREAD=0: all up front).
-        const bool copy_now = p == G - 1;
-        if (copy_now) {
+        if (p == G - 1) {
+            // the slot of tile t + 1 held tile t - 1, which the last band read until the previous step
             if (G > 1) __syncwarp();
-            if (!spread) issue_tile(t + 1);
+            issue_tile(t + 1);
         }
-        const bool copy_spread = copy_now && spread && t + 1 < ntile;
-        const int ccol = 8 * (t + 1) + 4 * half;
-        const uint32_t cdst = dst_lane + (uint32_t)((t + 1) & 1) * Geo::SLOT_BYTES;
-        auto copy_hook = [&](const int s) {
-            constexpr int NCOPY = (MPW / 2) * (TR / 8), NSTEP = RL + NC - 1, CPS = (NCOPY + NSTEP - 1) / NSTEP;
-            if (copy_spread) {
-#pragma unroll
-                for (int e = 0; e < CPS; ++e) {
-                    const int qc = s * CPS + e;
-                    if (qc < NCOPY) {
-                        const int k = qc / (TR / 8), rb = qc % (TR / 8);
-                        const int Pm = (int)(sq[k] & 0xffffu), Tm = (int)(sq[k] >> 16);
-                        if (ccol < Pm && rr + 8 * rb < Tm)
-                            cp_async_cg16_l2(cdst + (uint32_t)k * 32 + (uint32_t)rb * 8 * Geo::ROW_BYTES,
-                                             sp[k] + 8 * (t + 1) + (int64_t)(rb * 8) * Pm);
-                    }
-                }
-            }
-        };
         double bnd[NC], diag0;
 #pragma unroll
         for (int c = 0; c < NC; ++c) bnd[c] = (G == 1 || band == 0) ? INF : nb[c];
         diag0 = (G == 1 || band == 0) ? ((mg == 0) ? 0.0 : INF) : nd;
         plast = last[NC - 1];
-        dtw_lane_cols<RL, NC>(D, acc, lv, diag0, bnd, last, 1u << sh, 2u << sh, copy_hook);
-        if (copy_now && spread) cp_async_commit();           // one group per tile, also when nothing was issued
+        dtw_lane_cols<RL, NC>(D, acc, lv, diag0, bnd, last, 1u << sh, 2u << sh);
         if (G > 1 && mg < 0) {                               // a band that has not started yet: undo the step
 #pragma unroll
             for (int i = 0; i < RL; ++i) { D[i] = INF; acc[i] = 0; }
@@ -940,7 +913,7 @@ extern "C" int wts_dtw_batch_sized(const void* d_cost, int32_t cost_is_f64, cons
                 WTS_CUDA_CHECK(cudaFuncSetAttribute(dtw_lane_kernel<TR_, NC_, G_>,                                        \
                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem_l));                \
                 dtw_lane_kernel<TR_, NC_, G_><<<warps, 32, smem_l, st>>>((const float*)d_cost, d_segs, nseg, d_dir_ws,    \
-                                                                         d_jumps, bt, lane_spread);                       \
+                                                                         d_jumps, bt);                                    \
             } while (0)
             static int n_sm = 0;
             if (n_sm == 0) {
@@ -948,8 +921,6 @@ extern "C" int wts_dtw_batch_sized(const void* d_cost, int32_t cost_is_f64, cons
                 WTS_CUDA_CHECK(cudaGetDevice(&dev));
                 WTS_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
             }
-            const char* sp_env = getenv("WTS_DTW_LANE_SPREAD");
-            const int lane_spread = sp_env ? atoi(sp_env) : 0;
             const char* bt_env = getenv("WTS_DTW_LANE_BT_SMEM");   // 0: the backtrack walks the direction words in L2
             const int bt_smem = bt_env ? atoi(bt_env) : 1;
             // WTS_DTW_LANE_NC: columns advanced together per lane (2 or 4 independent chains); WTS_DTW_LANE_G: lanes
