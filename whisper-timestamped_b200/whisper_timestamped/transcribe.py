@@ -21,6 +21,7 @@ import numpy as np
 from . import vad as V
 from . import words as W
 from .tokenizer import LANGUAGES, TO_LANGUAGE_CODE, get_tokenizer
+from .writers import filtered_keys, flatten, remove_keys, write_csv, write_tsv  # noqa: F401  (T.py:2298-2323, 3183-3199)
 from .windows import (HOP_LENGTH, N_FRAMES, SAMPLE_RATE, WindowRecord, make_decode_setup, plan_window_alignment,
                       slice_window_segments)
 
