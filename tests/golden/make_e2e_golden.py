@@ -10,6 +10,8 @@ model = synthetic_state_dict(DIMS[name], seed), audio = synthetic_speech(duratio
 """
 import importlib.util
 import json
+import contextlib
+import io
 import logging
 import os
 import sys
@@ -78,6 +80,11 @@ CASES = {
                                                          "naive_approach": True, "temperature": 0.0}),
     # explicit-list VAD: speech spans glued, times mapped back, `speech_activity` reported
     "tiny_vad_list": ("tiny", {}, (70.0, 19), {"language": "en", "vad": [(2.0, 21.5), (30.25, 52.0), (58.0, 66.4)]}),
+    # stdout of `verbose=True` (T.py:323, 346, 817-820, 844-846, 1304): detection lines + one line per word, for the one-pass
+    # strategy, the two-pass strategy and a VAD list (times printed after the mapping back to the original audio)
+    "tiny_verbose_detect": ("tiny", {}, (35.0, 13), {"verbose": True}),
+    "tiny_verbose_naive": ("tiny", {}, (45.0, 28), {"language": "en", "naive_approach": True, "temperature": 0.0, "verbose": True}),
+    "tiny_verbose_vad": ("tiny", {}, (70.0, 19), {"verbose": True, "vad": [(2.0, 21.5), (30.25, 52.0), (58.0, 66.4)]}),
     # ---- the configurations bench.py measures (BASELINE.json configs 2-4), at their real dimensions
     # large-v3 with the bench recipe, sequential (two windows: the second-round / prompt carry-over path)
     "large_v3_45s": ("large-v3", BENCH_KW, (45.0, 31), {"language": "en"}),
@@ -135,10 +142,13 @@ def run_reference(model, audio, **kw):
     cap = _Capture()
     lg = logging.getLogger("whisper_timestamped")
     lg.addHandler(cap)
+    out = io.StringIO()
     try:
-        res = ref.transcribe(model, audio, **kw)
+        with contextlib.redirect_stdout(out):
+            res = ref.transcribe(model, audio, **kw)
     finally:
         lg.removeHandler(cap)
+    run_reference.stdout = out.getvalue()       # what the reference (and upstream under it) printed: pinned for `verbose`
     return to_py(res), cap.messages
 
 
@@ -182,6 +192,8 @@ def main():
         out = {"case": case, "model": mname, "model_seed": 1234, "model_kwargs": mkw, "audio": [dur, aseed],
                "transcribe_kwargs": tkw, "reference_version": ref.__version__, "cpu_seconds": round(dt, 2),
                "warnings": warns, "result": res}
+        if tkw.get("verbose") is not None or case == "tiny_detect_lang":
+            out["stdout"] = run_reference.stdout
         with open(os.path.join(HERE, f"e2e_{case}.json"), "w") as f:
             json.dump(out, f, indent=1, ensure_ascii=False)
         nseg = len(res["segments"])

@@ -4,6 +4,8 @@ The device work is done by the test-only OracleEngine (CPU stand-ins), so this r
 and checks that the offline replay of the reference's hook state machine gives the same tokens,
 segments, words, timestamps and confidences."""
 import glob
+import contextlib
+import io
 import json
 import logging
 import os
@@ -64,9 +66,11 @@ def run_case(path, **extra):
     audio = synthetic_speech(*g["audio"])
     if "chunks" in g:
         extra = dict(extra, chunks=g["chunks"])
-    with CaptureWarnings() as cap:
+    out = io.StringIO()
+    with CaptureWarnings() as cap, contextlib.redirect_stdout(out):
         res = transcribe_timestamped(shim, audio, engine=eng, **g["transcribe_kwargs"], **extra)
     res["_warnings"] = cap.messages
+    res["_stdout"] = out.getvalue()
     return g, res
 
 
@@ -130,6 +134,9 @@ def test_host_logic_matches_reference_golden(path):
     compare(res, g["result"])
     if "warnings" in g:
         assert norm_warnings(res["_warnings"]) == norm_warnings(g["warnings"])
+    if "stdout" in g:
+        # what the reference (and upstream under it) prints: `verbose=True` word lines, language-detection lines
+        assert res["_stdout"] == g["stdout"]
 
 
 @pytest.mark.parametrize("path", CHUNK_CASES, ids=[os.path.basename(p)[:-5] for p in CHUNK_CASES])

@@ -66,7 +66,7 @@ def _listed_words(req):
 
 def second_pass(eng, audio, whisper_segments, tokenizer, language, *, use_space, refine_nframes, trust_whisper_timestamps,
                 remove_punctuation_from_words, compute_word_confidence, include_punctuation_in_confidence,
-                min_word_duration=0.0, detect_disfluencies=False):
+                min_word_duration=0.0, detect_disfluencies=False, verbose=False):
     """Adds `confidence` (and possibly corrected `tokens` / `text`) to the segments in place; returns the word list
     (each word carries `idx_segment`)."""
     tok = tokenizer
@@ -198,6 +198,9 @@ def second_pass(eng, audio, whisper_segments, tokenizer, language, *, use_space,
                 else:
                     word["confidence"] = W.round_confidence(0)
             words.append(word)
+            if verbose:                                   # T.py:1304-1305
+                from .transcribe import print_timestamped
+                print_timestamped(word)
 
         if last_token_check is not None:
             check.append(last_token_check)

@@ -14,6 +14,7 @@ Same signature, option checks and return value as the reference
   3. words, confidences and post-processing follow T.py:912-1002 and 313-357.
 """
 import logging
+import sys
 from typing import List, Optional
 
 import numpy as np
@@ -234,7 +235,15 @@ def transcribe_timestamped(
         else:
             language_detected = True
             tok0 = get_tokenizer(True, num_languages=num_languages)
+            # stdout as the reference + upstream produce it (T.py:817-820, 844-846, 1030-1032, 1073-1075; upstream
+            # prints the result whenever verbose is not None).  With a VAD the inner call runs with verbose=False (T.py:286).
+            inner_verbose = verbose if (vad is None or verbose is not True) else False
+            if inner_verbose:
+                print("Detecting language using up to the first 30 seconds. Use `--language` to specify the language")
             language, language_probs = eng.detect_language(mels[0], tok0)
+            if inner_verbose is not None:
+                print(f"Detected language: {LANGUAGES[language].title()}")
+                sys.stdout.flush()
     language = language.lower() if language else language
     if language not in LANGUAGES and language in TO_LANGUAGE_CODE:
         language = TO_LANGUAGE_CODE[language]
@@ -286,7 +295,8 @@ def transcribe_timestamped(
                                    remove_punctuation_from_words=remove_punctuation_from_words,
                                    compute_word_confidence=compute_word_confidence,
                                    include_punctuation_in_confidence=include_punctuation_in_confidence,
-                                   min_word_duration=0.0, detect_disfluencies=detect_disfluencies)
+                                   min_word_duration=0.0, detect_disfluencies=detect_disfluencies,
+                                   verbose=bool(verbose) and vad is None)
         for w in all_words:
             w["_stream"] = 0
         text_parts = [tokenizer.decode(st.all_tokens[st.n_initial_prompt:])]
@@ -487,6 +497,8 @@ def transcribe_timestamped(
                                       min_duration=min_word_duration if trust_whisper_timestamps else 0)
     segs = transcription["segments"]
     for word in words:
+        if verbose and not naive_approach and vad is None:        # T.py:323-324
+            print_timestamped(word)
         word.pop("tokens", None)
         word.pop("tokens_indices", None)
         word.pop("avg_logprob_reliable", None)
@@ -510,6 +522,8 @@ def transcribe_timestamped(
         for seg in segs:
             for word in seg.get("words", []):
                 word["start"], word["end"] = convert_timestamps(word["start"], word["end"])
+                if verbose:                                        # T.py:346-347
+                    print_timestamped(word)
             if refine_whisper_precision and len(seg.get("words", [])):
                 seg["start"] = seg["words"][0]["start"]
                 seg["end"] = seg["words"][-1]["end"]
@@ -519,6 +533,14 @@ def transcribe_timestamped(
     if hasattr(eng, "release"):
         eng.release()
     return transcription
+
+
+def print_timestamped(w):
+    """`[mm:ss.mmm --> mm:ss.mmm] text` on stdout (T.py:1363-1368)."""
+    from .make_subtitles import format_timestamp
+    line = f"[{format_timestamp(w['start'])} --> {format_timestamp(w['end'])}] {w['text']}\n"
+    sys.stdout.write(line.encode(sys.getdefaultencoding(), errors="replace").decode())
+    sys.stdout.flush()
 
 
 transcribe = transcribe_timestamped
