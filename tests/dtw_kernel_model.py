@@ -416,3 +416,43 @@ def model_dtw_lane(cost, TR=24, stale=None, NC=2, G=2):
         i -= 1
     jumps[0] = 0
     return jumps
+
+
+def lane_ring_schedule_ok(NC, G, ntile, early, issue_step=None):
+    """The two-slot staging ring of dtw_lane_kernel<TR, NC, G> as a schedule: tile t (8 columns) goes to slot t & 1; the
+    step with gs % GPT == 0 first waits for every copy issued so far, the step with gs % GPT == G - 1 then issues tile
+    gs // GPT + 1; band b reads column group gs - b in step gs.  `early`: a copy lands the moment it is issued (the
+    earliest it can overwrite its slot) — otherwise only at the next wait (the latest it may).  `issue_step` overrides
+    G - 1 (to show that the rule is tight).  Returns True when every read of every band finds its own tile in the slot."""
+    GPT = 8 // NC
+    assert G - 1 < GPT
+    issue_step = G - 1 if issue_step is None else issue_step
+    slots = {0: None, 1: None}                           # slot -> tile it holds
+    pending = []                                         # issued, not yet landed
+
+    def land():
+        for t in pending:
+            slots[t & 1] = t
+        del pending[:]
+
+    def issue(t):
+        if t < ntile:
+            pending.append(t)
+            if early:
+                land()
+
+    issue(0)
+    for gs in range(ntile * GPT + G - 1):
+        t, p = divmod(gs, GPT)
+        if p == 0 and t < ntile:
+            land()                                       # cp.async.wait_group 0 + __syncwarp
+        # this step's shared-memory reads happen before the copies issued in the same step (program order)
+        for b in range(G):
+            mg = gs - b
+            if 0 <= mg < ntile * GPT:
+                tm = mg // GPT
+                if slots[tm & 1] != tm:
+                    return False
+        if p == issue_step:
+            issue(t + 1)
+    return True

@@ -89,3 +89,16 @@ def test_lane_kernel_model_matches_oracle(TR, NC, G):
         assert np.array_equal(jumps, model_dtw_lane(c, TR=TR, NC=NC, G=G)), (T, F, TR, NC, G)
         if n % 4 == 0:
             assert np.array_equal(jumps, model_dtw_lane(c, TR=TR, NC=NC, G=G, stale=np.float32("nan"))), (T, F, TR, NC, G, "nan")
+
+
+@pytest.mark.parametrize("NC,G", [(2, 1), (4, 1), (2, 2), (4, 2), (2, 4)])
+def test_lane_kernel_staging_ring_schedule(NC, G):
+    """Slot reuse of the lane kernel's two-tile cp.async ring: whether a copy lands at once or only at the next wait, every
+    band reads its own tile (a step's shared-memory reads precede the copies it issues, in program order)."""
+    from dtw_kernel_model import lane_ring_schedule_ok
+    for ntile in (1, 2, 3, 7, 38):
+        assert lane_ring_schedule_ok(NC, G, ntile, early=True), (NC, G, ntile, "early")
+        assert lane_ring_schedule_ok(NC, G, ntile, early=False), (NC, G, ntile, "late")
+    if G > 2:
+        # two steps earlier the last band is still two groups inside the tile being replaced
+        assert not lane_ring_schedule_ok(NC, G, 7, early=True, issue_step=G - 3), (NC, G, "two steps too early must fail")
